@@ -1,0 +1,255 @@
+/* brm.h -- C ABI of the B200 rollout engine for rule-aware multi-agent MCTS.
+ *
+ * This is the drop-in boundary for the simulation phase of
+ * bark-simulator/planner-rules-mcts.  The reference has no FFI: its boundary is the
+ * C++ CRTP plugin mvmcts::StateInterface<Impl> (Execute / GetNumActions / IsTerminal /
+ * GetTerminalReward; /root/reference/src/rules_mcts_state.hpp:43-64,
+ * /root/reference/gridworld/grid_world_state.hpp:28-71) called by
+ * mvmcts::Mvmcts::Search and mvmcts::RandomHeuristic.  Each entry point below cites
+ * the reference interface it replaces; include/brm_state.hpp is the thin C++ adapter
+ * that re-exposes the StateInterface member set on top of this ABI, and
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions, no STL, no torch types.
+ *   - every call returns BRM_OK (0) or a negative error; brm_last_error() gives text.
+ *   - one brm_engine = one GPU + one CUDA stream; calls on one engine are not
+ *     re-entrant (the reference is single-threaded too: a process-global
+ *     std::mt19937, src/behavior_rules_mcts.hpp:154).
+ *   - batches are structure-of-arrays: element [k][i] of an array documented as
+ *     [K][n] lives at k*n + i, i = index of the state / leaf in the batch.
+ *   - `mem` selects where the batch arrays live: BRM_MEM_HOST (copied in and out
+ *     inside the call) or BRM_MEM_DEVICE (pointers valid on the engine's GPU; the
+ *     call only enqueues work on the engine's stream and returns).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     BRM_ERR_NO_DEVICE when no sm_100-class GPU is usable.
+ */
+#ifndef BRM_H_
+#define BRM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRM_ABI_VERSION 1
+
+#define BRM_OK 0
+#define BRM_ERR_INVALID (-1)
+#define BRM_ERR_NO_DEVICE (-2)
+#define BRM_ERR_CUDA (-3)
+#define BRM_ERR_TERMINAL (-4) /* Execute on a terminal state (BARK_EXPECT_TRUE, src/rules_mcts_state.cpp:59) */
+#define BRM_ERR_NOT_CONFIGURED (-5)
+
+#define BRM_MEM_HOST 0
+#define BRM_MEM_DEVICE 1
+
+#define BRM_MAX_APS 4
+#define BRM_MAX_DFA_STATES 16
+#define BRM_MAX_RULES 8
+#define BRM_MAX_REWARD 4
+#define BRM_MAX_ACTIONS 8
+#define BRM_VIOLATION 0xFF
+
+typedef struct brm_engine brm_engine;
+
+/* ---------------------------------------------------------------- engine ---- */
+
+/* Create an engine on CUDA device `device`.  `cuda_stream` may be NULL (the engine
+ * creates its own non-blocking stream) or an existing cudaStream_t to enqueue on
+ * (e.g. the caller's torch stream). */
+int brm_create(int device, void* cuda_stream, brm_engine** out);
+void brm_destroy(brm_engine* e);
+const char* brm_last_error(void);
+int brm_abi_version(void);
+/* Block until everything enqueued on the engine's stream has finished. */
+int brm_synchronize(brm_engine* e);
+/* Number of kernels this engine has launched since creation (bench `gpu_launches`). */
+uint64_t brm_launch_count(const brm_engine* e);
+/* Device-side timing of the rollout kernels on the engine's stream: elapsed ms and
+ * launch count accumulated since the last reset (CUDA events around every rollout
+ * kernel launch; requires brm_set_kernel_timing(e, 1)). */
+int brm_set_kernel_timing(brm_engine* e, int enabled);
+int brm_kernel_time(brm_engine* e, double* ms_total, uint64_t* launches, int reset);
+/* Device properties the roofline needs. */
+int brm_device_info(brm_engine* e, int* sm_count, int* sm_clock_khz, int* cc_major, int* cc_minor);
+
+/* ----------------------------------------------------------- rule monitors --- */
+
+/* A deterministic rule monitor = what ltl::RuleMonitor::MakeRule(formula, weight,
+ * priority) yields (call sites gridworld/base_test_env.cpp:101-102,
+ * test/single_agent_test.cpp:62), compiled on the host to a dense table
+ * (planner_rules_mcts_b200.ltl.compile_rule).  Evaluate()/FinalTransit() contract as
+ * used at src/rules_mcts_state.cpp:158-159,180-181 and
+ * gridworld/grid_world_state.cpp:77-78,147-148:
+ *   letter = sum_k value(ap_k) << (n_aps-1-k); next = trans[state*(1<<n_aps)+letter];
+ *   next == BRM_VIOLATION: reward[priority] += weight, ++violations, state := init_state
+ *   (on_violation 0 = reset) or unchanged (1 = stay); FinalTransit = accepting[state]
+ *   ? 0 : weight.
+ * ap_label[k] is a label kind of the world the rule is used in (BRM_GW_LABEL_* or
+ * BRM_CW_LABEL_*); ap_agent_specific[k] != 0 marks a `label#0` placeholder: the rule
+ * is then instantiated once per other agent (MakeRuleState(others, {}),
+ * gridworld/base_test_env.cpp:129-136, src/behavior_rules_mcts.hpp:295-322). */
+typedef struct {
+  uint8_t n_aps;
+  uint8_t n_states;
+  uint8_t init_state;
+  uint8_t priority;
+  uint8_t on_violation; /* 0 reset to init_state, 1 stay */
+  uint8_t _pad[3];
+  float weight;
+  uint8_t ap_label[BRM_MAX_APS];
+  uint8_t ap_agent_specific[BRM_MAX_APS];
+  uint8_t trans[BRM_MAX_DFA_STATES * (1 << BRM_MAX_APS)]; /* row stride 1<<n_aps */
+  uint8_t accepting[BRM_MAX_DFA_STATES];
+} brm_rule;
+
+/* ---------------------------------------------- rollout policy (RandomHeuristic) */
+
+/* mvmcts::RandomHeuristic settings (src/util.cpp:28-49, gridworld/base_test_env.cpp:50,73):
+ * per rollout, uniform random joint actions until the state is terminal or
+ * max_steps Executes were done; return = sum_k gamma^(k+first_discount_exp) r_k +
+ * gamma^(K+first_discount_exp) GetTerminalReward().
+ * Random actions: Philox4x32-10, key = seed, counter = (rollout_lo, rollout_hi,
+ * step>>2, agent), word step&3, action = mulhi32(word, n_actions(agent)). */
+typedef struct {
+  uint64_t seed;
+  uint64_t rollout_base; /* global id of rollout 0 of leaf 0; leaf l, rollout i has id base + l*rollouts_per_leaf + i */
+  int32_t rollouts_per_leaf;
+  int32_t max_steps;          /* MAX_NUMBER_OF_ITERATIONS, default 30 */
+  double discount_factor;     /* DISCOUNT_FACTOR */
+  int32_t first_discount_exp; /* 1: first step reward weighted by gamma (default), 0: by 1 */
+  int32_t _pad;
+} brm_rollout_params;
+
+/* ------------------------------------------------------------- GridWorld ------ */
+
+#define BRM_GW_MAX_AGENTS 8
+#define BRM_GW_MAX_SLOTS 16 /* rule states per agent */
+
+/* label kinds: the four evaluators of gridworld/base_test_env.cpp:104-117 */
+#define BRM_GW_LABEL_COLLISION 0         /* EvaluatorLabelCollision   "collision"          */
+#define BRM_GW_LABEL_MERGED_E 1          /* EvaluatorLabelEgoRange    "merged_e"           */
+#define BRM_GW_LABEL_MERGED_X 2          /* EvaluatorLabelInRange     "merged_x#j"         */
+#define BRM_GW_LABEL_IN_DIRECT_FRONT_X 3 /* EvaluatorLabelInDirectFront "in_direct_front_x#j" */
+
+/* mirrors GridWorldStateParameter, gridworld/grid_world_state_parameter.h:15-29 */
+typedef struct {
+  int32_t n_agents; /* num_other_agents + 1 */
+  int32_t state_x_length;
+  int32_t ego_goal_reached_position;
+  int32_t terminal_depth;
+  int32_t merging_point;
+  int32_t reward_vec_size;
+  int32_t n_actions;
+  int32_t action_map[BRM_MAX_ACTIONS];
+  double speed_deviation_weight;
+  double acceleration_weight;
+  double potential_weight;
+} brm_gw_params;
+
+/* A batch of n GridWorld states (GridWorldState members, gridworld/grid_world_state.hpp:84-90).
+ *   agents [A][n][4] int32 (x_pos, last_action, lane, init_lane)  -- one 16-byte vector per agent
+ *   term   [n]       bit a = terminal_agents_[a]; bit 0 = IsTerminal()
+ *   depth  [n]       depth_
+ *   q      [A][R][n] automaton state of rule slot r of agent a (R = brm_gw_rules_per_agent)
+ *   viol   [A][R][n] violation counters (may be NULL: not tracked)                        */
+typedef struct {
+  int32_t n;
+  int32_t mem;
+  int32_t* agents;
+  uint8_t* term;
+  int32_t* depth;
+  uint8_t* q;
+  uint32_t* viol;
+} brm_gw_states;
+
+/* Upload scenario constants and the common rules of every agent (rule-state layout
+ * per agent as BaseTestEnv::GetAutomataVec, gridworld/base_test_env.cpp:122-140:
+ * rules in order, agent-specific rules expanded per other agent ascending). */
+int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rules, int32_t n_rules);
+int32_t brm_gw_rules_per_agent(const brm_engine* e);
+
+/* GridWorldState::Execute (gridworld/grid_world_state.cpp:45-90) for n states.
+ *   actions [A][n] uint8 action indices; rewards [A][V][n] double.
+ * Step rewards of agents that were already terminal are 0 (the reference leaves the
+ * caller's slot untouched, :59-62). */
+int brm_gw_execute(brm_engine* e, const brm_gw_states* in, const uint8_t* actions,
+                   brm_gw_states* out, double* rewards);
+/* GridWorldState::GetNumActions (:154-159): out [A][n] */
+int brm_gw_get_num_actions(brm_engine* e, const brm_gw_states* s, uint8_t* out);
+/* GridWorldState::IsTerminal (:153): out [n] */
+int brm_gw_is_terminal(brm_engine* e, const brm_gw_states* s, uint8_t* out);
+/* GridWorldState::GetTerminalReward (:141-152): out [A][V][n] double */
+int brm_gw_terminal_reward(brm_engine* e, const brm_gw_states* s, double* out);
+
+/* The rollout loop of mvmcts::RandomHeuristic over GridWorldState (call site
+ * gridworld/grid_world_env.h:40): rollouts_per_leaf rollouts from each
+ * of leaves->n leaf states, fused on the device (K1 gridworld_rollout).
+ *   returns_sum [n][A][V] double  sum over the leaf's rollouts of the discounted return
+ *   viol_sum    [n][A][R] uint64  sum of final violation counters (NULL: skip)
+ *   agent_steps [n]       uint64  executed agent-steps (non-terminal agents stepped)
+ * Optional per-rollout outputs for parity checks (NULL: skip), rollout index
+ * g = leaf*rollouts_per_leaf + i:
+ *   ro_returns [N][A][V] double, ro_viol [N][A][R] uint8, ro_q [N][A][R] uint8,
+ *   ro_agents [N][A][4] int32, ro_steps [N] int32.
+ * Output arrays live where `leaves->mem` says. */
+typedef struct {
+  double* returns_sum;
+  uint64_t* viol_sum;
+  uint64_t* agent_steps;
+  double* ro_returns;
+  uint8_t* ro_viol;
+  uint8_t* ro_q;
+  int32_t* ro_agents;
+  int32_t* ro_steps;
+} brm_gw_rollout_out;
+
+int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                   const brm_gw_rollout_out* out);
+
+/* Deterministic replay of given action sequences (parity instrument; the closed loop
+ * of gridworld/test_runner.cpp:28-42 without the search): B traces of T steps from
+ * B initial states; a trace stops once its state is terminal.
+ *   actions [B][T][A] uint8
+ *   agents_out [B][T][A][4] int32, term_out [B][T] uint8 (bitmask), q_out [B][T][A][R] uint8,
+ *   viol_out [B][T][A][R] uint32, rewards_out [B][T][A][V] double,
+ *   labels_out [B][T][A][3] uint32 (word 0: bit0 collision, bit1 merged_e; word 1: merged_x
+ *   mask over j; word 2: in_direct_front_x mask over j), term_reward_out [B][A][V] double,
+ *   steps_out [B] int32.   All host or all device according to s0->mem. */
+typedef struct {
+  int32_t* agents_out;
+  uint8_t* term_out;
+  uint8_t* q_out;
+  uint32_t* viol_out;
+  double* rewards_out;
+  uint32_t* labels_out;
+  double* term_reward_out;
+  int32_t* steps_out;
+} brm_gw_trace;
+
+int brm_gw_replay(brm_engine* e, const brm_gw_states* s0, const uint8_t* actions, int32_t T,
+                  const brm_gw_trace* trace);
+
+/* ---------------------------------------------------- root statistics merge ---- */
+
+/* Root-parallel merge (new: the reference has a single tree; what must be summed is
+ * the root's per-agent, per-action visit count and value-vector sum read by
+ * ReturnBestAction / GetEgoIntNode().GetExpectedRewards(), gridworld/grid_world_env.h:33,38).
+ * Fold per-leaf rollout sums into root statistics on the device (K5 root_stats_reduce):
+ *   leaf_first_action [n][A] uint8 : the root joint action each leaf descends from
+ *   returns_sum [n][A][V] double, rollouts_per_leaf
+ *   stats (device or host per `mem`) [A][n_actions][1+V] double : (visits, value sums),
+ *   ACCUMULATED into (zero it first for a fresh decision).
+ * The packed `stats` buffer is what ranks allreduce(sum) over NCCL. */
+int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t n_agents,
+                          int32_t n_actions, int32_t reward_vec_size,
+                          const uint8_t* leaf_first_action, const double* returns_sum,
+                          int32_t rollouts_per_leaf, double* stats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BRM_H_ */

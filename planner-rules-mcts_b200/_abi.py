@@ -1,0 +1,170 @@
+"""ctypes view of the C ABI declared in include/brm.h (libbrm.so).
+
+The library is the product; this module only loads it and declares the argument
+types.  There is no CPU fallback: if libbrm.so is missing the import fails, and every
+compute entry point fails with BRM_ERR_NO_DEVICE when no B200-class GPU is present.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbrm.so")
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_TERMINAL, ERR_NOT_CONFIGURED = 0, -1, -2, -3, -4, -5
+MEM_HOST, MEM_DEVICE = 0, 1
+MAX_APS, MAX_DFA_STATES, MAX_RULES, MAX_REWARD, MAX_ACTIONS = 4, 16, 8, 4, 8
+VIOLATION = 0xFF
+GW_MAX_AGENTS, GW_MAX_SLOTS = 8, 16
+GW_LABEL_COLLISION, GW_LABEL_MERGED_E, GW_LABEL_MERGED_X, GW_LABEL_IN_DIRECT_FRONT_X = 0, 1, 2, 3
+
+
+class BrmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("brm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Rule(C.Structure):
+    _fields_ = [
+        ("n_aps", C.c_uint8), ("n_states", C.c_uint8), ("init_state", C.c_uint8),
+        ("priority", C.c_uint8), ("on_violation", C.c_uint8), ("_pad", C.c_uint8 * 3),
+        ("weight", C.c_float),
+        ("ap_label", C.c_uint8 * MAX_APS),
+        ("ap_agent_specific", C.c_uint8 * MAX_APS),
+        ("trans", C.c_uint8 * (MAX_DFA_STATES * (1 << MAX_APS))),
+        ("accepting", C.c_uint8 * MAX_DFA_STATES),
+    ]
+
+
+class RolloutParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("rollout_base", C.c_uint64),
+        ("rollouts_per_leaf", C.c_int32), ("max_steps", C.c_int32),
+        ("discount_factor", C.c_double),
+        ("first_discount_exp", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class GwParams(C.Structure):
+    _fields_ = [
+        ("n_agents", C.c_int32), ("state_x_length", C.c_int32),
+        ("ego_goal_reached_position", C.c_int32), ("terminal_depth", C.c_int32),
+        ("merging_point", C.c_int32), ("reward_vec_size", C.c_int32),
+        ("n_actions", C.c_int32), ("action_map", C.c_int32 * MAX_ACTIONS),
+        ("speed_deviation_weight", C.c_double), ("acceleration_weight", C.c_double),
+        ("potential_weight", C.c_double),
+    ]
+
+
+class GwStates(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("mem", C.c_int32),
+        ("agents", C.c_void_p), ("term", C.c_void_p), ("depth", C.c_void_p),
+        ("q", C.c_void_p), ("viol", C.c_void_p),
+    ]
+
+
+class GwRolloutOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "returns_sum", "viol_sum", "agent_steps", "ro_returns", "ro_viol", "ro_q", "ro_agents",
+        "ro_steps")]
+
+
+class GwTrace(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "agents_out", "term_out", "q_out", "viol_out", "rewards_out", "labels_out",
+        "term_reward_out", "steps_out")]
+
+
+# every symbol include/brm.h declares (tests/test_abi.py checks the library exports them)
+SYMBOLS = [
+    "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_synchronize",
+    "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
+    "brm_gw_configure", "brm_gw_rules_per_agent", "brm_gw_execute", "brm_gw_get_num_actions",
+    "brm_gw_is_terminal", "brm_gw_terminal_reward", "brm_gw_rollout", "brm_gw_replay",
+    "brm_root_stats_reduce",
+]
+
+_lib = None
+
+
+def load():
+    """Load libbrm.so (built in-tree by __graft_entry__.build()); fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+            "g.build()'); there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u64, dbl = C.c_void_p, C.c_int32, C.c_uint64, C.c_double
+    P = C.POINTER
+    lib.brm_create.argtypes = [C.c_int, vp, P(vp)]
+    lib.brm_destroy.argtypes = [vp]
+    lib.brm_destroy.restype = None
+    lib.brm_last_error.restype = C.c_char_p
+    lib.brm_synchronize.argtypes = [vp]
+    lib.brm_launch_count.argtypes = [vp]
+    lib.brm_launch_count.restype = u64
+    lib.brm_set_kernel_timing.argtypes = [vp, C.c_int]
+    lib.brm_kernel_time.argtypes = [vp, P(dbl), P(u64), C.c_int]
+    lib.brm_device_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int), P(C.c_int)]
+    lib.brm_gw_configure.argtypes = [vp, P(GwParams), P(Rule), i32]
+    lib.brm_gw_rules_per_agent.argtypes = [vp]
+    lib.brm_gw_execute.argtypes = [vp, P(GwStates), vp, P(GwStates), vp]
+    lib.brm_gw_get_num_actions.argtypes = [vp, P(GwStates), vp]
+    lib.brm_gw_is_terminal.argtypes = [vp, P(GwStates), vp]
+    lib.brm_gw_terminal_reward.argtypes = [vp, P(GwStates), vp]
+    lib.brm_gw_rollout.argtypes = [vp, P(GwStates), P(RolloutParams), P(GwRolloutOut)]
+    lib.brm_gw_replay.argtypes = [vp, P(GwStates), vp, i32, P(GwTrace)]
+    lib.brm_root_stats_reduce.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        raise BrmError(rc, load().brm_last_error().decode("utf-8", "replace"))
+
+
+class Engine:
+    """One GPU + one CUDA stream (brm_engine)."""
+
+    def __init__(self, device=0, cuda_stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.brm_create(int(device), C.c_void_p(cuda_stream or 0), C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.brm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self.lib.brm_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.brm_launch_count(self.handle))
+
+    def set_kernel_timing(self, enabled=True):
+        check(self.lib.brm_set_kernel_timing(self.handle, 1 if enabled else 0))
+
+    def kernel_time(self, reset=True):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        check(self.lib.brm_kernel_time(self.handle, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, int(n.value)
+
+    def device_info(self):
+        a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self.lib.brm_device_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(sm_count=a.value, sm_clock_khz=b.value, cc=(c.value, d.value))

@@ -1,0 +1,83 @@
+// Shared host/device declarations of the rollout engine (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "brm.h"
+
+namespace brm {
+
+void set_error(const char* fmt, ...);
+
+#define BRM_CUDA_CHECK(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _err = (expr);                                                        \
+    if (_err != cudaSuccess) {                                                        \
+      ::brm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_err), __FILE__, \
+                       __LINE__);                                                     \
+      return BRM_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define BRM_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::brm::set_error(__VA_ARGS__);      \
+      return BRM_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+// ---- GridWorld scenario blob: staged into shared memory by one TMA bulk copy ----
+struct alignas(16) GwBlob {
+  int32_t A, V, R, n_actions;
+  int32_t merging_point, x_len, terminal_depth, n_rules;
+  int32_t action_map[BRM_MAX_ACTIONS];
+  double w_speed, w_acc;
+  uint8_t slot_rule[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
+  int8_t slot_other[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
+  brm_rule rules[BRM_MAX_RULES];
+  uint8_t _tail[16 - (sizeof(brm_rule) * BRM_MAX_RULES) % 16];
+};
+static_assert(sizeof(GwBlob) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+}  // namespace brm
+
+struct CwScenario;  // cw_kernels.cu
+
+struct brm_engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0, clock_khz = 0, cc_major = 0, cc_minor = 0;
+  uint64_t launches = 0;
+  // kernel timing
+  bool timing = false;
+  std::vector<brm::EventPair> ev_pool;
+  size_t ev_used = 0;
+  double kernel_ms = 0.0;
+  uint64_t timed_launches = 0;
+  // gridworld
+  bool gw_ready = false;
+  brm::GwBlob gw_blob;
+  brm::GwBlob* d_gw_blob = nullptr;
+  // continuous world (cw_engine.cu)
+  void* cw = nullptr;
+  // scratch
+  void* d_ws = nullptr;
+  size_t ws_bytes = 0;
+
+  int ensure_ws(size_t bytes);
+  // timing helpers around the dominant kernels
+  void time_begin();
+  void time_end();
+};

@@ -1,0 +1,302 @@
+// GridWorld host API (include/brm.h, brm_gw_*): scenario upload and the batched
+// StateInterface surface.  Kernels live in gw_kernels.cu.
+#include "common.cuh"
+#include "staging.cuh"
+
+namespace brm {
+int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_rollout_params& rp,
+                      const brm_gw_rollout_out& out);
+int gw_launch_execute(brm_engine* e, const brm_gw_states& in, const uint8_t* actions,
+                      const brm_gw_states& out, double* rewards);
+int gw_launch_query(brm_engine* e, const brm_gw_states& s, uint8_t* num_actions,
+                    uint8_t* is_terminal, double* term_reward);
+int gw_launch_replay(brm_engine* e, const brm_gw_states& s0, const uint8_t* actions, int32_t T,
+                     const brm_gw_trace& tr);
+
+namespace {
+
+int check_ready(const brm_engine* e, const char* fn) {
+  if (!e) {
+    set_error("%s: engine is NULL", fn);
+    return BRM_ERR_INVALID;
+  }
+  if (!e->gw_ready) {
+    set_error("%s: call brm_gw_configure first", fn);
+    return BRM_ERR_NOT_CONFIGURED;
+  }
+  return BRM_OK;
+}
+
+int check_states(const brm_gw_states* s, const char* fn) {
+  BRM_REQUIRE(s != nullptr, "%s: states is NULL", fn);
+  BRM_REQUIRE(s->n > 0, "%s: empty batch (n=%d)", fn, s->n);
+  BRM_REQUIRE(s->agents && s->term && s->depth && s->q, "%s: agents/term/depth/q must be set", fn);
+  BRM_REQUIRE(s->mem == BRM_MEM_HOST || s->mem == BRM_MEM_DEVICE, "%s: bad mem %d", fn, s->mem);
+  return BRM_OK;
+}
+
+int upload_states(Stager& st, const brm_gw_states& h, int A, int R, brm_gw_states* d) {
+  const size_t n = h.n;
+  *d = h;
+  d->mem = BRM_MEM_DEVICE;
+  BRM_TRY(st.in(h.agents, A * n * 4, &d->agents));
+  BRM_TRY(st.in(h.term, n, &d->term));
+  BRM_TRY(st.in(h.depth, n, &d->depth));
+  BRM_TRY(st.in(h.q, A * R * n, &d->q));
+  if (h.viol) BRM_TRY(st.in(h.viol, A * R * n, &d->viol));
+  return BRM_OK;
+}
+
+int alloc_states(Stager& st, const brm_gw_states& like, int A, int R, brm_gw_states* d) {
+  const size_t n = like.n;
+  *d = like;
+  d->mem = BRM_MEM_DEVICE;
+  BRM_TRY(st.alloc(A * n * 4, &d->agents));
+  BRM_TRY(st.alloc(n, &d->term));
+  BRM_TRY(st.alloc(n, &d->depth));
+  BRM_TRY(st.alloc(A * R * n, &d->q));
+  if (like.viol) BRM_TRY(st.alloc(A * R * n, &d->viol, true));
+  return BRM_OK;
+}
+
+int download_states(Stager& st, const brm_gw_states& d, int A, int R, brm_gw_states* h) {
+  const size_t n = h->n;
+  BRM_TRY(st.out(h->agents, d.agents, A * n * 4));
+  BRM_TRY(st.out(h->term, d.term, n));
+  BRM_TRY(st.out(h->depth, d.depth, n));
+  BRM_TRY(st.out(h->q, d.q, A * R * n));
+  if (h->viol) BRM_TRY(st.out(h->viol, d.viol, A * R * n));
+  return BRM_OK;
+}
+
+}  // namespace
+}  // namespace brm
+
+using namespace brm;
+
+extern "C" {
+
+int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rules, int32_t n_rules) {
+  BRM_REQUIRE(e && p, "brm_gw_configure: NULL argument");
+  BRM_REQUIRE(p->n_agents >= 1 && p->n_agents <= BRM_GW_MAX_AGENTS,
+              "brm_gw_configure: n_agents %d not in [1,%d]", p->n_agents, BRM_GW_MAX_AGENTS);
+  BRM_REQUIRE(p->reward_vec_size >= 1 && p->reward_vec_size <= BRM_MAX_REWARD,
+              "brm_gw_configure: reward_vec_size %d not in [1,%d]", p->reward_vec_size, BRM_MAX_REWARD);
+  BRM_REQUIRE(p->n_actions >= 1 && p->n_actions <= BRM_MAX_ACTIONS,
+              "brm_gw_configure: n_actions %d not in [1,%d]", p->n_actions, BRM_MAX_ACTIONS);
+  BRM_REQUIRE(n_rules >= 0 && n_rules <= BRM_MAX_RULES, "brm_gw_configure: n_rules %d not in [0,%d]",
+              n_rules, BRM_MAX_RULES);
+  BRM_REQUIRE(n_rules == 0 || rules, "brm_gw_configure: rules is NULL");
+  GwBlob& B = e->gw_blob;
+  memset(&B, 0, sizeof(B));
+  B.A = p->n_agents;
+  B.V = p->reward_vec_size;
+  B.n_actions = p->n_actions;
+  B.merging_point = p->merging_point;
+  B.x_len = p->state_x_length;
+  B.terminal_depth = p->terminal_depth;
+  B.n_rules = n_rules;
+  for (int k = 0; k < p->n_actions; ++k) B.action_map[k] = p->action_map[k];
+  B.w_speed = p->speed_deviation_weight;
+  B.w_acc = p->acceleration_weight;
+  for (int k = 0; k < n_rules; ++k) {
+    const brm_rule& r = rules[k];
+    BRM_REQUIRE(r.n_aps <= BRM_MAX_APS && r.n_states >= 1 && r.n_states <= BRM_MAX_DFA_STATES,
+                "brm_gw_configure: rule %d has bad sizes (n_aps=%d n_states=%d)", k, r.n_aps, r.n_states);
+    BRM_REQUIRE(r.priority < p->reward_vec_size, "brm_gw_configure: rule %d priority %d >= V", k,
+                r.priority);
+    BRM_REQUIRE(r.init_state < r.n_states, "brm_gw_configure: rule %d init_state out of range", k);
+    for (int a = 0; a < r.n_aps; ++a) {
+      BRM_REQUIRE(r.ap_label[a] <= BRM_GW_LABEL_IN_DIRECT_FRONT_X,
+                  "brm_gw_configure: rule %d AP %d: unknown GridWorld label kind %d", k, a, r.ap_label[a]);
+      const bool per_other = r.ap_label[a] >= BRM_GW_LABEL_MERGED_X;
+      BRM_REQUIRE(per_other == (r.ap_agent_specific[a] != 0),
+                  "brm_gw_configure: rule %d AP %d: label kind %d %s a #0 placeholder", k, a,
+                  r.ap_label[a], per_other ? "needs" : "cannot take");
+    }
+    for (int s = 0; s < r.n_states * (1 << r.n_aps); ++s)
+      BRM_REQUIRE(r.trans[s] == BRM_VIOLATION || r.trans[s] < r.n_states,
+                  "brm_gw_configure: rule %d transition %d out of range", k, s);
+    B.rules[k] = r;
+  }
+  // rule-slot layout per agent (BaseTestEnv::GetAutomataVec, gridworld/base_test_env.cpp:122-140)
+  int R = 0;
+  for (int i = 0; i < B.A; ++i) {
+    int n = 0;
+    for (int k = 0; k < n_rules; ++k) {
+      bool specific = false;
+      for (int a = 0; a < rules[k].n_aps; ++a) specific |= rules[k].ap_agent_specific[a] != 0;
+      if (specific) {
+        for (int j = 0; j < B.A; ++j)
+          if (j != i) {
+            BRM_REQUIRE(n < BRM_GW_MAX_SLOTS, "brm_gw_configure: more than %d rule states per agent",
+                        BRM_GW_MAX_SLOTS);
+            B.slot_rule[i][n] = static_cast<uint8_t>(k);
+            B.slot_other[i][n] = static_cast<int8_t>(j);
+            ++n;
+          }
+      } else {
+        BRM_REQUIRE(n < BRM_GW_MAX_SLOTS, "brm_gw_configure: more than %d rule states per agent",
+                    BRM_GW_MAX_SLOTS);
+        B.slot_rule[i][n] = static_cast<uint8_t>(k);
+        B.slot_other[i][n] = -1;
+        ++n;
+      }
+    }
+    R = n;
+  }
+  B.R = R;
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  if (!e->d_gw_blob) BRM_CUDA_CHECK(cudaMalloc(&e->d_gw_blob, sizeof(GwBlob)));
+  BRM_CUDA_CHECK(cudaMemcpyAsync(e->d_gw_blob, &B, sizeof(GwBlob), cudaMemcpyHostToDevice, e->stream));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->gw_ready = true;
+  return BRM_OK;
+}
+
+int32_t brm_gw_rules_per_agent(const brm_engine* e) { return (e && e->gw_ready) ? e->gw_blob.R : -1; }
+
+int brm_gw_execute(brm_engine* e, const brm_gw_states* in, const uint8_t* actions,
+                   brm_gw_states* out, double* rewards) {
+  BRM_TRY(check_ready(e, "brm_gw_execute"));
+  BRM_TRY(check_states(in, "brm_gw_execute"));
+  BRM_TRY(check_states(out, "brm_gw_execute(out)"));
+  BRM_REQUIRE(actions && rewards, "brm_gw_execute: actions/rewards is NULL");
+  BRM_REQUIRE(in->n == out->n && in->mem == out->mem, "brm_gw_execute: in/out batch mismatch");
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
+  const size_t n = in->n;
+  if (in->mem == BRM_MEM_DEVICE) return gw_launch_execute(e, *in, actions, *out, rewards);
+  // Execute on a terminal state is an error in the reference's BARK-backed state
+  // (src/rules_mcts_state.cpp:59); GridWorldState does not check, neither do we.
+  Stager st(e);
+  brm_gw_states d_in, d_out;
+  uint8_t* d_act;
+  double* d_rew;
+  BRM_TRY(upload_states(st, *in, A, R, &d_in));
+  BRM_TRY(alloc_states(st, *out, A, R, &d_out));
+  BRM_TRY(st.in(actions, A * n, &d_act));
+  BRM_TRY(st.alloc(A * V * n, &d_rew));
+  BRM_TRY(gw_launch_execute(e, d_in, d_act, d_out, d_rew));
+  BRM_TRY(download_states(st, d_out, A, R, out));
+  BRM_TRY(st.out(rewards, d_rew, A * V * n));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRM_OK;
+}
+
+static int gw_query(brm_engine* e, const brm_gw_states* s, uint8_t* num_actions,
+                    uint8_t* is_terminal, double* term_reward, const char* fn) {
+  BRM_TRY(check_ready(e, fn));
+  BRM_TRY(check_states(s, fn));
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
+  const size_t n = s->n;
+  if (s->mem == BRM_MEM_DEVICE) return gw_launch_query(e, *s, num_actions, is_terminal, term_reward);
+  Stager st(e);
+  brm_gw_states d;
+  BRM_TRY(upload_states(st, *s, A, R, &d));
+  uint8_t *d_na = nullptr, *d_it = nullptr;
+  double* d_tr = nullptr;
+  if (num_actions) BRM_TRY(st.alloc(A * n, &d_na));
+  if (is_terminal) BRM_TRY(st.alloc(n, &d_it));
+  if (term_reward) BRM_TRY(st.alloc(A * V * n, &d_tr));
+  BRM_TRY(gw_launch_query(e, d, d_na, d_it, d_tr));
+  if (num_actions) BRM_TRY(st.out(num_actions, d_na, A * n));
+  if (is_terminal) BRM_TRY(st.out(is_terminal, d_it, n));
+  if (term_reward) BRM_TRY(st.out(term_reward, d_tr, A * V * n));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRM_OK;
+}
+
+int brm_gw_get_num_actions(brm_engine* e, const brm_gw_states* s, uint8_t* out) {
+  BRM_REQUIRE(out, "brm_gw_get_num_actions: out is NULL");
+  return gw_query(e, s, out, nullptr, nullptr, "brm_gw_get_num_actions");
+}
+int brm_gw_is_terminal(brm_engine* e, const brm_gw_states* s, uint8_t* out) {
+  BRM_REQUIRE(out, "brm_gw_is_terminal: out is NULL");
+  return gw_query(e, s, nullptr, out, nullptr, "brm_gw_is_terminal");
+}
+int brm_gw_terminal_reward(brm_engine* e, const brm_gw_states* s, double* out) {
+  BRM_REQUIRE(out, "brm_gw_terminal_reward: out is NULL");
+  return gw_query(e, s, nullptr, nullptr, out, "brm_gw_terminal_reward");
+}
+
+int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                   const brm_gw_rollout_out* out) {
+  BRM_TRY(check_ready(e, "brm_gw_rollout"));
+  BRM_TRY(check_states(leaves, "brm_gw_rollout"));
+  BRM_REQUIRE(rp && out, "brm_gw_rollout: NULL argument");
+  BRM_REQUIRE(out->returns_sum, "brm_gw_rollout: returns_sum is required");
+  BRM_REQUIRE(rp->rollouts_per_leaf >= 1, "brm_gw_rollout: rollouts_per_leaf must be >= 1");
+  BRM_REQUIRE(rp->max_steps >= 0 && rp->max_steps <= 255, "brm_gw_rollout: max_steps %d not in [0,255]",
+              rp->max_steps);
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
+  if (leaves->mem == BRM_MEM_DEVICE) return gw_launch_rollout(e, *leaves, *rp, *out);
+  const size_t L = leaves->n;
+  const size_t N = L * static_cast<size_t>(rp->rollouts_per_leaf);
+  Stager st(e);
+  brm_gw_states d;
+  BRM_TRY(upload_states(st, *leaves, A, R, &d));
+  brm_gw_rollout_out o = {};
+  BRM_TRY(st.alloc(L * A * V, &o.returns_sum));
+  if (out->viol_sum) BRM_TRY(st.alloc(L * A * R, &o.viol_sum));
+  if (out->agent_steps) BRM_TRY(st.alloc(L, &o.agent_steps));
+  if (out->ro_returns) BRM_TRY(st.alloc(N * A * V, &o.ro_returns));
+  if (out->ro_viol) BRM_TRY(st.alloc(N * A * R, &o.ro_viol));
+  if (out->ro_q) BRM_TRY(st.alloc(N * A * R, &o.ro_q));
+  if (out->ro_agents) BRM_TRY(st.alloc(N * A * 4, &o.ro_agents));
+  if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
+  BRM_TRY(gw_launch_rollout(e, d, *rp, o));
+  BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * A * V));
+  if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * A * R));
+  if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));
+  if (out->ro_returns) BRM_TRY(st.out(out->ro_returns, o.ro_returns, N * A * V));
+  if (out->ro_viol) BRM_TRY(st.out(out->ro_viol, o.ro_viol, N * A * R));
+  if (out->ro_q) BRM_TRY(st.out(out->ro_q, o.ro_q, N * A * R));
+  if (out->ro_agents) BRM_TRY(st.out(out->ro_agents, o.ro_agents, N * A * 4));
+  if (out->ro_steps) BRM_TRY(st.out(out->ro_steps, o.ro_steps, N));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRM_OK;
+}
+
+int brm_gw_replay(brm_engine* e, const brm_gw_states* s0, const uint8_t* actions, int32_t T,
+                  const brm_gw_trace* tr) {
+  BRM_TRY(check_ready(e, "brm_gw_replay"));
+  BRM_TRY(check_states(s0, "brm_gw_replay"));
+  BRM_REQUIRE(actions && tr && T >= 1, "brm_gw_replay: bad arguments");
+  BRM_REQUIRE(tr->agents_out && tr->term_out && tr->q_out && tr->viol_out && tr->rewards_out &&
+                  tr->labels_out && tr->term_reward_out && tr->steps_out,
+              "brm_gw_replay: every trace array is required");
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
+  if (s0->mem == BRM_MEM_DEVICE) return gw_launch_replay(e, *s0, actions, T, *tr);
+  const size_t B = s0->n, BT = B * static_cast<size_t>(T);
+  Stager st(e);
+  brm_gw_states d;
+  BRM_TRY(upload_states(st, *s0, A, R, &d));
+  uint8_t* d_act;
+  BRM_TRY(st.in(actions, BT * A, &d_act));
+  brm_gw_trace o = {};
+  BRM_TRY(st.alloc(BT * A * 4, &o.agents_out, true));
+  BRM_TRY(st.alloc(BT, &o.term_out, true));
+  BRM_TRY(st.alloc(BT * A * R, &o.q_out, true));
+  BRM_TRY(st.alloc(BT * A * R, &o.viol_out, true));
+  BRM_TRY(st.alloc(BT * A * V, &o.rewards_out, true));
+  BRM_TRY(st.alloc(BT * A * 3, &o.labels_out, true));
+  BRM_TRY(st.alloc(B * A * V, &o.term_reward_out, true));
+  BRM_TRY(st.alloc(B, &o.steps_out, true));
+  BRM_TRY(gw_launch_replay(e, d, d_act, T, o));
+  BRM_TRY(st.out(tr->agents_out, o.agents_out, BT * A * 4));
+  BRM_TRY(st.out(tr->term_out, o.term_out, BT));
+  BRM_TRY(st.out(tr->q_out, o.q_out, BT * A * R));
+  BRM_TRY(st.out(tr->viol_out, o.viol_out, BT * A * R));
+  BRM_TRY(st.out(tr->rewards_out, o.rewards_out, BT * A * V));
+  BRM_TRY(st.out(tr->labels_out, o.labels_out, BT * A * 3));
+  BRM_TRY(st.out(tr->term_reward_out, o.term_reward_out, B * A * V));
+  BRM_TRY(st.out(tr->steps_out, o.steps_out, B));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,488 @@
+// GridWorld kernels (sm_100a):
+//   K1 gw_rollout_kernel   fused random rollouts (mvmcts::RandomHeuristic over
+//                          GridWorldState::Execute), one thread = one rollout, all
+//                          agents in registers, automaton tables in shared memory.
+//   K2 gw_execute_kernel   one Execute for n states, SoA in / SoA out.
+//   K6 gw_replay_kernel    replay of given action sequences with a full trace.
+// The scenario blob (parameters, rule-slot layout, transition tables) is staged into
+// shared memory with one TMA bulk copy per CTA.
+#include "common.cuh"
+#include "gw_device.cuh"
+#include "philox.cuh"
+#include "tma.cuh"
+
+namespace brm {
+
+namespace {
+
+constexpr int kRolloutThreads = 256;
+
+template <int A>
+__device__ __forceinline__ void gw_load_state(const brm_gw_states& S, int R, int64_t i,
+                                              GwRegs<A>& s) {
+  const int4* ag = reinterpret_cast<const int4*>(S.agents);
+  const int64_t n = S.n;
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    const int4 v = ag[a * n + i];
+    s.x[a] = v.x;
+    s.last[a] = v.y;
+    s.lane[a] = v.z;
+    s.init_lane[a] = v.w;
+    uint64_t q = 0;
+    for (int r = 0; r < R; ++r)
+      q |= static_cast<uint64_t>(S.q[(static_cast<int64_t>(a) * R + r) * n + i] & 15u) << (4 * r);
+    s.q[a] = q;
+  }
+  s.term = S.term[i];
+  s.depth = S.depth[i];
+}
+
+// ------------------------------------------------------------------ K1 rollout
+struct GwRolloutArgs {
+  brm_gw_states leaves;
+  brm_gw_rollout_out out;   // final (device) outputs; returns_sum produced by the reduce kernel
+  double* part_returns;     // [units][A*V] warp partial sums
+  const GwBlob* blob;
+  uint64_t seed, rollout_base;
+  int32_t rollouts_per_leaf, max_steps, first_exp;
+  int32_t warps_per_leaf;
+  int64_t units;            // leaves * warps_per_leaf
+  double gamma;
+};
+
+template <int A>
+__global__ void __launch_bounds__(kRolloutThreads)
+gw_rollout_kernel(const GwRolloutArgs args) {
+  __shared__ GwBlob sB;
+  __shared__ __align__(8) uint64_t bar;
+  stage_blob(&sB, args.blob, static_cast<uint32_t>(sizeof(GwBlob)), &bar, 0, true);
+  const GwBlob& B = sB;
+  const int V = B.V, R = B.R;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int n_act = B.n_actions;
+
+  for (int64_t unit = warp0; unit < args.units; unit += n_warps) {
+    const int64_t leaf = unit / args.warps_per_leaf;
+    const int chunk = static_cast<int>(unit - leaf * args.warps_per_leaf);
+    const int idx = chunk * 32 + lane;  // rollout index within the leaf
+    const bool active = idx < args.rollouts_per_leaf;
+    const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
+    const uint64_t rid = args.rollout_base + local;
+
+    GwRegs<A> s;
+    gw_load_state<A>(args.leaves, R, leaf, s);
+    double acc[A][BRM_MAX_REWARD];
+    uint64_t viol[A][2];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      viol[a][0] = viol[a][1] = 0;
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[a][v] = 0.0;
+    }
+    double disc = args.first_exp ? args.gamma : 1.0;
+    uint32_t agent_steps = 0;
+    int k = 0;
+    if (active) {
+      Philox4 blk[A];
+      while (!(s.term & 1u) && k < args.max_steps) {
+        uint32_t act[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          if ((k & 3) == 0) blk[a] = action_block(args.seed, rid, k, a);
+          const bool t = (s.term >> a) & 1u;
+          act[a] = draw_action(pick_word(blk[a], k), t ? 1u : static_cast<uint32_t>(n_act));
+          agent_steps += t ? 0u : 1u;
+        }
+        gw_step<A>(
+            B, s, act,
+            [&](int i, const double(&r)[BRM_MAX_REWARD]) {
+#pragma unroll
+              for (int v = 0; v < BRM_MAX_REWARD; ++v)
+                acc[i][v] = __dadd_rn(acc[i][v], __dmul_rn(disc, r[v]));
+            },
+            [&](int i, int sl) { viol[i][sl >> 3] += 1ull << (8 * (sl & 7)); },
+            [](int, const GwLabels&) {});
+        disc = __dmul_rn(disc, args.gamma);
+        ++k;
+      }
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        double tr[BRM_MAX_REWARD];
+        gw_terminal_reward<A>(B, s, a, tr);
+#pragma unroll
+        for (int v = 0; v < BRM_MAX_REWARD; ++v)
+          acc[a][v] = __dadd_rn(acc[a][v], __dmul_rn(disc, tr[v]));
+      }
+      // optional per-rollout outputs (parity instrument)
+      if (args.out.ro_returns) {
+        for (int a = 0; a < A; ++a)
+          for (int v = 0; v < V; ++v) args.out.ro_returns[(local * A + a) * V + v] = acc[a][v];
+      }
+      if (args.out.ro_viol || args.out.ro_q) {
+        for (int a = 0; a < A; ++a)
+          for (int r = 0; r < R; ++r) {
+            if (args.out.ro_viol)
+              args.out.ro_viol[(local * A + a) * R + r] =
+                  static_cast<uint8_t>(viol[a][r >> 3] >> (8 * (r & 7)));
+            if (args.out.ro_q)
+              args.out.ro_q[(local * A + a) * R + r] = static_cast<uint8_t>((s.q[a] >> (4 * r)) & 15u);
+          }
+      }
+      if (args.out.ro_agents) {
+        int4* o = reinterpret_cast<int4*>(args.out.ro_agents);
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+          o[local * A + a] = make_int4(s.x[a], s.last[a], s.lane[a], s.init_lane[a]);
+      }
+      if (args.out.ro_steps) args.out.ro_steps[local] = k;
+    }
+    // warp-level reduction of the unit (inactive lanes contribute zeros)
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) {
+        if (v < V) {
+          double x = acc[a][v];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (lane == 0) args.part_returns[unit * (A * V) + a * V + v] = x;
+        }
+      }
+    }
+    if (args.out.viol_sum) {
+      for (int a = 0; a < A; ++a)
+        for (int r = 0; r < R; ++r) {
+          const uint32_t c = static_cast<uint32_t>(viol[a][r >> 3] >> (8 * (r & 7))) & 255u;
+          const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+          if (lane == 0 && tot)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * A + a) * R + r]),
+                      static_cast<unsigned long long>(tot));
+        }
+    }
+    if (args.out.agent_steps) {
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, agent_steps);
+      if (lane == 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
+                  static_cast<unsigned long long>(tot));
+    }
+  }
+}
+
+// Deterministic second stage: per leaf, sum the warp partials in a fixed order.
+__global__ void __launch_bounds__(128)
+leaf_reduce_kernel(const double* __restrict__ part, int32_t warps_per_leaf, int32_t nvals,
+                   double* __restrict__ out) {
+  __shared__ double sm[128];
+  const int64_t leaf = blockIdx.x;
+  for (int val = 0; val < nvals; ++val) {
+    double x = 0.0;
+    for (int w = threadIdx.x; w < warps_per_leaf; w += blockDim.x)
+      x += part[(leaf * warps_per_leaf + w) * nvals + val];
+    sm[threadIdx.x] = x;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[leaf * nvals + val] = sm[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ K2 execute
+struct GwExecArgs {
+  brm_gw_states in, out;
+  const uint8_t* actions;  // [A][n]
+  double* rewards;         // [A][V][n]
+  const GwBlob* blob;
+};
+
+template <int A>
+__global__ void __launch_bounds__(256) gw_execute_kernel(const GwExecArgs args) {
+  __shared__ GwBlob sB;
+  __shared__ __align__(8) uint64_t bar;
+  stage_blob(&sB, args.blob, static_cast<uint32_t>(sizeof(GwBlob)), &bar, 0, true);
+  const GwBlob& B = sB;
+  const int V = B.V, R = B.R;
+  const int64_t n = args.in.n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    GwRegs<A> s;
+    gw_load_state<A>(args.in, R, i, s);
+    uint32_t act[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) act[a] = args.actions[static_cast<int64_t>(a) * n + i];
+    // carry violation counters through (if tracked)
+    if (args.out.viol && args.in.viol)
+      for (int a = 0; a < A; ++a)
+        for (int r = 0; r < R; ++r) {
+          const int64_t o = (static_cast<int64_t>(a) * R + r) * n + i;
+          args.out.viol[o] = args.in.viol[o];
+        }
+    gw_step<A>(
+        B, s, act,
+        [&](int a, const double(&r)[BRM_MAX_REWARD]) {
+          for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = r[v];
+        },
+        [&](int a, int sl) {
+          if (args.out.viol) args.out.viol[(static_cast<int64_t>(a) * R + sl) * n + i] += 1u;
+        },
+        [](int, const GwLabels&) {});
+    int4* ag = reinterpret_cast<int4*>(args.out.agents);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      ag[a * n + i] = make_int4(s.x[a], s.last[a], s.lane[a], s.init_lane[a]);
+      for (int r = 0; r < R; ++r)
+        args.out.q[(static_cast<int64_t>(a) * R + r) * n + i] =
+            static_cast<uint8_t>((s.q[a] >> (4 * r)) & 15u);
+    }
+    args.out.term[i] = static_cast<uint8_t>(s.term);
+    args.out.depth[i] = s.depth;
+  }
+}
+
+// GetNumActions / IsTerminal / GetTerminalReward for n states
+struct GwQueryArgs {
+  brm_gw_states s;
+  uint8_t* num_actions;  // [A][n] or null
+  uint8_t* is_terminal;  // [n] or null
+  double* term_reward;   // [A][V][n] or null
+  const GwBlob* blob;
+};
+
+template <int A>
+__global__ void __launch_bounds__(256) gw_query_kernel(const GwQueryArgs args) {
+  __shared__ GwBlob sB;
+  __shared__ __align__(8) uint64_t bar;
+  stage_blob(&sB, args.blob, static_cast<uint32_t>(sizeof(GwBlob)), &bar, 0, true);
+  const GwBlob& B = sB;
+  const int64_t n = args.s.n;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    GwRegs<A> s;
+    gw_load_state<A>(args.s, B.R, i, s);
+    if (args.is_terminal) args.is_terminal[i] = s.term & 1u;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      if (args.num_actions)
+        args.num_actions[static_cast<int64_t>(a) * n + i] =
+            ((s.term >> a) & 1u) ? 1 : static_cast<uint8_t>(B.n_actions);
+      if (args.term_reward) {
+        double r[BRM_MAX_REWARD];
+        gw_terminal_reward<A>(B, s, a, r);
+        for (int v = 0; v < B.V; ++v)
+          args.term_reward[(static_cast<int64_t>(a) * B.V + v) * n + i] = r[v];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K6 replay
+struct GwReplayArgs {
+  brm_gw_states s0;
+  const uint8_t* actions;  // [B][T][A]
+  int32_t T;
+  brm_gw_trace tr;
+  const GwBlob* blob;
+};
+
+template <int A>
+__global__ void __launch_bounds__(128) gw_replay_kernel(const GwReplayArgs args) {
+  __shared__ GwBlob sB;
+  __shared__ __align__(8) uint64_t bar;
+  stage_blob(&sB, args.blob, static_cast<uint32_t>(sizeof(GwBlob)), &bar, 0, true);
+  const GwBlob& B = sB;
+  const int V = B.V, R = B.R, T = args.T;
+  const int64_t nb = args.s0.n;
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b < nb;
+       b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    GwRegs<A> s;
+    gw_load_state<A>(args.s0, R, b, s);
+    uint32_t viol[A][BRM_GW_MAX_SLOTS];
+    for (int a = 0; a < A; ++a)
+      for (int r = 0; r < BRM_GW_MAX_SLOTS; ++r) viol[a][r] = 0;
+    int t = 0;
+    for (; t < T && !(s.term & 1u); ++t) {
+      const int64_t bt = b * T + t;
+      uint32_t act[A];
+#pragma unroll
+      for (int a = 0; a < A; ++a) act[a] = args.actions[bt * A + a];
+      gw_step<A>(
+          B, s, act,
+          [&](int a, const double(&r)[BRM_MAX_REWARD]) {
+            for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * A + a) * V + v] = r[v];
+          },
+          [&](int a, int sl) { viol[a][sl] += 1u; },
+          [&](int a, const GwLabels& lab) {
+            uint32_t* o = args.tr.labels_out + (bt * A + a) * 3;
+            o[0] = lab.ego;
+            o[1] = lab.merged;
+            o[2] = lab.front;
+          });
+      int4* ag = reinterpret_cast<int4*>(args.tr.agents_out);
+      for (int a = 0; a < A; ++a) {
+        ag[bt * A + a] = make_int4(s.x[a], s.last[a], s.lane[a], s.init_lane[a]);
+        for (int r = 0; r < R; ++r) {
+          args.tr.q_out[(bt * A + a) * R + r] = static_cast<uint8_t>((s.q[a] >> (4 * r)) & 15u);
+          args.tr.viol_out[(bt * A + a) * R + r] = viol[a][r];
+        }
+      }
+      args.tr.term_out[bt] = static_cast<uint8_t>(s.term);
+    }
+    args.tr.steps_out[b] = t;
+    for (int a = 0; a < A; ++a) {
+      double r[BRM_MAX_REWARD];
+      gw_terminal_reward<A>(B, s, a, r);
+      for (int v = 0; v < V; ++v) args.tr.term_reward_out[(b * A + a) * V + v] = r[v];
+    }
+  }
+}
+
+template <template <int> class Launcher, class... Args>
+int dispatch_agents(int A, Args&&... args) {
+  switch (A) {
+    case 1: return Launcher<1>::run(args...);
+    case 2: return Launcher<2>::run(args...);
+    case 3: return Launcher<3>::run(args...);
+    case 4: return Launcher<4>::run(args...);
+    case 5: return Launcher<5>::run(args...);
+    case 6: return Launcher<6>::run(args...);
+    case 7: return Launcher<7>::run(args...);
+    case 8: return Launcher<8>::run(args...);
+    default: set_error("GridWorld supports 1..8 agents, got %d", A); return BRM_ERR_INVALID;
+  }
+}
+
+template <int A>
+struct RolloutLauncher {
+  static int run(brm_engine* e, const GwRolloutArgs& a, int grid) {
+    gw_rollout_kernel<A><<<grid, kRolloutThreads, 0, e->stream>>>(a);
+    return BRM_OK;
+  }
+};
+template <int A>
+struct ExecLauncher {
+  static int run(brm_engine* e, const GwExecArgs& a, int grid) {
+    gw_execute_kernel<A><<<grid, 256, 0, e->stream>>>(a);
+    return BRM_OK;
+  }
+};
+template <int A>
+struct QueryLauncher {
+  static int run(brm_engine* e, const GwQueryArgs& a, int grid) {
+    gw_query_kernel<A><<<grid, 256, 0, e->stream>>>(a);
+    return BRM_OK;
+  }
+};
+template <int A>
+struct ReplayLauncher {
+  static int run(brm_engine* e, const GwReplayArgs& a, int grid) {
+    gw_replay_kernel<A><<<grid, 128, 0, e->stream>>>(a);
+    return BRM_OK;
+  }
+};
+
+int grid_for(const brm_engine* e, int64_t threads_needed, int block, int ctas_per_sm) {
+  int64_t blocks = (threads_needed + block - 1) / block;
+  const int64_t cap = static_cast<int64_t>(e->sm_count) * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+// ---- launch wrappers used by gw_engine.cu (all pointers are device pointers here) ----
+
+int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_rollout_params& rp,
+                      const brm_gw_rollout_out& out) {
+  const int A = e->gw_blob.A, V = e->gw_blob.V;
+  GwRolloutArgs a;
+  a.leaves = leaves;
+  a.out = out;
+  a.blob = e->d_gw_blob;
+  a.seed = rp.seed;
+  a.rollout_base = rp.rollout_base;
+  a.rollouts_per_leaf = rp.rollouts_per_leaf;
+  a.max_steps = rp.max_steps;
+  a.first_exp = rp.first_discount_exp;
+  a.gamma = rp.discount_factor;
+  a.warps_per_leaf = (rp.rollouts_per_leaf + 31) / 32;
+  a.units = static_cast<int64_t>(leaves.n) * a.warps_per_leaf;
+  const size_t part_bytes = static_cast<size_t>(a.units) * A * V * sizeof(double);
+  int rc = e->ensure_ws(part_bytes);
+  if (rc != BRM_OK) return rc;
+  a.part_returns = static_cast<double*>(e->d_ws);
+  if (out.viol_sum)
+    BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0,
+                                   static_cast<size_t>(leaves.n) * A * e->gw_blob.R * sizeof(uint64_t),
+                                   e->stream));
+  if (out.agent_steps)
+    BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
+                                   e->stream));
+  // persistent grid: a multiple of the SM count, 4 CTAs of 8 warps per SM
+  const int grid = grid_for(e, a.units * 32, kRolloutThreads, 4);
+  e->time_begin();
+  rc = dispatch_agents<RolloutLauncher>(A, e, a, grid);
+  if (rc != BRM_OK) return rc;
+  e->launches++;
+  leaf_reduce_kernel<<<leaves.n, 128, 0, e->stream>>>(a.part_returns, a.warps_per_leaf, A * V,
+                                                      out.returns_sum);
+  e->launches++;
+  e->time_end();
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+int gw_launch_execute(brm_engine* e, const brm_gw_states& in, const uint8_t* actions,
+                      const brm_gw_states& out, double* rewards) {
+  GwExecArgs a;
+  a.in = in;
+  a.out = out;
+  a.actions = actions;
+  a.rewards = rewards;
+  a.blob = e->d_gw_blob;
+  const int grid = grid_for(e, in.n, 256, 8);
+  int rc = dispatch_agents<ExecLauncher>(e->gw_blob.A, e, a, grid);
+  if (rc != BRM_OK) return rc;
+  e->launches++;
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+int gw_launch_query(brm_engine* e, const brm_gw_states& s, uint8_t* num_actions,
+                    uint8_t* is_terminal, double* term_reward) {
+  GwQueryArgs a;
+  a.s = s;
+  a.num_actions = num_actions;
+  a.is_terminal = is_terminal;
+  a.term_reward = term_reward;
+  a.blob = e->d_gw_blob;
+  const int grid = grid_for(e, s.n, 256, 8);
+  int rc = dispatch_agents<QueryLauncher>(e->gw_blob.A, e, a, grid);
+  if (rc != BRM_OK) return rc;
+  e->launches++;
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+int gw_launch_replay(brm_engine* e, const brm_gw_states& s0, const uint8_t* actions, int32_t T,
+                     const brm_gw_trace& tr) {
+  GwReplayArgs a;
+  a.s0 = s0;
+  a.actions = actions;
+  a.T = T;
+  a.tr = tr;
+  a.blob = e->d_gw_blob;
+  const int grid = grid_for(e, s0.n, 128, 8);
+  int rc = dispatch_agents<ReplayLauncher>(e->gw_blob.A, e, a, grid);
+  if (rc != BRM_OK) return rc;
+  e->launches++;
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+}  // namespace brm

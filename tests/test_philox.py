@@ -1,0 +1,15 @@
+"""Philox4x32-10 known answers (Random123 kat_vectors) for the oracle-side generator."""
+from oracle import gw as ogw
+
+KAT = [
+    ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+    ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+    ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+     [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+]
+
+
+def test_philox_known_answers(built):
+    port = ogw.GwOracle("port")
+    for ctr, key, want in KAT:
+        assert port.philox(ctr, key) == want
