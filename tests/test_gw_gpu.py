@@ -18,9 +18,18 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gw_
 HAVE_REF = os.path.exists(os.path.join(ogw.HERE, "_ref", "libgw_ref.so"))
 
 
-def make_engine(A=3, terminal_depth=8, on_violation="reset", **kw):
+def make_engine(A=3, terminal_depth=8, on_violation="reset", appendix_b_tables=False, **kw):
     p = brm.GridWorldStateParameter(num_other_agents=A - 1, terminal_depth_=terminal_depth, **kw)
-    return brm.GridWorldEngine(p, brm.make_default_rules(on_violation), device=0)
+    rules = brm.make_default_rules(on_violation)
+    if appendix_b_tables:
+        # the golden traces number the ZIP monitor's states as SURVEY.md Appendix B does; the
+        # compiler's breadth-first numbering is an isomorphic relabelling (tests/test_ltl.py)
+        zip_aps = ["in_direct_front_x#0", "merged_e", "merged_x#0"]
+        rules = [brm.RuleMonitor(brm.ltl.RuleTable("G !collision", ["collision"],
+                                                   ogw.G_NOT_COLLISION["trans"], [1]), -1.0, 0, on_violation),
+                 brm.RuleMonitor(brm.ltl.RuleTable(brm.ZIP_FORMULA, zip_aps, ogw.ZIP["trans"],
+                                                   ogw.ZIP["accepting"]), -1.0, 1, on_violation)]
+    return brm.GridWorldEngine(p, rules, device=0)
 
 
 def check_trace(tr, b, o, A):
@@ -40,7 +49,8 @@ def test_replay_matches_golden_from_reference(built):
     g = np.load(GOLDEN)
     for name in ["base3_reset", "base3_stay", "merge4_reset"]:
         cfg, A = scenario(name)
-        eng = make_engine(A, cfg.terminal_depth, "reset" if name.endswith("reset") else "stay")
+        eng = make_engine(A, cfg.terminal_depth, "reset" if name.endswith("reset") else "stay",
+                          appendix_b_tables=True)
         ag, term, acts = g[name + "/agents0"], g[name + "/term0"], g[name + "/actions"]
         tr = eng.replay(eng.make_batch(ag, term), acts)
         for b in range(ag.shape[0]):
