@@ -232,6 +232,172 @@ typedef struct {
 int brm_gw_replay(brm_engine* e, const brm_gw_states* s0, const uint8_t* actions, int32_t T,
                   const brm_gw_trace* trace);
 
+/* ------------------------------------------- continuous world (MvmctsState) ------ */
+
+/* The BARK-backed state plugin MvmctsState (src/rules_mcts_state.{hpp,cpp}) on a
+ * self-contained world model: agents are rectangles with single-track kinematics and
+ * motion primitives (a, delta), the map is a set of lane centre polylines plus one road
+ * polygon.  bark / ltl / mvmcts are un-vendored dependencies of the reference; DESIGN.md
+ * states which definitions restate reference lines and which restate the published
+ * algorithms ("parity unpinned"). */
+
+#define BRM_CW_MAX_AGENTS 16
+#define BRM_CW_MAX_LANES 8
+#define BRM_CW_MAX_PTS 64    /* points per lane centre line */
+#define BRM_CW_MAX_ROAD 32   /* road polygon vertices */
+#define BRM_CW_MAX_PRIMS 8   /* motion primitives per agent */
+#define BRM_CW_MAX_SLOTS 32  /* rule states per agent */
+
+/* label kinds; kinds >= 8 are per-other-agent (`name#0`).  bark label functions named in
+ * brackets (bark/world/evaluation/ltl/label_functions/, un-vendored). */
+#define BRM_CW_LABEL_COLLISION_EGO 0       /* GenericEgoLabelFunction<EvaluatorCollisionEgoAgent>, test/single_agent_test.cpp:51-52 */
+#define BRM_CW_LABEL_COLLISION_CORRIDOR 1  /* GenericEgoLabelFunction<EvaluatorDrivableArea>, :55-56 */
+#define BRM_CW_LABEL_GOAL_REACHED 2        /* GenericEgoLabelFunction<EvaluatorGoalReached>, :53-54 */
+#define BRM_CW_LABEL_SAFE_DISTANCE_FRONT 3 /* [SafeDistanceLabelFunction] true while the gap to the preceding agent is safe */
+#define BRM_CW_LABEL_MERGED_E 4            /* [EgoBeyondPointLabelFunction] */
+#define BRM_CW_LABEL_RIGHTMOST_LANE 5      /* [RightmostLaneLabelFunction] */
+#define BRM_CW_LABEL_ON_ROAD 6             /* ego is on some lane */
+#define BRM_CW_LABEL_MERGED_X 8            /* [AgentBeyondPointLabelFunction] `merged_x#0` */
+#define BRM_CW_LABEL_IN_DIRECT_FRONT_X 9   /* [PrecedingAgentLabelFunction]   `in_direct_front_x#0` */
+#define BRM_CW_LABEL_NEAR_X 10             /* [AgentNearLabelFunction]        `near_x#0` */
+
+/* mirrors RulesMctsStateParameters (src/rules_mcts_state_parameters.hpp:33-46, defaults
+ * src/rules_mcts_state_parameters.cpp:36-78) plus the dynamics / label constants that
+ * live in bark's parameter server. */
+typedef struct {
+  float collision_weight;            /* 0     */
+  float out_of_map_weight;           /* -800  */
+  float potential_weight;            /* 32    */
+  float acceleration_weight;         /* 0     */
+  float radial_acceleration_weight;  /* 0     */
+  float desired_velocity_weight;     /* -5    */
+  float lane_center_weight;          /* 0     */
+  float prediction_time_span;        /* 0.3   */
+  float desired_velocity;            /* 10    */
+  float discount_factor;             /* 0.9 (used by PotentialReward, :250-257) */
+  float goal_reward;                 /* 0     */
+  int32_t reward_vector_size;        /* 1     */
+  int32_t horizon;                   /* 30    */
+  int32_t use_rule_reward_for_ego_only; /* false */
+  float wheel_base;                  /* 2.7   SingleTrackModel */
+  float integration_time_delta;      /* 0.02  BehaviorMotionPrimitives::IntegrationTimeDelta */
+  float sd_reaction_time;            /* safe-distance label: reaction time delta        */
+  float sd_max_decel_rear;           /* |a_r|                                           */
+  float sd_max_decel_front;          /* |a_f|                                           */
+  float near_distance;               /* near_x#j: centre distance below this            */
+} brm_cw_params;
+
+typedef struct {
+  float front, rear, half_width; /* rectangle [-rear, front] x [-half_width, half_width] around the pose */
+  int32_t has_goal;
+  float goal[6];                 /* xmin, xmax, ymin, ymax, theta_lo, theta_hi */
+  int32_t n_prims;               /* motion primitives; agents outside the MCTS agent list use primitive 0 */
+  float prim_acc[BRM_CW_MAX_PRIMS];
+  float prim_delta[BRM_CW_MAX_PRIMS];
+} brm_cw_agent;
+
+typedef struct {
+  int32_t n_pts;
+  int32_t successor; /* lane that continues this one (-1: none) */
+  int32_t flags;     /* bit0: rightmost lane */
+  float half_width;
+  float s_point;     /* arc length of the merge point on this lane (beyond-point labels) */
+  float pts[BRM_CW_MAX_PTS][2];
+} brm_cw_lane;
+
+/* One scenario.  Agents 0..n_mcts_agents-1 are the MCTS agents (ego = 0; the reference's
+ * agent_idx list, src/behavior_rules_mcts.hpp:392-414); the rest are simulated only. */
+typedef struct {
+  brm_cw_params params;
+  int32_t n_agents, n_mcts_agents, n_lanes, n_road, n_rules;
+  brm_cw_agent agents[BRM_CW_MAX_AGENTS];
+  brm_cw_lane lanes[BRM_CW_MAX_LANES];
+  float road[BRM_CW_MAX_ROAD][2];
+  brm_rule rules[BRM_MAX_RULES]; /* common rules of every MCTS agent */
+} brm_cw_scenario;
+
+/* agent flag bits */
+#define BRM_CW_PRESENT 1 /* agent exists in the world */
+#define BRM_CW_VALID 2   /* ExecutionStatus::VALID (cleared after a collision, :116-120) */
+
+/* A batch of n states of scenarios (MvmctsState members, src/rules_mcts_state.hpp:80-87).
+ *   scenario [n]        index of the uploaded scenario each state lives in
+ *   agents   [A][n][4]  float (x, y, theta, v): one 16-byte vector per agent
+ *   flags    [A][n]     BRM_CW_PRESENT | BRM_CW_VALID
+ *   horizon  [n]        remaining horizon_
+ *   terminal [n]        is_terminal_state_ (CheckTerminal, :266-285; fill with brm_cw_check_terminal)
+ *   q        [M][R][n]  automaton states;  viol [M][R][n] violation counters (may be NULL) */
+typedef struct {
+  int32_t n;
+  int32_t mem;
+  int32_t* scenario;
+  float* agents;
+  uint8_t* flags;
+  int32_t* horizon;
+  uint8_t* terminal;
+  uint8_t* q;
+  uint32_t* viol;
+} brm_cw_states;
+
+/* Upload n_scenarios scenarios (all with the same n_agents, n_mcts_agents,
+ * reward_vector_size and rule list shapes; geometry, goals and primitives may differ). */
+int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_scenarios);
+int32_t brm_cw_rules_per_agent(const brm_engine* e);
+
+/* MvmctsState ctor's CheckTerminal (:52, :266-285): fills s->terminal. */
+int brm_cw_check_terminal(brm_engine* e, brm_cw_states* s);
+/* MvmctsState::Execute (:57-128): actions [M][n] uint8, rewards [M][V][n] float.
+ * BRM_MEM_HOST batches are checked first: BRM_ERR_TERMINAL if any state is terminal (:59). */
+int brm_cw_execute(brm_engine* e, const brm_cw_states* in, const uint8_t* actions,
+                   brm_cw_states* out, float* rewards);
+/* MvmctsState::GetNumActions (:129-141): out [M][n] */
+int brm_cw_get_num_actions(brm_engine* e, const brm_cw_states* s, uint8_t* out);
+/* MvmctsState::GetTerminalReward (:148-164): out [M][V][n] float */
+int brm_cw_terminal_reward(brm_engine* e, const brm_cw_states* s, float* out);
+
+/* mvmcts::RandomHeuristic over MvmctsState (instantiated at
+ * src/behavior_rules_mcts.hpp:188-189), fused on the device (K3 rules_rollout):
+ *   returns_sum [n][M][V] double, viol_sum [n][M][R] uint64, agent_steps [n] uint64
+ *   (agents integrated: present and VALID, MCTS or not).
+ * Optional per-rollout outputs: ro_returns [N][M][V] float, ro_viol [N][M][R] uint8,
+ * ro_q [N][M][R] uint8, ro_agents [N][A][4] float, ro_flags [N][A] uint8, ro_steps [N] int32. */
+typedef struct {
+  double* returns_sum;
+  uint64_t* viol_sum;
+  uint64_t* agent_steps;
+  float* ro_returns;
+  uint8_t* ro_viol;
+  uint8_t* ro_q;
+  float* ro_agents;
+  uint8_t* ro_flags;
+  int32_t* ro_steps;
+} brm_cw_rollout_out;
+
+int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
+                   const brm_cw_rollout_out* out);
+
+/* Replay of given action sequences with a full trace (K6): actions [B][T][M];
+ *   agents_out [B][T][A][4] float, flags_out [B][T][A], terminal_out [B][T],
+ *   q_out [B][T][M][R], viol_out [B][T][M][R] uint32, rewards_out [B][T][M][V] float,
+ *   labels_out [B][T][M][4] uint32 (word 0: ego bits by label kind; words 1..3: masks over j
+ *   for kinds 8, 9, 10), frenet_out [B][T][A][3] float (lane, s, lat),
+ *   term_reward_out [B][M][V] float, steps_out [B]. */
+typedef struct {
+  float* agents_out;
+  uint8_t* flags_out;
+  uint8_t* terminal_out;
+  uint8_t* q_out;
+  uint32_t* viol_out;
+  float* rewards_out;
+  uint32_t* labels_out;
+  float* frenet_out;
+  float* term_reward_out;
+  int32_t* steps_out;
+} brm_cw_trace;
+
+int brm_cw_replay(brm_engine* e, const brm_cw_states* s0, const uint8_t* actions, int32_t T,
+                  const brm_cw_trace* trace);
+
 /* ---------------------------------------------------- root statistics merge ---- */
 
 /* Root-parallel merge (new: the reference has a single tree; what must be summed is

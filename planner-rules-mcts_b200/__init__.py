@@ -15,3 +15,9 @@ from .ltl import RuleMonitor, compile_rule  # noqa: F401
 
 __all__ = ["Engine", "BrmError", "GridWorldEngine", "GridWorldState", "GridWorldStateParameter",
            "GwBatch", "RuleMonitor", "compile_rule", "ZIP_FORMULA", "make_default_rules", "ltl"]
+from .continuous import (AgentModel, CwBatch, Lane, MvmctsState, RulesMctsEngine,  # noqa: E402,F401
+                         RulesMctsStateParameters, Scenario)
+from . import scenarios  # noqa: E402,F401
+
+__all__ += ["AgentModel", "CwBatch", "Lane", "MvmctsState", "RulesMctsEngine", "RulesMctsStateParameters",
+            "Scenario", "scenarios"]

@@ -76,8 +76,64 @@ class GwTrace(C.Structure):
         "term_reward_out", "steps_out")]
 
 
+CW_MAX_AGENTS, CW_MAX_LANES, CW_MAX_PTS, CW_MAX_ROAD, CW_MAX_PRIMS, CW_MAX_SLOTS = 16, 8, 64, 32, 8, 32
+(CW_LABEL_COLLISION_EGO, CW_LABEL_COLLISION_CORRIDOR, CW_LABEL_GOAL_REACHED,
+ CW_LABEL_SAFE_DISTANCE_FRONT, CW_LABEL_MERGED_E, CW_LABEL_RIGHTMOST_LANE, CW_LABEL_ON_ROAD) = range(7)
+CW_LABEL_MERGED_X, CW_LABEL_IN_DIRECT_FRONT_X, CW_LABEL_NEAR_X = 8, 9, 10
+CW_PRESENT, CW_VALID = 1, 2
+
+
+class CwParams(C.Structure):
+    _fields_ = [(k, C.c_float) for k in (
+        "collision_weight", "out_of_map_weight", "potential_weight", "acceleration_weight",
+        "radial_acceleration_weight", "desired_velocity_weight", "lane_center_weight",
+        "prediction_time_span", "desired_velocity", "discount_factor", "goal_reward")] + [
+        ("reward_vector_size", C.c_int32), ("horizon", C.c_int32),
+        ("use_rule_reward_for_ego_only", C.c_int32)] + [(k, C.c_float) for k in (
+            "wheel_base", "integration_time_delta", "sd_reaction_time", "sd_max_decel_rear",
+            "sd_max_decel_front", "near_distance")]
+
+
+class CwAgent(C.Structure):
+    _fields_ = [("front", C.c_float), ("rear", C.c_float), ("half_width", C.c_float),
+                ("has_goal", C.c_int32), ("goal", C.c_float * 6), ("n_prims", C.c_int32),
+                ("prim_acc", C.c_float * CW_MAX_PRIMS), ("prim_delta", C.c_float * CW_MAX_PRIMS)]
+
+
+class CwLane(C.Structure):
+    _fields_ = [("n_pts", C.c_int32), ("successor", C.c_int32), ("flags", C.c_int32),
+                ("half_width", C.c_float), ("s_point", C.c_float),
+                ("pts", (C.c_float * 2) * CW_MAX_PTS)]
+
+
+class CwScenario(C.Structure):
+    _fields_ = [("params", CwParams), ("n_agents", C.c_int32), ("n_mcts_agents", C.c_int32),
+                ("n_lanes", C.c_int32), ("n_road", C.c_int32), ("n_rules", C.c_int32),
+                ("agents", CwAgent * CW_MAX_AGENTS), ("lanes", CwLane * CW_MAX_LANES),
+                ("road", (C.c_float * 2) * CW_MAX_ROAD), ("rules", Rule * MAX_RULES)]
+
+
+class CwStates(C.Structure):
+    _fields_ = [("n", C.c_int32), ("mem", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "scenario", "agents", "flags", "horizon", "terminal", "q", "viol")]
+
+
+class CwRolloutOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "returns_sum", "viol_sum", "agent_steps", "ro_returns", "ro_viol", "ro_q", "ro_agents",
+        "ro_flags", "ro_steps")]
+
+
+class CwTrace(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "agents_out", "flags_out", "terminal_out", "q_out", "viol_out", "rewards_out", "labels_out",
+        "frenet_out", "term_reward_out", "steps_out")]
+
+
 # every symbol include/brm.h declares (tests/test_abi.py checks the library exports them)
 SYMBOLS = [
+    "brm_cw_configure", "brm_cw_rules_per_agent", "brm_cw_check_terminal", "brm_cw_execute",
+    "brm_cw_get_num_actions", "brm_cw_terminal_reward", "brm_cw_rollout", "brm_cw_replay",
     "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_synchronize",
     "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
     "brm_gw_configure", "brm_gw_rules_per_agent", "brm_gw_execute", "brm_gw_get_num_actions",
@@ -119,6 +175,14 @@ def load():
     lib.brm_gw_rollout.argtypes = [vp, P(GwStates), P(RolloutParams), P(GwRolloutOut)]
     lib.brm_gw_replay.argtypes = [vp, P(GwStates), vp, i32, P(GwTrace)]
     lib.brm_root_stats_reduce.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]
+    lib.brm_cw_configure.argtypes = [vp, P(CwScenario), i32]
+    lib.brm_cw_rules_per_agent.argtypes = [vp]
+    lib.brm_cw_check_terminal.argtypes = [vp, P(CwStates)]
+    lib.brm_cw_execute.argtypes = [vp, P(CwStates), vp, P(CwStates), vp]
+    lib.brm_cw_get_num_actions.argtypes = [vp, P(CwStates), vp]
+    lib.brm_cw_terminal_reward.argtypes = [vp, P(CwStates), vp]
+    lib.brm_cw_rollout.argtypes = [vp, P(CwStates), P(RolloutParams), P(CwRolloutOut)]
+    lib.brm_cw_replay.argtypes = [vp, P(CwStates), vp, i32, P(CwTrace)]
     _lib = lib
     return lib
 

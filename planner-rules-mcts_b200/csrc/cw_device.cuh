@@ -1,0 +1,389 @@
+// Device-side continuous-world step: MvmctsState::Execute
+// (/root/reference/src/rules_mcts_state.cpp:57-128) with one lane = one agent of one
+// rollout.  floor(32/A) rollouts share a warp; agents of a rollout exchange poses with
+// warp shuffles, pairwise predicates (collision, preceding agent, near) are evaluated
+// by every lane against its group, the rule automata of an agent step in its lane.
+// The scenario blob (parameters, lane polylines, road polygon, automaton tables) sits in
+// shared memory, staged by a TMA bulk copy.
+#pragma once
+#include "common.cuh"
+
+namespace brm {
+
+struct alignas(16) CwSeg {
+  float x0, y0, dx, dy;
+  float inv_len2, len, s0, _pad;
+};
+
+struct alignas(16) CwLaneHdr {
+  int32_t seg_off, n_seg, succ, flags;
+  float hw, hw2, length, s_point;
+};
+
+constexpr int kCwMaxSegs = BRM_CW_MAX_LANES * (BRM_CW_MAX_PTS - 1);
+
+struct alignas(16) CwBlob {
+  int32_t A, M, V, R, n_lanes, n_road, n_rules, n_sub;
+  int32_t ego_only, total_bytes, _p0, _p1;
+  float w_coll, w_oom, w_pot, w_acc, w_rad, w_vel, w_lane, dt;
+  float v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
+  float near2, inv_dt, _p2, _p3;
+  float front[BRM_CW_MAX_AGENTS], rear[BRM_CW_MAX_AGENTS], hw[BRM_CW_MAX_AGENTS];
+  float goal[BRM_CW_MAX_AGENTS][6];
+  uint8_t has_goal[BRM_CW_MAX_AGENTS], n_prims[BRM_CW_MAX_AGENTS];
+  float prim_a[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];
+  float prim_k[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];  // tan(delta) / wheel_base
+  uint8_t slot_rule[BRM_CW_MAX_SLOTS];
+  int8_t slot_rank[BRM_CW_MAX_SLOTS];  // rank of the bound other agent among the others, -1: ego rule
+  brm_rule rules[BRM_MAX_RULES];
+  float4 road_edge[BRM_CW_MAX_ROAD];  // (ya, yb, xa, m = (xb-xa)/(yb-ya))
+  CwLaneHdr lanes[BRM_CW_MAX_LANES];
+  CwSeg segs[kCwMaxSegs];  // last: only the used part is copied
+};
+static_assert(sizeof(CwBlob) % 16 == 0, "blob must be a multiple of 16 bytes");
+static_assert(offsetof(CwBlob, segs) % 16 == 0, "segment array must be 16-byte aligned");
+
+// launch context shared by cw_engine.cu (host API) and cw_kernels.cu
+struct CwCommon {
+  const uint8_t* blobs;       // [n_scenarios] CwBlob, stride blob_stride
+  const int32_t* blob_bytes;  // used bytes of each blob (multiple of 16)
+  size_t blob_stride;
+  int32_t blob_cap;           // bytes reserved for the blob in shared memory
+  int32_t A, M, V, R, G;      // G = rollouts (states) per warp
+};
+struct CwLaunchCtx {
+  CwCommon c;
+  size_t smem_bytes;
+};
+enum { MODE_EXECUTE = 0, MODE_QUERY = 1, MODE_REPLAY = 2 };
+
+// per-lane agent state
+struct CwAgent {
+  float x, y, th, v;
+  float cs, sn;     // cos / sin of th
+  uint32_t flags;   // BRM_CW_PRESENT | BRM_CW_VALID
+  int lane;         // lane index of the current position (-1: none)
+  float s, lat;
+};
+
+struct CwStepOut {
+  float r[BRM_MAX_REWARD];
+  uint32_t w[4];  // labels: ego bits by kind, masks over j for kinds 8, 9, 10
+  bool terminal;  // state-level (group-uniform)
+};
+
+__device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a, uint32_t prim) {
+  const float acc = B.prim_a[a][prim];
+  const float k = B.prim_k[a][prim];
+  float x = t.x, y = t.y, th = t.th, v = t.v;
+  float cs = t.cs, sn = t.sn;
+  const int n_sub = B.n_sub;
+  if (k == 0.0f) {
+    // no steering: theta stays bit-identical, so cos/sin are loop invariants
+    for (int n = 0; n < n_sub; ++n) {
+      const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
+      x = x + h * (v * cs);
+      y = y + h * (v * sn);
+      v = v + h * acc;
+    }
+  } else {
+    for (int n = 0; n < n_sub; ++n) {
+      const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
+      if (n > 0) sincosf(th, &sn, &cs);
+      x = x + h * (v * cs);
+      y = y + h * (v * sn);
+      th = th + h * (v * k);
+      v = v + h * acc;
+    }
+    sincosf(th, &sn, &cs);
+  }
+  t.x = x; t.y = y; t.th = th; t.v = v; t.cs = cs; t.sn = sn;
+}
+
+// nearest point on every lane centre line, first lane that contains the point wins
+__device__ __forceinline__ void cw_frenet(const CwBlob& B, CwAgent& t) {
+  t.lane = -1;
+  t.s = 0.f;
+  t.lat = 0.f;
+  for (int l = 0; l < B.n_lanes; ++l) {
+    const CwLaneHdr L = B.lanes[l];
+    const CwSeg* seg = B.segs + L.seg_off;
+    float best = __int_as_float(0x7f800000), bt = 0.f, btu = 0.f, bcross = 0.f;
+    int bk = 0;
+    for (int k = 0; k < L.n_seg; ++k) {
+      const float4 p = reinterpret_cast<const float4*>(seg + k)[0];
+      const float4 m = reinterpret_cast<const float4*>(seg + k)[1];
+      const float wx = t.x - p.x, wy = t.y - p.y;
+      const float tu = (wx * p.z + wy * p.w) * m.x;
+      const float tc = fminf(fmaxf(tu, 0.f), 1.f);
+      const float ex = wx - tc * p.z, ey = wy - tc * p.w;
+      const float d2 = ex * ex + ey * ey;
+      if (d2 < best) {
+        best = d2; bk = k; bt = tc; btu = tu;
+        bcross = p.z * wy - p.w * wx;
+      }
+    }
+    const bool interior = !(bk == 0 && btu < 0.f) && !(bk == L.n_seg - 1 && btu > 1.f);
+    if (interior && best <= L.hw2) {
+      t.lane = l;
+      t.s = seg[bk].s0 + bt * seg[bk].len;
+      const float d = sqrtf(best);
+      t.lat = bcross < 0.f ? -d : d;
+      return;
+    }
+  }
+}
+
+__device__ __forceinline__ bool cw_point_in_road(const CwBlob& B, float px, float py) {
+  bool inside = false;
+  for (int e = 0; e < B.n_road; ++e) {
+    const float4 g = B.road_edge[e];
+    if ((g.x > py) != (g.y > py)) {
+      if (px < g.w * (py - g.x) + g.z) inside = !inside;
+    }
+  }
+  return inside;
+}
+
+__device__ __forceinline__ void cw_corners(const CwBlob& B, const CwAgent& t, int a, float (&cx)[4],
+                                           float (&cy)[4]) {
+  const float f = B.front[a], r = B.rear[a], h = B.hw[a];
+  const float lx[4] = {f, f, -r, -r};
+  const float ly[4] = {h, -h, -h, h};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    cx[k] = t.x + (lx[k] * t.cs - ly[k] * t.sn);
+    cy[k] = t.y + (lx[k] * t.sn + ly[k] * t.cs);
+  }
+}
+
+// EvaluatorDrivableArea restated: a corner outside the road polygon, or a road vertex
+// strictly inside the rectangle
+__device__ __forceinline__ bool cw_out_of_map(const CwBlob& B, const CwAgent& t, int a,
+                                              const float (&cx)[4], const float (&cy)[4]) {
+  bool out = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out = !cw_point_in_road(B, cx[k], cy[k]) || out;
+  const float f = B.front[a], r = B.rear[a], h = B.hw[a];
+  for (int e = 0; e < B.n_road; ++e) {
+    const float4 g = B.road_edge[e];
+    const float dx = g.z - t.x, dy = g.x - t.y;
+    const float lx = dx * t.cs + dy * t.sn, ly = -dx * t.sn + dy * t.cs;
+    out = (lx > -r && lx < f && fabsf(ly) < h) || out;
+  }
+  return out;
+}
+
+__device__ __forceinline__ bool cw_at_goal(const CwBlob& B, const CwAgent& t, int a,
+                                           const float (&cx)[4], const float (&cy)[4]) {
+  if (!B.has_goal[a]) return false;
+  const float* g = B.goal[a];
+  bool in = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    in = in && cx[k] >= g[0] && cx[k] <= g[1] && cy[k] >= g[2] && cy[k] <= g[3];
+  return in && t.th >= g[4] && t.th <= g[5];
+}
+
+// pose of agent j of my group, fetched with shuffles (executed by every lane of the warp)
+struct CwPeer {
+  float x, y, cs, sn, v, s;
+  int lane;
+  uint32_t flags;
+};
+
+__device__ __forceinline__ CwPeer cw_fetch(const CwAgent& t, int src) {
+  CwPeer p;
+  p.x = __shfl_sync(0xffffffffu, t.x, src);
+  p.y = __shfl_sync(0xffffffffu, t.y, src);
+  p.cs = __shfl_sync(0xffffffffu, t.cs, src);
+  p.sn = __shfl_sync(0xffffffffu, t.sn, src);
+  p.v = __shfl_sync(0xffffffffu, t.v, src);
+  p.s = __shfl_sync(0xffffffffu, t.s, src);
+  const int packed = __shfl_sync(0xffffffffu, (t.lane << 8) | static_cast<int>(t.flags), src);
+  p.lane = packed >> 8;
+  p.flags = static_cast<uint32_t>(packed) & 0xffu;
+  return p;
+}
+
+// separating-axis test of my rectangle against peer j's
+__device__ __forceinline__ bool cw_rect_overlap(const CwBlob& B, const CwAgent& t, int a,
+                                                const CwPeer& p, int j) {
+  const float oi = (B.front[a] - B.rear[a]) * 0.5f, oj = (B.front[j] - B.rear[j]) * 0.5f;
+  const float eix = (B.front[a] + B.rear[a]) * 0.5f, ejx = (B.front[j] + B.rear[j]) * 0.5f;
+  const float eiy = B.hw[a], ejy = B.hw[j];
+  const float dx = (p.x + oj * p.cs) - (t.x + oi * t.cs);
+  const float dy = (p.y + oj * p.sn) - (t.y + oi * t.sn);
+  const float cd = fabsf(t.cs * p.cs + t.sn * p.sn), sd = fabsf(t.sn * p.cs - t.cs * p.sn);
+  bool hit = fabsf(dx * t.cs + dy * t.sn) <= eix + ejx * cd + ejy * sd;
+  hit = (fabsf(-dx * t.sn + dy * t.cs) <= eiy + ejx * sd + ejy * cd) && hit;
+  hit = (fabsf(dx * p.cs + dy * p.sn) <= ejx + eix * cd + eiy * sd) && hit;
+  hit = (fabsf(-dx * p.sn + dy * p.cs) <= ejy + eix * sd + eiy * cd) && hit;
+  return hit;
+}
+
+// Everything of Execute that follows the kinematic step, for the lane's own agent:
+// collision / drivable area / goal, labels, rule automata, reward vector, validity and
+// the state's terminal flag.  Must be called by all 32 lanes (shuffles inside).
+//   a, base : my agent index and the first lane of my group; real: lane maps to an agent
+//   live    : my group executes this step
+//   in_*    : my agent's v, theta, flags BEFORE the kinematic step
+//   q, viol : this thread's column of the per-slot automaton state / violation counters
+template <bool WITH_LABELS>
+__device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, int base, bool real,
+                                            bool live, float in_v, float in_th, uint32_t in_flags,
+                                            int horizon_after, uint8_t* q, uint8_t* viol,
+                                            int col_stride, CwStepOut& o) {
+  const int A = B.A, M = B.M, V = B.V;
+  const bool present = real && (t.flags & BRM_CW_PRESENT);
+  const bool evaluated = live && present && (in_flags & BRM_CW_VALID) && a < M;
+#pragma unroll
+  for (int v = 0; v < BRM_MAX_REWARD; ++v) o.r[v] = 0.f;
+  o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
+
+  bool oom = false, goal = false;
+  if (evaluated || (live && present && a == 0)) {
+    float cx[4], cy[4];
+    cw_corners(B, t, a, cx, cy);
+    oom = cw_out_of_map(B, t, a, cx, cy);
+    goal = cw_at_goal(B, t, a, cx, cy);
+  }
+  // pairwise predicates against the agents of my group
+  bool coll = false;
+  int jf = -1;
+  float gf = 0.f;
+  uint32_t merged_mask = 0, near_mask = 0;
+  const float my_len = (t.lane >= 0) ? B.lanes[t.lane].length : 0.f;
+  const int my_succ = (t.lane >= 0) ? B.lanes[t.lane].succ : -2;
+  for (int j = 0; j < A; ++j) {
+    const CwPeer p = cw_fetch(t, base + j);
+    if (j == a || !(p.flags & BRM_CW_PRESENT) || !present) continue;
+    coll = cw_rect_overlap(B, t, a, p, j) || coll;
+    // gap along my corridor: own lane, then its successor
+    if (t.lane >= 0 && p.lane >= 0) {
+      float g = 0.f;
+      bool has = false;
+      if (p.lane == t.lane) {
+        g = p.s - t.s;
+        has = true;
+      } else if (my_succ == p.lane) {
+        g = (my_len - t.s) + p.s;
+        has = true;
+      }
+      if (has && g > 0.f && (jf < 0 || g < gf)) {
+        jf = j;
+        gf = g;
+      }
+    }
+    if (p.lane >= 0 && p.s >= B.lanes[p.lane].s_point) merged_mask |= 1u << j;
+    const float dx = p.x - t.x, dy = p.y - t.y;
+    if (dx * dx + dy * dy < B.near2) near_mask |= 1u << j;
+  }
+  // speed of the preceding agent (one more shuffle, executed by all lanes)
+  const float vf = __shfl_sync(0xffffffffu, t.v, base + (jf < 0 ? 0 : jf));
+
+  if (evaluated) {
+    o.r[0] += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92
+    o.r[0] += (oom ? 1.f : 0.f) * B.w_oom;    // :94-96
+    // GetActionCost (:202-248)
+    {
+      const float acc = (t.v - in_v) * B.inv_dt;
+      float cost = B.w_acc * acc * acc * B.dt;
+      const float theta_dot = (t.th - in_th) * B.inv_dt;
+      const float avg_vel = 0.5f * acc * B.dt + in_v;
+      const float a_lat = theta_dot * avg_vel;
+      cost += B.w_rad * a_lat * a_lat * B.dt;
+      cost += B.w_vel * fabsf(in_v - B.v_des) * B.dt;
+      if (t.lane >= 0) cost += B.w_lane * fabsf(t.lat) * B.dt;
+      // PotentialReward (:250-264)
+      const float pot_new = -B.w_pot * B.dt * fabsf(t.v - B.v_des);
+      const float pot_cur = -B.w_pot * B.dt * fabsf(in_v - B.v_des);
+      const float pot = B.gamma * pot_new - pot_cur;
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v)
+        if (v == V - 1) o.r[v] = (o.r[v] + cost) + pot;
+    }
+    // labels (EvaluateRules, :165-185)
+    uint32_t w0 = 0;
+    if (coll) w0 |= 1u << BRM_CW_LABEL_COLLISION_EGO;
+    if (oom) w0 |= 1u << BRM_CW_LABEL_COLLISION_CORRIDOR;
+    if (goal) w0 |= 1u << BRM_CW_LABEL_GOAL_REACHED;
+    bool safe = true;
+    if (jf >= 0) {
+      const float dist = gf - (B.front[a] + B.rear[jf]);
+      const float dsafe = t.v * B.sd_delta + (t.v * t.v) * B.sd_ar - (vf * vf) * B.sd_af;
+      safe = dist >= dsafe;
+    }
+    if (safe) w0 |= 1u << BRM_CW_LABEL_SAFE_DISTANCE_FRONT;
+    if (t.lane >= 0) {
+      const CwLaneHdr L = B.lanes[t.lane];
+      if (t.s >= L.s_point) w0 |= 1u << BRM_CW_LABEL_MERGED_E;
+      if (L.flags & 1) w0 |= 1u << BRM_CW_LABEL_RIGHTMOST_LANE;
+      w0 |= 1u << BRM_CW_LABEL_ON_ROAD;
+    }
+    const uint32_t front_mask = jf >= 0 ? (1u << jf) : 0u;
+    if (WITH_LABELS) {
+      o.w[0] = w0; o.w[1] = merged_mask; o.w[2] = front_mask; o.w[3] = near_mask;
+    }
+    if (!(B.ego_only && a != 0)) {  // :104-108
+      float rr[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
+      for (int sl = 0; sl < B.R; ++sl) {
+        const brm_rule& rule = B.rules[B.slot_rule[sl]];
+        const int rank = B.slot_rank[sl];
+        const int other = rank < 0 ? 0 : (rank < a ? rank : rank + 1);
+        const int n_aps = rule.n_aps;
+        uint32_t letter = 0;
+        for (int k = 0; k < n_aps; ++k) {
+          const uint32_t kind = rule.ap_label[k];
+          uint32_t val;
+          if (kind < 8) val = (w0 >> kind) & 1u;
+          else if (kind == BRM_CW_LABEL_MERGED_X) val = (merged_mask >> other) & 1u;
+          else if (kind == BRM_CW_LABEL_IN_DIRECT_FRONT_X) val = (front_mask >> other) & 1u;
+          else val = (near_mask >> other) & 1u;
+          letter |= val << (n_aps - 1 - k);
+        }
+        const uint32_t cur = q[sl * col_stride];
+        uint32_t nxt = rule.trans[(cur << n_aps) + letter];
+        if (nxt == BRM_VIOLATION) {
+          viol[sl * col_stride] += 1;
+          nxt = rule.on_violation ? cur : rule.init_state;
+          const int pr = rule.priority;
+#pragma unroll
+          for (int v = 0; v < BRM_MAX_REWARD; ++v)
+            if (v == pr) rr[v] += rule.weight;
+        }
+        q[sl * col_stride] = static_cast<uint8_t>(nxt);
+      }
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) o.r[v] += rr[v];
+    }
+    if (goal) {  // :110-113
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v)
+        if (v == V - 1) o.r[v] += B.goal_reward;
+    }
+    if (coll) t.flags &= ~static_cast<uint32_t>(BRM_CW_VALID);  // :116-120
+  }
+  // CheckTerminal of the new state (:266-285), decided by the ego lane of the group
+  const bool ego_term = !present || horizon_after == 0 || oom || coll || goal;
+  o.terminal = __shfl_sync(0xffffffffu, ego_term ? 1 : 0, base) != 0;
+}
+
+// GetTerminalReward (:148-164) for my agent
+__device__ __forceinline__ void cw_terminal_reward(const CwBlob& B, const CwAgent& t, int a,
+                                                   bool real, const uint8_t* q, int col_stride,
+                                                   float (&r)[BRM_MAX_REWARD]) {
+#pragma unroll
+  for (int v = 0; v < BRM_MAX_REWARD; ++v) r[v] = 0.f;
+  if (!real || a >= B.M || !(t.flags & BRM_CW_PRESENT)) return;
+  for (int sl = 0; sl < B.R; ++sl) {
+    const brm_rule& rule = B.rules[B.slot_rule[sl]];
+    const float pen = rule.accepting[q[sl * col_stride]] ? 0.f : rule.weight;
+    const int pr = rule.priority;
+#pragma unroll
+    for (int v = 0; v < BRM_MAX_REWARD; ++v)
+      if (v == pr) r[v] += pen;
+  }
+}
+
+}  // namespace brm

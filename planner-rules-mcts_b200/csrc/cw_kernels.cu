@@ -1,0 +1,484 @@
+// Continuous-world kernels (sm_100a):
+//   K3 cw_rollout_kernel   fused random rollouts (mvmcts::RandomHeuristic over
+//                          MvmctsState::Execute): lane = agent, floor(32/A) rollouts / warp
+//   K4 cw_execute_kernel   one Execute for n states
+//   K6 cw_replay_kernel    replay of given action sequences with a full trace
+//      cw_query_kernel     CheckTerminal / GetNumActions / GetTerminalReward
+// Every CTA stages the scenario blob of the leaf it works on into shared memory with a
+// TMA bulk copy (re-staged only when the scenario changes).
+#include "common.cuh"
+#include "cw_device.cuh"
+#include "philox.cuh"
+#include "tma.cuh"
+
+namespace brm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// shared memory layout: [blob_cap bytes blob][R*kThreads q][R*kThreads viol]
+struct CwSmem {
+  const CwBlob* B;
+  uint8_t* q;     // this thread's column
+  uint8_t* viol;  // this thread's column
+};
+
+__device__ __forceinline__ CwSmem cw_smem(uint8_t* smem, const CwCommon& c) {
+  CwSmem s;
+  s.B = reinterpret_cast<const CwBlob*>(smem);
+  s.q = smem + c.blob_cap + threadIdx.x;
+  s.viol = smem + c.blob_cap + c.R * kThreads + threadIdx.x;
+  return s;
+}
+
+// (re)stage the blob of scenario `scn`; all threads of the CTA call this together
+__device__ __forceinline__ void cw_stage(uint8_t* smem, uint64_t* bar, const CwCommon& c, int scn,
+                                         int& cur_scn, uint32_t& phase) {
+  if (scn == cur_scn) return;
+  const bool first = cur_scn < 0;
+  __syncthreads();  // everybody is done with the previous blob
+  if (threadIdx.x == 0) {
+    if (first) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const uint32_t bytes = static_cast<uint32_t>(c.blob_bytes[scn]);
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(smem, c.blobs + static_cast<size_t>(scn) * c.blob_stride, bytes, bar);
+  }
+  if (first) __syncthreads();
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  cur_scn = scn;
+}
+
+__device__ __forceinline__ void cw_load_agent(const brm_cw_states& S, int64_t i, int a, bool on,
+                                              CwAgent& t) {
+  t.x = t.y = t.th = t.v = 0.f;
+  t.cs = 1.f;
+  t.sn = 0.f;
+  t.flags = 0;
+  t.lane = -1;
+  t.s = t.lat = 0.f;
+  if (on) {
+    const float4 v = reinterpret_cast<const float4*>(S.agents)[static_cast<int64_t>(a) * S.n + i];
+    t.x = v.x; t.y = v.y; t.th = v.z; t.v = v.w;
+    t.flags = S.flags[static_cast<int64_t>(a) * S.n + i];
+    sincosf(t.th, &t.sn, &t.cs);
+  }
+}
+
+__device__ __forceinline__ void cw_load_rules(const brm_cw_states& S, const CwCommon& c, int64_t i,
+                                              int a, bool on, const CwSmem& sm, bool with_viol) {
+  for (int sl = 0; sl < c.R; ++sl) {
+    uint8_t q = 0, v = 0;
+    if (on && a < c.M) {
+      const int64_t o = (static_cast<int64_t>(a) * c.R + sl) * S.n + i;
+      q = S.q[o];
+      if (with_viol && S.viol) v = static_cast<uint8_t>(S.viol[o]);
+    }
+    sm.q[sl * kThreads] = q;
+    sm.viol[sl * kThreads] = v;
+  }
+}
+
+// ------------------------------------------------------------------ K3 rollout
+struct CwRolloutArgs {
+  CwCommon c;
+  brm_cw_states leaves;
+  brm_cw_rollout_out out;
+  double* part_returns;  // [cta_units*kWarps][M*V]
+  uint64_t seed, rollout_base;
+  int32_t rollouts_per_leaf, max_steps, first_exp;
+  int32_t chunks_per_leaf;  // CTA-units per leaf, each kWarps*G rollouts
+  int64_t cta_units;
+  float gamma;
+};
+
+__global__ void __launch_bounds__(kThreads) cw_rollout_kernel(const CwRolloutArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const CwCommon& c = args.c;
+  const CwSmem sm = cw_smem(smem, c);
+  const CwBlob& B = *sm.B;
+  const int lane = threadIdx.x & 31, widx = threadIdx.x >> 5;
+  const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
+  const int a = lane % A, g = lane / A, base = g * A;
+  const bool real = g < G;
+  int cur_scn = -1;
+  uint32_t phase = 0;
+
+  for (int64_t unit = blockIdx.x; unit < args.cta_units; unit += gridDim.x) {
+    const int64_t leaf = unit / args.chunks_per_leaf;
+    const int chunk = static_cast<int>(unit - leaf * args.chunks_per_leaf);
+    cw_stage(smem, &bar, c, args.leaves.scenario[leaf], cur_scn, phase);
+    const int idx = (chunk * kWarps + widx) * G + g;
+    const bool active = real && idx < args.rollouts_per_leaf;
+    const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
+    const uint64_t rid = args.rollout_base + local;
+
+    CwAgent t;
+    cw_load_agent(args.leaves, leaf, a, active, t);
+    cw_load_rules(args.leaves, c, leaf, a, active, sm, false);
+    if (t.flags & BRM_CW_PRESENT) cw_frenet(B, t);
+    int horizon = args.leaves.horizon[leaf];
+    bool done = !active || args.leaves.terminal[leaf] != 0;
+    float acc[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
+    float disc = args.first_exp ? args.gamma : 1.f;
+    uint32_t agent_steps = 0;
+    int steps = 0;
+    Philox4 blk;
+    blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+    for (int k = 0;; ++k) {
+      const bool live = !done && k < args.max_steps;
+      if (!__any_sync(0xffffffffu, live)) break;
+      const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
+      uint32_t act = 0;
+      if (a < M) {
+        if ((k & 3) == 0) blk = action_block(args.seed, rid, k, a);
+        act = draw_action(pick_word(blk, k), movable ? B.n_prims[a] : 1u);
+      }
+      const float in_v = t.v, in_th = t.th;
+      const uint32_t in_flags = t.flags;
+      if (live && movable) {
+        cw_integrate(B, t, a, act);
+        cw_frenet(B, t);
+        ++agent_steps;
+      }
+      CwStepOut o;
+      cw_evaluate<false>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                         kThreads, o);
+      if (live) {
+#pragma unroll
+        for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * o.r[v];
+        disc *= args.gamma;
+        --horizon;
+        ++steps;
+        if (o.terminal) done = true;
+      }
+    }
+    {
+      float tr[BRM_MAX_REWARD];
+      cw_terminal_reward(B, t, a, active, sm.q, kThreads, tr);
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * tr[v];
+    }
+    // optional per-rollout outputs
+    if (active) {
+      if (a < M) {
+        if (args.out.ro_returns)
+          for (int v = 0; v < V; ++v) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
+        for (int sl = 0; sl < R; ++sl) {
+          if (args.out.ro_viol) args.out.ro_viol[(local * M + a) * R + sl] = sm.viol[sl * kThreads];
+          if (args.out.ro_q) args.out.ro_q[(local * M + a) * R + sl] = sm.q[sl * kThreads];
+        }
+      }
+      if (args.out.ro_agents)
+        reinterpret_cast<float4*>(args.out.ro_agents)[local * A + a] = make_float4(t.x, t.y, t.th, t.v);
+      if (args.out.ro_flags) args.out.ro_flags[local * A + a] = static_cast<uint8_t>(t.flags);
+      if (args.out.ro_steps && a == 0) args.out.ro_steps[local] = steps;
+    }
+    // warp-level reduction over the G rollouts of this warp: lanes of group 0 collect
+    const bool contrib = active && a < M;
+    for (int v = 0; v < V; ++v) {
+      double x = contrib ? static_cast<double>(acc[v]) : 0.0;
+      for (int gg = 1; gg < G; ++gg) {
+        const double y = __shfl_sync(0xffffffffu, x, (lane + gg * A) & 31);
+        if (g == 0) x += y;
+      }
+      // careful: x of group 0 must not be polluted before others read theirs: lanes of
+      // group gg only ever read, group 0 only accumulates values of groups > 0
+      if (g == 0 && a < M) args.part_returns[(unit * kWarps + widx) * (M * V) + a * V + v] = x;
+    }
+    if (args.out.viol_sum) {
+      for (int sl = 0; sl < R; ++sl) {
+        uint32_t x = contrib ? sm.viol[sl * kThreads] : 0u;
+        for (int gg = 1; gg < G; ++gg) {
+          const uint32_t y = __shfl_sync(0xffffffffu, x, (lane + gg * A) & 31);
+          if (g == 0) x += y;
+        }
+        if (g == 0 && a < M && x)
+          atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + a) * R + sl]),
+                    static_cast<unsigned long long>(x));
+      }
+    }
+    if (args.out.agent_steps) {
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, agent_steps);
+      if (lane == 0 && tot)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
+                  static_cast<unsigned long long>(tot));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K4 / K6 / queries
+// states are mapped G per warp, lane = agent
+struct CwBatchArgs {
+  CwCommon c;
+  brm_cw_states in, out;
+  const uint8_t* actions;  // execute: [M][n]; replay: [B][T][M]
+  float* rewards;          // execute: [M][V][n]
+  // queries
+  uint8_t* num_actions;    // [M][n]
+  float* term_reward;      // [M][V][n]
+  int32_t do_check_terminal;
+  // replay
+  int32_t T;
+  brm_cw_trace tr;
+  int64_t warp_units;  // ceil(n / G)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const CwCommon& c = args.c;
+  const CwSmem sm = cw_smem(smem, c);
+  const CwBlob& B = *sm.B;
+  const int lane = threadIdx.x & 31, widx = threadIdx.x >> 5;
+  const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
+  const int a = lane % A, g = lane / A, base = g * A;
+  const bool real = g < G;
+  const int64_t n = args.in.n;
+  int cur_scn = -1;
+  uint32_t phase = 0;
+  // A CTA walks over blocks of kWarps*G consecutive states; all states of one block must
+  // live in the same scenario for the shared blob, so the host sorts / groups batches by
+  // scenario and pads: here we simply re-stage per warp-unit when needed.
+  const int64_t cta_units = (args.warp_units + kWarps - 1) / kWarps;
+  for (int64_t cu = blockIdx.x; cu < cta_units; cu += gridDim.x) {
+    const int64_t first_state = cu * kWarps * G;
+    cw_stage(smem, &bar, c, args.in.scenario[first_state < n ? first_state : n - 1], cur_scn, phase);
+    const int64_t i = (cu * kWarps + widx) * G + g;
+    const bool on = real && i < n;
+    const int64_t ii = on ? i : 0;
+    CwAgent t;
+    cw_load_agent(args.in, ii, a, on, t);
+    cw_load_rules(args.in, c, ii, a, on, sm, true);
+    if (t.flags & BRM_CW_PRESENT) cw_frenet(B, t);
+    int horizon = on ? args.in.horizon[ii] : 0;
+
+    if (MODE == MODE_QUERY) {
+      if (args.do_check_terminal) {
+        // CheckTerminal (:266-285) for the ego of each state
+        float cx[4], cy[4];
+        cw_corners(B, t, a, cx, cy);
+        const bool present = on && (t.flags & BRM_CW_PRESENT);
+        bool coll = false;
+        for (int j = 0; j < A; ++j) {
+          const CwPeer p = cw_fetch(t, base + j);
+          if (j == a || !(p.flags & BRM_CW_PRESENT) || !present) continue;
+          coll = cw_rect_overlap(B, t, a, p, j) || coll;
+        }
+        if (on && a == 0) {
+          const bool term = !present || horizon == 0 || cw_out_of_map(B, t, a, cx, cy) || coll ||
+                            cw_at_goal(B, t, a, cx, cy);
+          args.in.terminal[i] = term ? 1 : 0;
+        }
+      }
+      if (on && a < M) {
+        if (args.num_actions) {
+          const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
+          args.num_actions[static_cast<int64_t>(a) * n + i] = movable ? B.n_prims[a] : 1;
+        }
+        if (args.term_reward) {
+          float tr[BRM_MAX_REWARD];
+          cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
+          for (int v = 0; v < V; ++v) args.term_reward[(static_cast<int64_t>(a) * V + v) * n + i] = tr[v];
+        }
+      }
+      continue;
+    }
+
+    if (MODE == MODE_EXECUTE) {
+      const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
+      uint32_t act = 0;
+      if (on && a < M) act = args.actions[static_cast<int64_t>(a) * n + i];
+      if (!movable) act = 0;
+      const float in_v = t.v, in_th = t.th;
+      const uint32_t in_flags = t.flags;
+      if (on && movable) {
+        cw_integrate(B, t, a, act);
+        cw_frenet(B, t);
+      }
+      CwStepOut o;
+      cw_evaluate<false>(B, t, a, base, real, on, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                         kThreads, o);
+      if (on) {
+        reinterpret_cast<float4*>(args.out.agents)[static_cast<int64_t>(a) * n + i] =
+            make_float4(t.x, t.y, t.th, t.v);
+        args.out.flags[static_cast<int64_t>(a) * n + i] = static_cast<uint8_t>(t.flags);
+        if (a == 0) {
+          args.out.horizon[i] = horizon - 1;
+          args.out.terminal[i] = o.terminal ? 1 : 0;
+          args.out.scenario[i] = args.in.scenario[i];
+        }
+        if (a < M) {
+          for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = o.r[v];
+          for (int sl = 0; sl < R; ++sl) {
+            const int64_t off = (static_cast<int64_t>(a) * R + sl) * n + i;
+            args.out.q[off] = sm.q[sl * kThreads];
+            if (args.out.viol) {
+              const uint32_t prev = args.in.viol ? args.in.viol[off] : 0u;
+              const uint32_t inc = static_cast<uint8_t>(sm.viol[sl * kThreads] - static_cast<uint8_t>(prev));
+              args.out.viol[off] = prev + inc;
+            }
+          }
+        }
+      }
+      continue;
+    }
+
+    if (MODE == MODE_REPLAY) {
+      const int T = args.T;
+      bool done = !on || args.in.terminal[ii] != 0;
+      int steps = 0;
+      uint32_t viol32[BRM_CW_MAX_SLOTS];
+      for (int sl = 0; sl < BRM_CW_MAX_SLOTS; ++sl) viol32[sl] = 0;
+      for (int sl = 0; sl < R; ++sl) sm.viol[sl * kThreads] = 0;
+      for (int k = 0; k < T; ++k) {
+        const bool live = !done;
+        if (!__any_sync(0xffffffffu, live)) break;
+        const int64_t bt = ii * T + k;
+        const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
+        uint32_t act = 0;
+        if (live && a < M && movable) act = args.actions[bt * M + a];
+        const float in_v = t.v, in_th = t.th;
+        const uint32_t in_flags = t.flags;
+        if (live && movable) {
+          cw_integrate(B, t, a, act);
+          cw_frenet(B, t);
+        }
+        CwStepOut o;
+        cw_evaluate<true>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                          kThreads, o);
+        if (live) {
+          --horizon;
+          ++steps;
+          reinterpret_cast<float4*>(args.tr.agents_out)[bt * A + a] = make_float4(t.x, t.y, t.th, t.v);
+          args.tr.flags_out[bt * A + a] = static_cast<uint8_t>(t.flags);
+          float* fo = args.tr.frenet_out + (bt * A + a) * 3;
+          fo[0] = static_cast<float>(t.lane);
+          fo[1] = t.s;
+          fo[2] = t.lat;
+          if (a == 0) args.tr.terminal_out[bt] = o.terminal ? 1 : 0;
+          if (a < M) {
+            for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = o.r[v];
+            for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = o.w[w];
+            for (int sl = 0; sl < R; ++sl) {
+              viol32[sl] += sm.viol[sl * kThreads];
+              sm.viol[sl * kThreads] = 0;
+              args.tr.q_out[(bt * M + a) * R + sl] = sm.q[sl * kThreads];
+              args.tr.viol_out[(bt * M + a) * R + sl] = viol32[sl];
+            }
+          }
+          if (o.terminal) done = true;
+        }
+      }
+      if (on) {
+        if (a == 0) args.tr.steps_out[i] = steps;
+        if (a < M) {
+          float tr[BRM_MAX_REWARD];
+          cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
+          for (int v = 0; v < V; ++v) args.tr.term_reward_out[(i * M + a) * V + v] = tr[v];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t nvals,
+                        double* out, int32_t n_leaves);
+
+int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, const brm_cw_states& leaves,
+                      const brm_rollout_params& rp, const brm_cw_rollout_out& out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cw_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  CwRolloutArgs a;
+  a.c = ctx.c;
+  a.leaves = leaves;
+  a.out = out;
+  a.seed = rp.seed;
+  a.rollout_base = rp.rollout_base;
+  a.rollouts_per_leaf = rp.rollouts_per_leaf;
+  a.max_steps = rp.max_steps;
+  a.first_exp = rp.first_discount_exp;
+  a.gamma = static_cast<float>(rp.discount_factor);
+  const int per_cta = kWarps * ctx.c.G;
+  a.chunks_per_leaf = (rp.rollouts_per_leaf + per_cta - 1) / per_cta;
+  a.cta_units = static_cast<int64_t>(leaves.n) * a.chunks_per_leaf;
+  const int M = ctx.c.M, V = ctx.c.V, R = ctx.c.R;
+  const size_t part_bytes = static_cast<size_t>(a.cta_units) * kWarps * M * V * sizeof(double);
+  int rc = e->ensure_ws(part_bytes);
+  if (rc != BRM_OK) return rc;
+  a.part_returns = static_cast<double*>(e->d_ws);
+  if (out.viol_sum)
+    BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
+                                   e->stream));
+  if (out.agent_steps)
+    BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
+                                   e->stream));
+  int64_t grid = a.cta_units;
+  const int64_t cap = static_cast<int64_t>(e->sm_count) * 4;
+  if (grid > cap) grid = cap;
+  e->time_begin();
+  cw_rollout_kernel<<<static_cast<int>(grid), kThreads, ctx.smem_bytes, e->stream>>>(a);
+  e->launches++;
+  launch_leaf_reduce(e, a.part_returns, a.chunks_per_leaf * kWarps, M * V, out.returns_sum, leaves.n);
+  e->time_end();
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+static int64_t batch_grid(const brm_engine* e, int64_t warp_units) {
+  int64_t grid = (warp_units + kWarps - 1) / kWarps;
+  const int64_t cap = static_cast<int64_t>(e->sm_count) * 4;
+  if (grid > cap) grid = cap;
+  return grid < 1 ? 1 : grid;
+}
+
+int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_cw_states& in,
+                    const brm_cw_states* out, const uint8_t* actions, float* rewards,
+                    uint8_t* num_actions, float* term_reward, int do_check_terminal, int32_t T,
+                    const brm_cw_trace* tr) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(cw_batch_kernel<MODE_EXECUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_batch_kernel<MODE_QUERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_batch_kernel<MODE_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  CwBatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.c = ctx.c;
+  a.in = in;
+  if (out) a.out = *out;
+  a.actions = actions;
+  a.rewards = rewards;
+  a.num_actions = num_actions;
+  a.term_reward = term_reward;
+  a.do_check_terminal = do_check_terminal;
+  a.T = T;
+  if (tr) a.tr = *tr;
+  a.warp_units = (static_cast<int64_t>(in.n) + ctx.c.G - 1) / ctx.c.G;
+  const int grid = static_cast<int>(batch_grid(e, a.warp_units));
+  if (mode == MODE_EXECUTE)
+    cw_batch_kernel<MODE_EXECUTE><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
+  else if (mode == MODE_QUERY)
+    cw_batch_kernel<MODE_QUERY><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
+  else
+    cw_batch_kernel<MODE_REPLAY><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
+  e->launches++;
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+
+}  // namespace brm

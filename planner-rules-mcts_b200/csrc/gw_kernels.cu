@@ -395,6 +395,13 @@ int grid_for(const brm_engine* e, int64_t threads_needed, int block, int ctas_pe
 
 }  // namespace
 
+// second-stage reduction shared with the continuous-world rollout kernel
+void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t nvals,
+                        double* out, int32_t n_leaves) {
+  leaf_reduce_kernel<<<n_leaves, 128, 0, e->stream>>>(part, per_leaf, nvals, out);
+  e->launches++;
+}
+
 // ---- launch wrappers used by gw_engine.cu (all pointers are device pointers here) ----
 
 int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_rollout_params& rp,
@@ -429,9 +436,7 @@ int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_roll
   rc = dispatch_agents<RolloutLauncher>(A, e, a, grid);
   if (rc != BRM_OK) return rc;
   e->launches++;
-  leaf_reduce_kernel<<<leaves.n, 128, 0, e->stream>>>(a.part_returns, a.warps_per_leaf, A * V,
-                                                      out.returns_sum);
-  e->launches++;
+  launch_leaf_reduce(e, a.part_returns, a.warps_per_leaf, A * V, out.returns_sum, leaves.n);
   e->time_end();
   BRM_CUDA_CHECK(cudaGetLastError());
   return BRM_OK;

@@ -1,0 +1,268 @@
+"""GPU parity tests of the continuous-world path (MvmctsState on the device), all through
+the C ABI: CUDA kernels vs the FP64 CPU oracle on replayed action sequences and on
+Philox-driven rollouts.  Policy (tests/cw_common.py): kinematics/rewards within 1e-5
+relative; labels, automaton states, violation counts, flags bit-exact wherever no threshold
+comparison of the oracle came within GUARD of flipping."""
+import numpy as np
+import pytest
+
+import planner_rules_mcts_b200 as brm
+from oracle import cw as ocw
+from planner_rules_mcts_b200 import scenarios
+from planner_rules_mcts_b200.ltl import RuleMonitor
+from tests.cw_common import ATOL_POS, GUARD, close, compare_trace, oracle_config
+
+pytestmark = pytest.mark.gpu
+
+FL = lambda n: np.full(n, ocw.PRESENT | ocw.VALID, np.uint8)
+
+
+@pytest.fixture(scope="module")
+def orc(built):
+    return ocw.CwOracle()
+
+
+def replay_both(eng, orc, scn, acts, states=None, flags=None, horizon=None):
+    B = acts.shape[0]
+    A = len(scn.agents)
+    states = np.broadcast_to(scn.initial_state, (B, A, 4)) if states is None else states
+    flags = np.broadcast_to(FL(A), (B, A)) if flags is None else flags
+    horizon = scn.params.HORIZON if horizon is None else horizon
+    batch = eng.make_batch(states, flags=flags, horizon=horizon)
+    tr = eng.replay(batch, acts)
+    cfg = oracle_config(scn)
+    outs = [orc.replay(cfg, states[b], flags[b], horizon, acts[b]) for b in range(B)]
+    return tr, outs, batch
+
+
+def test_reference_pins_single_agent(built, orc):
+    """test/single_agent_test.cpp:136-173 through the StateInterface mirror on the GPU."""
+    scn = scenarios.straight_road_test_world()
+    eng = brm.RulesMctsEngine([scn], device=0)
+    s0 = brm.MvmctsState(eng)
+    assert not s0.IsTerminal() and s0.GetNumActions(0) == 3 and s0.GetAgentIdx() == [0]
+    rewards = []
+    s1 = s0.Execute([0], rewards)
+    total = rewards[0] + s1.GetTerminalReward()[0]
+    assert not s1.IsTerminal() and abs(total[0]) < 1e-5
+    s2 = s1.Execute([1], rewards)
+    total = total + rewards[0] + s2.GetTerminalReward()[0]
+    assert s2.IsTerminal() and abs(total[0] + 800.0) < 1e-5
+    s3 = s0.Execute([2], rewards)
+    assert s3.IsTerminal() and abs(rewards[0][0] + s3.GetTerminalReward()[0][0] + 1000.0) < 1e-5
+    assert s3.GetNumActions(0) == 1
+    with pytest.raises(brm.BrmError) as ei:  # BARK_EXPECT_TRUE(!IsTerminal()), src/rules_mcts_state.cpp:59
+        s3.Execute([0], rewards)
+    assert ei.value.code == brm._abi.ERR_TERMINAL
+    s = s0.Execute([0], rewards)
+    for _ in range(200):
+        if s.IsTerminal():
+            break
+        s = s.Execute([0], rewards)
+    assert s.IsTerminal() and 20.0 <= s.GetAgentStates()[0, 0] - 1.0 and s.GetAgentStates()[0, 0] + 3.0 <= 27.0
+
+
+def test_reference_pins_multi_agent(built, orc):
+    """test/multi_agent_test.cpp:115-139: 3 actions before, 1 after the collision, frozen positions."""
+    scn = scenarios.straight_road_test_world(n_others=2, ego_velocity=0.0, velocity_difference=-3.0,
+                                             multi_agent=True, primitives=[(0.0, 0.0), (50.0, 1.0), (4.0, 0.0)],
+                                             rules=[RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)])
+    scn.initial_state[1] = (10.0, -1.75, 0.0, 3.0)
+    scn.initial_state[2] = (14.1, -1.75, 0.0, 3.0)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    s = brm.MvmctsState(eng)
+    assert s.GetNumActions(2) == 3 and s.GetNumActions(1) == 3
+    rewards = []
+    s2 = s.Execute([0, 2, 0], rewards)
+    assert s2.GetNumActions(1) == 1 and s2.GetNumActions(2) == 1 and s2.GetNumActions(0) == 3
+    assert rewards[1][0] == -1000.0 and rewards[2][0] == -1000.0 and rewards[0][0] == 0.0
+    s3 = s2.Execute([0, 0, 0], rewards)
+    assert s3.GetNumActions(1) == 1 and s3.GetNumActions(2) == 1
+    assert np.array_equal(s3.GetAgentStates()[1:], s2.GetAgentStates()[1:])
+    assert rewards[1][0] == 0.0 and rewards[2][0] == 0.0  # INVALID agents are not evaluated (:83)
+
+
+@pytest.mark.parametrize("name", ["highway", "merge", "intersection", "test_world"])
+def test_replay_matches_oracle(built, orc, name):
+    scn = {"highway": scenarios.highway_scenario, "merge": scenarios.merge_scenario,
+           "intersection": scenarios.intersection_scenario,
+           "test_world": lambda: scenarios.straight_road_test_world(
+               n_others=2, multi_agent=True, primitives=[(0.0, 0.0), (3.0, 0.05), (-2.0, -0.05), (4.0, 0.0)])}[name]()
+    p = scn.params
+    p.ACCELERATION_WEIGHT, p.RADIAL_ACCELERATION_WEIGHT, p.LANE_CENTER_WEIGHT = -0.5, -1.0, -2.0
+    p.GOAL_REWARD, p.COLLISION_WEIGHT = 100.0, -50.0
+    eng = brm.RulesMctsEngine([scn], device=0)
+    rng = np.random.default_rng(11)
+    B, T = 96, 22
+    n_act = len(scn.agents[0].primitives)
+    acts = rng.integers(0, n_act, size=(B, T, scn.n_mcts_agents)).astype(np.uint8)
+    tr, outs, _ = replay_both(eng, orc, scn, acts)
+    compared = total = full = 0
+    for b, o in enumerate(outs):
+        c = compare_trace(tr, b, o, scn)
+        compared += c
+        total += o["steps"]
+        full += c == o["steps"]
+    assert total > 3 * B  # traces are not trivially short
+    assert compared >= 0.9 * total and full >= 0.8 * B, (compared, total, full)
+
+
+def test_replay_perturbed_states_and_flags(built, orc):
+    """Random start states (incl. collided / absent agents, partially advanced automata)."""
+    scn = scenarios.merge_scenario(seed=5)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    rng = np.random.default_rng(2)
+    B, T, A = 128, 12, 4
+    states = np.broadcast_to(scn.initial_state, (B, A, 4)).copy()
+    states[:, :, 0] += rng.uniform(-15, 25, size=(B, A))
+    states[:, :, 3] += rng.uniform(-4, 4, size=(B, A))
+    flags = np.broadcast_to(FL(A), (B, A)).copy()
+    flags[rng.random((B, A)) < 0.1] = ocw.PRESENT          # already collided (INVALID)
+    flags[:, 1:][rng.random((B, A - 1)) < 0.05] = 0         # absent
+    flags[:, 0] |= ocw.PRESENT
+    acts = rng.integers(0, 3, size=(B, T, A)).astype(np.uint8)
+    tr, outs, batch = replay_both(eng, orc, scn, acts, states, flags, 9)
+    cfg = oracle_config(scn)
+    n_term0 = 0
+    for b, o in enumerate(outs):
+        t0 = orc.check_terminal(cfg, states[b], flags[b], 9)
+        assert bool(batch.terminal[b]) == t0
+        n_term0 += t0
+        compare_trace(tr, b, o, scn)
+    assert 0 < n_term0 < B
+
+
+def test_execute_batch_matches_replay(built, orc):
+    """K4: batched Execute chained 3 times == replay; GetNumActions / GetTerminalReward."""
+    scn = scenarios.merge_scenario(seed=9)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    rng = np.random.default_rng(4)
+    n, A = 300, 4
+    states = np.broadcast_to(scn.initial_state, (n, A, 4)).copy()
+    states[:, :, 0] += rng.uniform(-10, 10, size=(n, A))
+    batch = eng.make_batch(states)
+    keep = np.flatnonzero(batch.terminal == 0)
+    batch = batch.select(keep)
+    acts = rng.integers(0, 3, size=(len(keep), 3, A)).astype(np.uint8)
+    tr = eng.replay(batch, acts)
+    cur = batch
+    alive = np.arange(len(keep))
+    for t in range(3):
+        nb, rew = eng.execute(cur, acts[alive, t].T.copy())
+        assert np.array_equal(nb.agents.transpose(1, 0, 2), tr["agents_out"][alive, t])
+        assert np.array_equal(nb.flags.T, tr["flags_out"][alive, t])
+        assert np.array_equal(nb.q.transpose(2, 0, 1), tr["q_out"][alive, t])
+        assert np.array_equal(nb.viol.transpose(2, 0, 1), tr["viol_out"][alive, t])
+        assert np.array_equal(rew.transpose(2, 0, 1), tr["rewards_out"][alive, t])
+        assert np.array_equal(nb.terminal, tr["terminal_out"][alive, t])
+        assert np.all(nb.horizon == scn.params.HORIZON - t - 1)
+        na = eng.get_num_actions(nb)
+        movable = (nb.flags & 3) == 3
+        assert np.array_equal(na, np.where(movable, 3, 1))
+        assert eng.terminal_reward(nb).shape == (A, 3, nb.n)
+        sel = np.flatnonzero(nb.terminal == 0)
+        cur, alive = nb.select(sel), alive[sel]
+        if len(sel) == 0:
+            break
+    with pytest.raises(brm.BrmError):
+        term = nb.select(np.flatnonzero(nb.terminal != 0)[:1]) if (nb.terminal != 0).any() else None
+        if term is None:
+            raise brm.BrmError(-4, "no terminal state to test")
+        eng.execute(term, np.zeros((A, 1), np.uint8))
+
+
+@pytest.mark.parametrize("name,n", [("merge", 4096), ("highway", 2048), ("intersection", 300)])
+def test_rollout_per_rollout_outputs_match_oracle(built, orc, name, n):
+    """K3 with Philox actions vs the oracle's rollouts, rollout by rollout."""
+    scn = {"highway": scenarios.highway_scenario, "merge": scenarios.merge_scenario,
+           "intersection": scenarios.intersection_scenario}[name](seed=21)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    cfg = oracle_config(scn)
+    A = len(scn.agents)
+    leaves = eng.initial_batch()
+    out = eng.rollout(leaves, n, seed=77, rollout_base=1000, max_steps=30, detail=True)
+    ref = orc.rollout_detail(cfg, scn.initial_state, FL(A), scn.params.HORIZON, 77, 1000, n, 30,
+                             scn.params.DISCOUNT_FACTOR)
+    safe = ref["margin"] >= GUARD
+    assert safe.mean() > 0.5
+    same = ((out["ro_steps"] == ref["steps"]) & (out["ro_viol"] == ref["viol"]).all(axis=(1, 2)) &
+            (out["ro_q"] == ref["q"]).all(axis=(1, 2)) & (out["ro_flags"] == ref["flags"]).all(axis=1))
+    assert same[safe].all(), "discrete outputs differ on %d rollouts with a safe margin" % (~same[safe]).sum()
+    assert same.mean() > 0.995, "too many fp32-sensitive rollouts differ: %d of %d" % ((~same).sum(), n)
+    assert close(out["ro_agents"][same], ref["states"][same], atol=ATOL_POS)
+    assert close(out["ro_returns"][same], ref["returns"][same], rtol=2e-5, atol=2e-3)
+    # aggregates
+    agg = orc.rollout(cfg, scn.initial_state, FL(A), scn.params.HORIZON, 77, 1000, n, 30,
+                      scn.params.DISCOUNT_FACTOR, n_threads=4)
+    if same.all():
+        assert int(out["agent_steps"][0]) == agg["agent_steps"]
+        assert np.array_equal(out["viol_sum"][0], agg["viol_sum"])
+    assert abs(int(out["agent_steps"][0]) - agg["agent_steps"]) <= 0.01 * agg["agent_steps"]
+    np.testing.assert_allclose(out["returns_sum"][0], out["ro_returns"].astype(np.float64).sum(0), rtol=1e-6, atol=1e-3)
+    np.testing.assert_allclose(out["returns_sum"][0], agg["returns_sum"], rtol=5e-3, atol=2.0)
+    assert np.array_equal(out["viol_sum"][0], out["ro_viol"].astype(np.uint64).sum(0))
+
+
+def test_multi_scenario_sweep_and_determinism(built, orc):
+    """Config W shape: several scenarios in one rollout call, 64 rollouts each."""
+    scns = [scenarios.intersection_scenario(seed=1000, scenario_id=k) for k in range(6)]
+    eng = brm.RulesMctsEngine(scns, device=0)
+    leaves = eng.initial_batch()
+    assert leaves.n == 6 and list(leaves.scenario) == list(range(6))
+    a = eng.rollout(leaves, 64, seed=3, detail=True)
+    b = eng.rollout(leaves, 64, seed=3, detail=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    for k, scn in enumerate(scns):
+        cfg = oracle_config(scn)
+        ref = orc.rollout_detail(cfg, scn.initial_state, FL(10), 20, 3, k * 64, 64, 30, 0.9)
+        sl = slice(k * 64, (k + 1) * 64)
+        safe = ref["margin"] >= GUARD
+        same = (a["ro_steps"][sl] == ref["steps"]) & (a["ro_viol"][sl] == ref["viol"]).all(axis=(1, 2))
+        assert same[safe].all()
+    assert len({float(x) for x in a["returns_sum"][:, 0, 3]}) == 6  # scenarios really differ
+
+
+def test_full_size_properties(built):
+    """BASELINE config M size (262144 rollouts/decision): split invariance, device path ==
+    host path, counts add up."""
+    import torch
+    scn = scenarios.merge_scenario(seed=1000)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    L, n = 64, 4096
+    rng = np.random.default_rng(0)
+    states = np.broadcast_to(scn.initial_state, (L, 4, 4)).copy()
+    states[:, :, 0] += rng.uniform(-5, 5, size=(L, 4))
+    leaves = eng.make_batch(states)
+    full = eng.rollout(leaves, n, seed=1000, max_steps=20)
+    assert full["agent_steps"].sum() <= L * n * 20 * 4
+    half = [eng.rollout(leaves.select([l]), n // 2, seed=1000, max_steps=20, rollout_base=l * n + h * (n // 2))
+            for l in range(4) for h in range(2)]
+    for l in range(4):
+        a, b = half[2 * l], half[2 * l + 1]
+        assert np.array_equal(a["viol_sum"][0] + b["viol_sum"][0], full["viol_sum"][l])
+        assert int(a["agent_steps"][0] + b["agent_steps"][0]) == int(full["agent_steps"][l])
+        np.testing.assert_allclose(a["returns_sum"][0] + b["returns_sum"][0], full["returns_sum"][l], rtol=1e-9, atol=1e-6)
+    dl = leaves.cuda(0)
+    out = dict(returns_sum=torch.zeros((L, 4, 3), dtype=torch.float64, device="cuda"),
+               viol_sum=torch.zeros((L, 4, eng.R), dtype=torch.int64, device="cuda"),
+               agent_steps=torch.zeros(L, dtype=torch.int64, device="cuda"))
+    eng.rollout(dl, n, seed=1000, max_steps=20, out=out)
+    eng.engine.synchronize()
+    assert np.array_equal(out["returns_sum"].cpu().numpy(), full["returns_sum"])
+    assert np.array_equal(out["viol_sum"].cpu().numpy().astype(np.uint64), full["viol_sum"])
+    assert np.array_equal(out["agent_steps"].cpu().numpy().astype(np.uint64), full["agent_steps"])
+
+
+def test_errors(built):
+    scn = scenarios.merge_scenario()
+    eng = brm.RulesMctsEngine([scn], device=0)
+    with pytest.raises(brm.BrmError):
+        eng.rollout(eng.initial_batch(), 0)
+    bad = scenarios.merge_scenario()
+    bad.rules = [RuleMonitor.MakeRule("G !collision_ego", -1.0, 5)]  # priority >= V
+    with pytest.raises(brm.BrmError):
+        brm.RulesMctsEngine([bad], device=0)
+    other = scenarios.highway_scenario()
+    with pytest.raises(brm.BrmError):
+        brm.RulesMctsEngine([scn, other], device=0)  # shapes differ

@@ -110,19 +110,27 @@ def test_state_interface_mirror(built):
     """GridWorldState.Execute / GetNumActions / IsTerminal / GetTerminalReward, used the way
     gridworld/test_runner.cpp:28-42 drives the reference."""
     eng = make_engine(3, 8)
+    cfg = oracle_config_from_engine(eng)
+    port = ogw.GwOracle("port")
     s = brm.GridWorldState(eng)
     assert s.GetAgentIdx() == [0, 1, 2] and not s.IsTerminal() and s.GetNumActions(0) == 3
     rewards = []
     steps = 0
+    # ego waits twice so that it reaches the merge point together with agent 2 -> collision
+    plan = [[1, 0, 0], [1, 0, 0]] + [[0, 0, 0]] * 18
+    agents, term, q = s.GetAgentStates(), np.zeros(3, np.uint8), s.GetRuleStates()
     while not s.IsTerminal() and steps < 20:
-        s = s.Execute([0, 0, 0], rewards)  # everybody FORWARD
-        s.ResetDepth()
+        o = port.replay(cfg, agents, term, 0, np.array([plan[steps]], np.uint8), q0=q)
+        s = s.Execute(plan[steps], rewards)
+        s.ResetDepth()  # closed loop of gridworld/test_runner.cpp:37-38
+        agents, term, q = o["agents"][0], o["term"][0], o["q"][0]
+        assert np.array_equal(s.GetAgentStates(), agents) and np.array_equal(s.GetRuleStates(), q)
+        assert np.array_equal(np.array(rewards), o["rewards"][0])
         steps += 1
-    # all FORWARD: 0 and 1 share a lane, 2 merges from the other lane; 0 and 2 reach the merge
-    # point region together -> ego collision ends the episode
-    assert s.IsTerminal() and len(rewards) == 3 and rewards[0].shape == (3,)
+    assert s.IsTerminal() and steps == 8 and len(rewards) == 3 and rewards[0].shape == (3,)
+    assert rewards[0][0] == -1.0  # `G !collision` violated by the ego, weight -1 at priority 0
     assert s.GetNumActions(0) == 1
-    assert s.PrintState().startswith("Ego: x=")
+    assert s.PrintState().startswith("Ego: x=8")
     tr = s.GetTerminalReward()
     assert len(tr) == 3 and all(np.all(t == 0) for t in tr)  # safety monitors: no final penalty
 
