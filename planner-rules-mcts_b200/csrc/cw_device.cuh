@@ -64,6 +64,7 @@ struct CwAgent {
   uint32_t flags;   // BRM_CW_PRESENT | BRM_CW_VALID
   int lane;         // lane index of the current position (-1: none)
   float s, lat;
+  float ex, ey, eth, ev;  // Kahan compensation of x, y, th, v (carried across steps)
 };
 
 struct CwStepOut {
@@ -72,32 +73,46 @@ struct CwStepOut {
   bool terminal;  // state-level (group-uniform)
 };
 
+// compensated (Kahan) accumulation: sum += term with the rounding error carried in `c`.
+// The reference integrates in double; fp32 states that simply accumulate 15 sub-steps per
+// step drift by ~1e-4 m over a rollout, which is visible in rewards that difference two
+// nearly equal speeds.  With the compensation the fp32 state stays within ~1 ulp of the
+// exactly accumulated value.
+__device__ __forceinline__ void kahan_add(float& sum, float& c, float term) {
+  const float y = term - c;
+  const float t = sum + y;
+  c = (t - sum) - y;
+  sum = t;
+}
+
 __device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a, uint32_t prim) {
   const float acc = B.prim_a[a][prim];
   const float k = B.prim_k[a][prim];
   float x = t.x, y = t.y, th = t.th, v = t.v;
+  float ex = t.ex, ey = t.ey, eth = t.eth, ev = t.ev;
   float cs = t.cs, sn = t.sn;
   const int n_sub = B.n_sub;
   if (k == 0.0f) {
     // no steering: theta stays bit-identical, so cos/sin are loop invariants
     for (int n = 0; n < n_sub; ++n) {
       const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
-      x = x + h * (v * cs);
-      y = y + h * (v * sn);
-      v = v + h * acc;
+      kahan_add(x, ex, h * (v * cs));
+      kahan_add(y, ey, h * (v * sn));
+      kahan_add(v, ev, h * acc);
     }
   } else {
     for (int n = 0; n < n_sub; ++n) {
       const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
       if (n > 0) sincosf(th, &sn, &cs);
-      x = x + h * (v * cs);
-      y = y + h * (v * sn);
-      th = th + h * (v * k);
-      v = v + h * acc;
+      kahan_add(x, ex, h * (v * cs));
+      kahan_add(y, ey, h * (v * sn));
+      kahan_add(th, eth, h * (v * k));
+      kahan_add(v, ev, h * acc);
     }
     sincosf(th, &sn, &cs);
   }
   t.x = x; t.y = y; t.th = th; t.v = v; t.cs = cs; t.sn = sn;
+  t.ex = ex; t.ey = ey; t.eth = eth; t.ev = ev;
 }
 
 // nearest point on every lane centre line, first lane that contains the point wins

@@ -63,6 +63,7 @@ __device__ __forceinline__ void cw_load_agent(const brm_cw_states& S, int64_t i,
   t.flags = 0;
   t.lane = -1;
   t.s = t.lat = 0.f;
+  t.ex = t.ey = t.eth = t.ev = 0.f;
   if (on) {
     const float4 v = reinterpret_cast<const float4*>(S.agents)[static_cast<int64_t>(a) * S.n + i];
     t.x = v.x; t.y = v.y; t.th = v.z; t.v = v.w;

@@ -9,8 +9,8 @@ from oracle import cw as ocw
 # wherever the oracle's smallest threshold margin exceeds GUARD (fp32 rounding of a ~300 m
 # coordinate is ~3e-5 m; positions accumulate a few ulps over the sub-steps).
 RTOL = 1e-5
-ATOL_POS = 2e-3      # metres, absolute floor for coordinates near 0
-GUARD = 1e-3
+ATOL_POS = 2e-4      # metres (fp32 ulp of a 300 m coordinate is 3e-5)
+GUARD = 5e-4
 
 
 def oracle_config(scn, precision=0):
@@ -117,7 +117,7 @@ def compare_trace(tr, b, o, scn, min_exact_frac=0.0):
         assert np.array_equal(tr["frenet_out"][b, t, :, 0], o["frenet"][t, :, 0]), ("lane", b, t)
         assert close(tr["agents_out"][b, t], o["states"][t], atol=ATOL_POS), ("state", b, t)
         assert close(tr["frenet_out"][b, t, :, 1:], o["frenet"][t, :, 1:], atol=ATOL_POS), ("frenet", b, t)
-        assert close(tr["rewards_out"][b, t], o["rewards"][t], rtol=1e-5, atol=1e-3), ("rewards", b, t)
+        assert close(tr["rewards_out"][b, t], o["rewards"][t], rtol=1e-5, atol=2e-4), ("rewards", b, t)
     if safe == k:
         assert close(tr["term_reward_out"][b], o["term_reward"], atol=1e-6)
     return safe

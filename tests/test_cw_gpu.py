@@ -149,11 +149,15 @@ def test_execute_batch_matches_replay(built, orc):
     alive = np.arange(len(keep))
     for t in range(3):
         nb, rew = eng.execute(cur, acts[alive, t].T.copy())
-        assert np.array_equal(nb.agents.transpose(1, 0, 2), tr["agents_out"][alive, t])
+        # the replay kernel carries the Kahan compensation of the integrator across steps, a
+        # chain of single Executes restarts it every step: identical at t = 0, ~1 ulp later
+        if t == 0:
+            assert np.array_equal(nb.agents.transpose(1, 0, 2), tr["agents_out"][alive, t])
+        assert np.allclose(nb.agents.transpose(1, 0, 2), tr["agents_out"][alive, t], rtol=1e-6, atol=1e-5)
         assert np.array_equal(nb.flags.T, tr["flags_out"][alive, t])
         assert np.array_equal(nb.q.transpose(2, 0, 1), tr["q_out"][alive, t])
         assert np.array_equal(nb.viol.transpose(2, 0, 1), tr["viol_out"][alive, t])
-        assert np.array_equal(rew.transpose(2, 0, 1), tr["rewards_out"][alive, t])
+        assert np.allclose(rew.transpose(2, 0, 1), tr["rewards_out"][alive, t], rtol=1e-5, atol=1e-4)
         assert np.array_equal(nb.terminal, tr["terminal_out"][alive, t])
         assert np.all(nb.horizon == scn.params.HORIZON - t - 1)
         na = eng.get_num_actions(nb)
@@ -190,7 +194,7 @@ def test_rollout_per_rollout_outputs_match_oracle(built, orc, name, n):
     assert same[safe].all(), "discrete outputs differ on %d rollouts with a safe margin" % (~same[safe]).sum()
     assert same.mean() > 0.995, "too many fp32-sensitive rollouts differ: %d of %d" % ((~same).sum(), n)
     assert close(out["ro_agents"][same], ref["states"][same], atol=ATOL_POS)
-    assert close(out["ro_returns"][same], ref["returns"][same], rtol=2e-5, atol=2e-3)
+    assert close(out["ro_returns"][same], ref["returns"][same], rtol=2e-5, atol=1e-3)
     # aggregates
     agg = orc.rollout(cfg, scn.initial_state, FL(A), scn.params.HORIZON, 77, 1000, n, 30,
                       scn.params.DISCOUNT_FACTOR, n_threads=4)
