@@ -1,0 +1,493 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path (BASELINE.json metric: rollout-steps/sec, agent-steps,
+device-timed).
+
+One "step" = one decision's worth of rollouts: `leaves` leaf states of a host-side search
+tree x `rollouts_per_leaf` random rollouts each (mvmcts::RandomHeuristic), fused on the GPU
+(K3 rules_rollout / K1 gridworld_rollout), reduced per leaf, folded into root statistics
+(K5) and -- with more than one rank -- merged by one NCCL allreduce.  Workloads:
+  M  multi-agent merge, 4 agents, zipper + safe-distance rules, 262144 rollouts/decision
+     (BASELINE.json configs[2]; the configuration north_star quotes its target on) [default]
+  S  single-agent highway, safe-distance rule, 65536 rollouts/decision, horizon 20 (configs[1])
+  G  GridWorld threshold-test scenario, 262144 rollouts/decision (configs[0] shape)
+  W  4096-intersection sweep shape, 10 agents x 5 rules, 64 rollouts/scenario (configs[4])
+
+`python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+`--impl reference` times the CPU implementation of the same path on the host cores
+(oracle/_ref = the reference's own GridWorld code for workload G, the CPU restatement in
+oracle/ for S/M/W -- the only place besides cpu_baseline where bench.py executes oracle/).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rollout-steps/sec (agent-steps, device-timed)"
+UNIT = "agent-steps/s"
+L2_FLUSH_BYTES = 256 << 20
+
+WORKLOADS = {
+    "M": dict(name="multi_agent_merge", leaves=256, rollouts_per_leaf=1024, max_steps=20, agents=4,
+              desc="multi-agent merge: 4 agents, zipper + safe-distance rules, 262144 rollouts/decision, horizon 20"),
+    "S": dict(name="single_agent_highway", leaves=64, rollouts_per_leaf=1024, max_steps=20, agents=4,
+              desc="single-agent highway lane change, safe-distance rule, 65536 rollouts/decision, horizon 20"),
+    "G": dict(name="gridworld_threshold_test", leaves=256, rollouts_per_leaf=1024, max_steps=30, agents=3,
+              desc="GridWorld BaseTestEnv: 3 agents, G !collision + ZIP rules, 262144 rollouts/decision, depth 8"),
+    "W": dict(name="intersection_sweep", leaves=512, rollouts_per_leaf=64, max_steps=20, agents=10,
+              desc="scenario sweep: 512 synthetic intersections per GPU x 10 agents x 5 rules, 64 rollouts each"),
+}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------- workloads
+def build_workload(kind, device, rank, cuda_stream=None):
+    """Returns a dict with the engine, host leaves, first actions, sizes and oracle hooks."""
+    import planner_rules_mcts_b200 as brm
+    from planner_rules_mcts_b200 import scenarios
+    w = dict(WORKLOADS[kind])
+    rng = np.random.default_rng(1000 + rank)
+    L = w["leaves"]
+    if kind == "G":
+        eng = brm.GridWorldEngine(device=device, cuda_stream=cuda_stream)
+        root = eng.base_test_env_batch(L)
+        first = rng.integers(0, 3, size=(L, eng.A)).astype(np.uint8)
+        leaves, _ = eng.execute(root, first.T.copy())
+        leaves.depth[:] = 0  # TestRunner::RunTest resets the depth after every real step
+        w.update(engine=eng, leaves=leaves, first=first, M=eng.A, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
+                 gamma=0.95, dtype="i32", state_bytes=16, scn=None)
+        return w
+    if kind == "W":
+        scns = [scenarios.intersection_scenario(seed=1000, scenario_id=rank * L + k) for k in range(L)]
+        eng = brm.RulesMctsEngine(scns, device=device, cuda_stream=cuda_stream)
+        leaves = eng.initial_batch()
+        first = np.zeros((L, eng.M), np.uint8)
+        w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
+                 gamma=0.9, dtype="f32", state_bytes=16, scn=scns)
+        return w
+    scn = scenarios.merge_scenario(seed=1000) if kind == "M" else scenarios.highway_scenario(seed=1000)
+    eng = brm.RulesMctsEngine([scn], device=device, cuda_stream=cuda_stream)
+    n_act = len(scn.agents[0].primitives)
+    # leaves = children of the root under random first joint actions (tree kept on the host)
+    root = eng.make_batch(np.broadcast_to(scn.initial_state, (L,) + scn.initial_state.shape))
+    first = rng.integers(0, n_act, size=(L, eng.M)).astype(np.uint8)
+    leaves, _ = eng.execute(root, first.T.copy())
+    bad = np.flatnonzero(leaves.terminal != 0)
+    for l in bad:  # a terminal child gets no rollouts in MCTS: fall back to the no-op action
+        first[l] = 0
+    if len(bad):
+        leaves, _ = eng.execute(root, first.T.copy())
+    w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=n_act,
+             gamma=scn.params.DISCOUNT_FACTOR, dtype="f32", state_bytes=16, scn=[scn])
+    return w
+
+
+def cpu_rollouts(kind, w, n_rollouts, n_threads, seed, leaf=0, impl=None):
+    """Runs the CPU implementation of the same rollouts on `n_threads` host threads.
+    Returns (agent_steps, seconds, kind)."""
+    if kind == "G":
+        from oracle import gw as ogw
+        from tests.gw_common import oracle_config_from_engine
+        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgw_ref.so"))
+        which = impl or ("ref" if have_ref else "port")
+        orc = ogw.GwOracle(which)
+        cfg = oracle_config_from_engine(w["engine"])
+        lv = w["leaves"]
+        agents0 = np.ascontiguousarray(lv.agents[:, leaf, :])
+        term0 = np.array([(int(lv.term[leaf]) >> a) & 1 for a in range(w["A"])], np.uint8)
+        t0 = time.perf_counter()
+        r = orc.rollout(cfg, agents0, term0, 0, seed, 0, n_rollouts, w["max_steps"], w["gamma"],
+                        n_threads=n_threads, q0=np.ascontiguousarray(lv.q[:, :, leaf]))
+        return r["agent_steps"], time.perf_counter() - t0, ("reference" if which == "ref" else "port")
+    from oracle import cw as ocw
+    from tests.cw_common import oracle_config
+    orc = ocw.CwOracle()
+    lv = w["leaves"]
+    scn = w["scn"][int(lv.scenario[leaf])]
+    cfg = oracle_config(scn)
+    t0 = time.perf_counter()
+    r = orc.rollout(cfg, np.ascontiguousarray(lv.agents[:, leaf, :]), np.ascontiguousarray(lv.flags[:, leaf]),
+                    int(lv.horizon[leaf]), seed, 0, n_rollouts, w["max_steps"], w["gamma"], n_threads=n_threads,
+                    q0=np.ascontiguousarray(lv.q[:, :, leaf]))
+    return r["agent_steps"], time.perf_counter() - t0, "port"
+
+
+def cpu_baseline(kind, w, target_seconds=12.0):
+    cores = os.cpu_count() or 1
+    steps, sec, impl_kind = cpu_rollouts(kind, w, 2000, cores, 1)
+    rate = steps / max(sec, 1e-9)
+    per_rollout = steps / 2000.0
+    n = int(max(2000, min(5e7, target_seconds * rate / max(per_rollout, 1e-9))))
+    steps, sec, impl_kind = cpu_rollouts(kind, w, n, cores, 2)
+    return dict(value=steps / sec, unit=UNIT, cores=cores, kind=impl_kind,
+                sample="%d rollouts from leaf 0 of workload %s on %d host threads (%.1f s)" % (n, kind, cores, sec))
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    g.build(only_missing=True)
+    # building the workload needs the engine only for leaf construction on a GPU; the CPU arm
+    # must also run where the GPU is busy/absent, so leaves are produced by the oracle itself.
+    kind = args.workload
+    w = reference_workload(kind)
+    cores = os.cpu_count() or 1
+    per_step = w["ref_rollouts_per_step"]
+    for i in range(args.warmup):
+        cpu_rollouts(kind, w, max(200, per_step // 10), cores, 100 + i)
+    total_steps, total_sec, impl_kind = 0, 0.0, "port"
+    for i in range(args.steps):
+        s, sec, impl_kind = cpu_rollouts(kind, w, per_step, cores, 200 + i)
+        total_steps += s
+        total_sec += sec
+    value = total_steps / max(total_sec, 1e-9)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total_sec / max(args.steps, 1), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=w["name"], description=w["desc"], leaves=WORKLOADS[kind]["leaves"],
+                            rollouts_per_leaf=w["rollouts_per_leaf"], max_steps=w["max_steps"],
+                            note="each reference step is a bounded sample of %d rollouts of the same workload" % per_step),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=impl_kind,
+                                  sample="%d rollouts per step x %d steps on %d host threads" % (per_step, args.steps, cores)),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+class _HostLeaves:
+    pass
+
+
+def reference_workload(kind):
+    """Leaf state for the CPU arm without touching a GPU: the root state of the scenario
+    (leaf 0 of the GPU arm is one Execute further; rollouts from either cost the same)."""
+    w = dict(WORKLOADS[kind])
+    if kind == "G":
+        from oracle import gw as ogw
+        import planner_rules_mcts_b200 as brm
+        agents, term = ogw.base_test_env_state()
+        lv = _HostLeaves()
+        lv.agents = agents[:, None, :].copy()
+        lv.term = np.zeros(1, np.uint8)
+        rules = brm.make_default_rules()
+        q = np.zeros((3, 3, 1), np.uint8)
+        lv.q = q
+
+        class _E:  # what oracle_config_from_engine reads
+            params = brm.GridWorldStateParameter()
+        _E.rules = rules
+        w.update(engine=_E, leaves=lv, A=3, gamma=0.95, ref_rollouts_per_step=200000)
+        return w
+    from planner_rules_mcts_b200 import scenarios
+    scn = {"M": scenarios.merge_scenario, "S": scenarios.highway_scenario,
+           "W": scenarios.intersection_scenario}[kind](seed=1000)
+    A = len(scn.agents)
+    lv = _HostLeaves()
+    lv.scenario = np.zeros(1, np.int32)
+    lv.agents = scn.initial_state[:, None, :].astype(np.float32).copy()
+    lv.flags = np.full((A, 1), 3, np.uint8)
+    lv.horizon = np.array([scn.params.HORIZON], np.int32)
+    M = scn.n_mcts_agents
+    R = sum((A - 1) if r.IsAgentSpecific() else 1 for r in scn.rules)
+    q = np.zeros((M, R, 1), np.uint8)
+    s = 0
+    for r in scn.rules:
+        reps = (A - 1) if r.IsAgentSpecific() else 1
+        q[:, s:s + reps, 0] = r.table.init
+        s += reps
+    lv.q = q
+    w.update(leaves=lv, scn=[scn], A=A, gamma=scn.params.DISCOUNT_FACTOR,
+             ref_rollouts_per_step={"M": 60000, "S": 100000, "W": 20000}[kind])
+    return w
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def load_inst_counts(kind):
+    path = os.path.join(ROOT, "profiles", "inst_counts.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(kind)
+        except (ValueError, OSError):
+            return None
+    return None
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rollout engine has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import __graft_entry__ as g
+    g.build(only_missing=True)
+
+    kind = args.workload
+    stream = torch.cuda.current_stream(dev)
+    w = build_workload(kind, local_rank, rank, cuda_stream=stream.cuda_stream)
+    eng, L, n = w["engine"], w["leaves"], w["rollouts_per_leaf"]
+    n_leaves = L.n
+    M, V, R, A = w["M"], w["V"], w["R"], w["A"]
+    rollouts_per_step = n_leaves * n
+
+    # device-resident inputs and outputs
+    d_leaves = L.cuda(local_rank)
+    d_first = torch.from_numpy(w["first"]).to(dev)
+    out = dict(returns_sum=torch.zeros((n_leaves, M, V), dtype=torch.float64, device=dev),
+               viol_sum=torch.zeros((n_leaves, M, R), dtype=torch.int64, device=dev),
+               agent_steps=torch.zeros(n_leaves, dtype=torch.int64, device=dev))
+    stats = torch.zeros((M, w["n_actions"], 1 + V), dtype=torch.float64, device=dev)
+    steps_acc = torch.zeros((), dtype=torch.int64, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def rollout_kwargs(step_idx):
+        base = (rank * 1_000_003 + step_idx) * rollouts_per_step
+        kw = dict(seed=1000, rollout_base=base, max_steps=w["max_steps"], discount_factor=w["gamma"])
+        return kw
+
+    def device_step(step_idx):
+        stats.zero_()
+        eng.rollout(d_leaves, n, out=out, **rollout_kwargs(step_idx))
+        eng.root_stats_reduce(d_first, out["returns_sum"], n, stats, n_actions=w["n_actions"])
+        if world > 1:
+            dist.all_reduce(stats)  # root-parallel merge: one small NCCL allreduce (sum)
+        steps_acc.add_(out["agent_steps"].sum())
+
+    for i in range(args.warmup):
+        device_step(i)
+    torch.cuda.synchronize(dev)
+    steps_acc.zero_()
+    eng.engine.set_kernel_timing(True)
+    eng.engine.kernel_time(reset=True)
+    launches0 = eng.engine.launch_count
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    evs = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)  # L2 flush between timed iterations (outside the event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        device_step(args.warmup + i)
+        b.record(stream)
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    kern_ms, kern_launches = eng.engine.kernel_time(reset=True)
+    eng.engine.set_kernel_timing(False)
+    gpu_launches = eng.engine.launch_count - launches0
+    agent_steps = int(steps_acc.item())
+
+    # ---- end-to-end: public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    def pin(a):
+        # pinned host copy (torch has no uint32/uint64 arithmetic: pin the signed view)
+        a = np.ascontiguousarray(a)
+        signed = {np.dtype(np.uint64): np.int64, np.dtype(np.uint32): np.int32}.get(a.dtype)
+        t = torch.from_numpy(a.view(signed) if signed else a).pin_memory()
+        return t.numpy().view(a.dtype) if signed else t.numpy()
+    fields = type(L).FIELDS if hasattr(type(L), "FIELDS") else ("agents", "term", "depth", "q", "viol")
+    host_leaves = type(L)(*[None if getattr(L, f) is None else pin(getattr(L, f)) for f in fields])
+    h_first = pin(w["first"])
+    h_out = dict(returns_sum=pin(np.zeros((n_leaves, M, V), np.float64)),
+                 viol_sum=pin(np.zeros((n_leaves, M, R), np.uint64)),
+                 agent_steps=pin(np.zeros(n_leaves, np.uint64)))
+    h_stats = pin(np.zeros((M, w["n_actions"], 1 + V), np.float64))
+    h2d = sum(getattr(host_leaves, f).nbytes for f in fields if getattr(host_leaves, f) is not None)
+    h2d += h_first.nbytes + h_out["returns_sum"].nbytes + h_stats.nbytes  # root_stats_reduce inputs
+    d2h = sum(v.nbytes for v in h_out.values()) + h_stats.nbytes
+
+    def e2e_step(step_idx):
+        h_stats[:] = 0
+        eng.rollout(host_leaves, n, out=h_out, **rollout_kwargs(step_idx))
+        eng.root_stats_reduce(h_first, h_out["returns_sum"], n, h_stats, n_actions=w["n_actions"])
+        if world > 1:
+            t = torch.from_numpy(h_stats).to(dev)
+            dist.all_reduce(t)
+            h_stats[:] = t.cpu().numpy()
+        return int(h_out["agent_steps"].sum())
+
+    e2e_step(10_000)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e2e_steps_n = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    e2e_agent_steps = 0
+    for i in range(e2e_steps_n):
+        e2e_agent_steps += e2e_step(20_000 + i)
+    torch.cuda.synchronize(dev)
+    e2e_sec = time.perf_counter() - t0
+
+    # ---- aggregate over ranks: totals summed, times maxed
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_sec, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_max, e2e_sec_max, kern_ms_max = [float(x) for x in t.tolist()]
+        c = torch.tensor([agent_steps, e2e_agent_steps, gpu_launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(c)
+        agent_steps_all, e2e_steps_all, launches_all = [int(x) for x in c.tolist()]
+    else:
+        dev_ms_max, e2e_sec_max, kern_ms_max = dev_ms, e2e_sec, kern_ms
+        agent_steps_all, e2e_steps_all, launches_all = agent_steps, e2e_agent_steps, gpu_launches
+
+    if rank == 0:
+        value = agent_steps_all / (dev_ms_max * 1e-3)
+        info = eng.engine.device_info()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        # dominant kernel = the fused rollout kernel (+ its tiny leaf reduce), timed live with
+        # CUDA events on the launching stream (brm_kernel_time)
+        kern_s = kern_ms_max * 1e-3
+        per_rank_steps = agent_steps_all / world
+        # algorithmic bytes of one rollout launch (rollout mode): every rollout
+        # reads its leaf state + rule states + Philox key/counter and writes returns and
+        # violation counters; lane polylines / automaton tables are staged once per CTA
+        bytes_per_rollout = A * (17 + R) + 16 + M * (4 * V + 4 * R)
+        algo_bytes = rollouts_per_step * bytes_per_rollout * args.steps
+        hbm_achieved = algo_bytes / kern_s / 1e9
+        sm_mhz = clocks.get("sm_mhz") or info["sm_clock_khz"] / 1e3
+        issue_peak = info["sm_count"] * 4 * sm_mhz * 1e6  # warp-instructions / s at the sampled clock
+        ic = load_inst_counts(kind)
+        roof = dict(bound="issue", unit="Gwarp-inst/s", peak=issue_peak / 1e9,
+                    peak_note="%d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the run)"
+                              % (info["sm_count"], sm_mhz),
+                    kernel="cw_rollout_kernel" if kind != "G" else "gw_rollout_kernel",
+                    kernel_ms_per_launch=kern_ms_max / max(args.steps, 1),
+                    kernel_share_of_step=kern_ms_max / dev_ms_max if dev_ms_max else None,
+                    hbm=dict(bound="hbm", achieved=hbm_achieved, peak=hbm_peak, unit="GB/s",
+                             frac=hbm_achieved / hbm_peak, peak_source=hbm_src,
+                             algorithmic_bytes_per_launch=rollouts_per_step * bytes_per_rollout,
+                             traffic=(ic or {}).get("dram_bytes_per_launch")))
+        if ic and ic.get("warp_inst_per_agent_step"):
+            achieved = per_rank_steps * ic["warp_inst_per_agent_step"] / kern_s
+            roof.update(achieved=achieved / 1e9, frac=achieved / issue_peak,
+                        warp_inst_per_agent_step=ic["warp_inst_per_agent_step"],
+                        thread_inst_per_agent_step=ic.get("thread_inst_per_agent_step"),
+                        inst_source=ic.get("source"), traffic=ic.get("dram_bytes_per_launch"))
+        else:
+            roof.update(achieved=None, frac=None, traffic=None,
+                        inst_source="no ncu instruction count committed yet for this workload")
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=dev_ms_max / max(args.steps, 1), higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype=w["dtype"], data="synthetic",
+                    config=dict(workload=w["name"], description=w["desc"], leaves_per_gpu=n_leaves,
+                                rollouts_per_leaf=n, rollouts_per_decision_per_gpu=rollouts_per_step,
+                                max_steps=w["max_steps"], agents=A, mcts_agents=M, reward_vec_size=V,
+                                rule_states_per_agent=R, parallelism="root-parallel x%d" % world,
+                                l2="flushed between timed iterations (256 MiB fill)",
+                                rollouts_per_sec=rollouts_per_step * world * args.steps / (dev_ms_max * 1e-3),
+                                decisions_per_sec=world * args.steps / (dev_ms_max * 1e-3),
+                                agent_steps_per_decision_per_gpu=per_rank_steps / max(args.steps, 1)),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_steps_all / e2e_sec_max, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                             d2h_bytes_per_step=int(d2h), steps=e2e_steps_n,
+                             note="planner_rules_mcts_b200 engine.rollout + root_stats_reduce on pinned host "
+                                  "buffers; H2D, kernels, D2H and the host wall clock all inside"),
+                    gpu_launches=int(launches_all), roofline=roof, wall_s=t_wall)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(kind, w)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="M", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -651,14 +651,21 @@ int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* 
   for (int p = 0; p < P; ++p) {
     const uint64_t b = rollout_begin + n_rollouts * p / P, e = rollout_begin + n_rollouts * (p + 1) / P;
     auto job = [=, &rs, &vs, &st]() {
+      // thread-private accumulators (no false sharing between workers), published at the end
+      std::vector<double> lr(M * V, 0.0);
+      std::vector<uint64_t> lv(M * R + 1, 0);
+      uint64_t ls = 0;
       if (cfg->precision)
         rollout_range<float>(cfg, states0, flags0, horizon0, q0, seed, b, e, max_steps, gamma,
-                             first_discount_exp, rs[p].data(), vs[p].data(), &st[p], nullptr, nullptr,
+                             first_discount_exp, lr.data(), lv.data(), &ls, nullptr, nullptr,
                              nullptr, nullptr, nullptr, nullptr, nullptr);
       else
         rollout_range<double>(cfg, states0, flags0, horizon0, q0, seed, b, e, max_steps, gamma,
-                              first_discount_exp, rs[p].data(), vs[p].data(), &st[p], nullptr, nullptr,
+                              first_discount_exp, lr.data(), lv.data(), &ls, nullptr, nullptr,
                               nullptr, nullptr, nullptr, nullptr, nullptr);
+      rs[p] = lr;
+      vs[p] = lv;
+      st[p] = ls;
     };
     if (P == 1) job(); else th.emplace_back(job);
   }

@@ -212,8 +212,15 @@ int32_t gwref_rollout(GWO_ROLLOUT_ARGS) {
       // each worker owns a private copy of the scenario (the reference is not thread-safe)
       RefEnv le = MakeEnv(cfg);
       std::shared_ptr<GridWorldState> lroot = MakeState(le, agents0, term0, depth0, q0);
-      RolloutRange(le, lroot, seed, b, en - b, max_steps, gamma, first_discount_exp, rs[p].data(),
-                   vs[p].data(), &steps[p]);
+      // thread-private accumulators (no false sharing between workers), published at the end
+      std::vector<double> lr(le.A * le.V, 0.0);
+      std::vector<uint64_t> lv(le.A * le.R, 0);
+      uint64_t ls = 0;
+      RolloutRange(le, lroot, seed, b, en - b, max_steps, gamma, first_discount_exp, lr.data(),
+                   lv.data(), &ls);
+      rs[p] = lr;
+      vs[p] = lv;
+      steps[p] = ls;
     });
   }
   for (auto& t : th) t.join();
