@@ -69,9 +69,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in [t0, t1] (the timed region); if the region was too
+        short to catch one, of all samples since start() (warm-up + timed region)."""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -81,7 +83,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = "timed region"
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1)]
+        if not rows:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than one sample)"
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -91,7 +97,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 # ----------------------------------------------------------------------------- workloads
@@ -287,7 +293,12 @@ def run_gpu(args):
     g.build(only_missing=True)
 
     kind = args.workload
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) torch stream: the engine enqueues on it, and the torch events
+    # below are recorded on it, so they bracket exactly the engine's kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     w = build_workload(kind, local_rank, rank, cuda_stream=stream.cuda_stream)
     eng, L, n = w["engine"], w["leaves"], w["rollouts_per_leaf"]
     n_leaves = L.n
@@ -324,11 +335,9 @@ def run_gpu(args):
     eng.engine.set_kernel_timing(True)
     eng.engine.kernel_time(reset=True)
     launches0 = eng.engine.launch_count
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
     t_wall0 = time.perf_counter()
     evs = []
     for i in range(args.steps):
@@ -341,8 +350,9 @@ def run_gpu(args):
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1)
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     kern_ms, kern_launches = eng.engine.kernel_time(reset=True)
     eng.engine.set_kernel_timing(False)
@@ -472,8 +482,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
