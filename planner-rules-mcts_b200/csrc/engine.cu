@@ -98,6 +98,16 @@ int brm_create(int device, void* cuda_stream, brm_engine** out) {
     return BRM_ERR_NO_DEVICE;
   }
   BRM_CUDA_CHECK(cudaSetDevice(device));
+  {
+    // BRM_MEM_HOST calls stage through stream-ordered allocations; keep freed blocks in the
+    // pool across synchronisations (the default threshold 0 returns them to the OS at every
+    // sync, which costs milliseconds per call)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   brm_engine* e = new brm_engine();
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
