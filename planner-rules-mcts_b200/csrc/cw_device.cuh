@@ -21,10 +21,15 @@ struct alignas(16) CwLaneHdr {
 };
 
 constexpr int kCwMaxSegs = BRM_CW_MAX_LANES * (BRM_CW_MAX_PTS - 1);
+constexpr int kCwThreads = 128;          // CTA size of every continuous-world kernel
+constexpr int kCwRolloutCtasPerSm = 6;   // register budget of the rollout kernel: 65536 / (6 * 128) = 85
+constexpr int kCwBlk = 8;                                        // segments per pruning block
+constexpr int kCwMaxBlk = (BRM_CW_MAX_PTS - 1 + kCwBlk - 1) / kCwBlk;  // blocks per lane
+constexpr int kCwMaxBlkTotal = BRM_CW_MAX_LANES * kCwMaxBlk;            // 64: one bit each
 
 struct alignas(16) CwBlob {
   int32_t A, M, V, R, n_lanes, n_road, n_rules, n_sub;
-  int32_t ego_only, total_bytes, _p0, _p1;
+  int32_t ego_only, total_bytes, n_blk, _p1;
   float w_coll, w_oom, w_pot, w_acc, w_rad, w_vel, w_lane, dt;
   float v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
   float near2, inv_dt, _p2, _p3;
@@ -37,6 +42,14 @@ struct alignas(16) CwBlob {
   int8_t slot_rank[BRM_CW_MAX_SLOTS];  // rank of the bound other agent among the others, -1: ego rule
   brm_rule rules[BRM_MAX_RULES];
   float4 road_edge[BRM_CW_MAX_ROAD];  // (ya, yb, xa, m = (xb-xa)/(yb-ya))
+  // exact pruning of the nearest-segment search: (xmin, ymin, xmax, ymax) of every lane
+  // (grown by its half width) and of every block of kCwBlk consecutive segments
+  // blocks of all lanes in lane order (n_blk <= 64, one bit each in the candidate mask):
+  // blk_gbox = bounding box grown by the lane's half width, blk_box = tight box,
+  // blk_info = lane | first segment (within the lane) << 8 | segment count << 16
+  float4 blk_gbox[kCwMaxBlkTotal];
+  float4 blk_box[kCwMaxBlkTotal];
+  uint32_t blk_info[kCwMaxBlkTotal];
   CwLaneHdr lanes[BRM_CW_MAX_LANES];
   CwSeg segs[kCwMaxSegs];  // last: only the used part is copied
 };
@@ -115,36 +128,77 @@ __device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a,
   t.ex = ex; t.ey = ey; t.eth = eth; t.ev = ev;
 }
 
-// nearest point on every lane centre line, first lane that contains the point wins
+// Nearest point on every lane centre line; the first lane that contains the point wins.
+// The reference semantics is a brute-force nearest-segment search per lane (that is what
+// the oracle does).  Two exact prunings keep the same answer:
+//   * only blocks of segments whose bounding box, grown by the lane's half width, contains
+//     the point can hold a segment within the half width (candidate mask, built with
+//     uniform control flow over all blocks of the scenario);
+//   * a candidate block whose tight box is farther than the best distance found so far on
+//     its lane cannot hold the nearest segment.
+// A lane none of whose blocks survives is a lane the point is not on.
 __device__ __forceinline__ void cw_frenet(const CwBlob& B, CwAgent& t) {
   t.lane = -1;
   t.s = 0.f;
   t.lat = 0.f;
-  for (int l = 0; l < B.n_lanes; ++l) {
-    const CwLaneHdr L = B.lanes[l];
-    const CwSeg* seg = B.segs + L.seg_off;
-    float best = __int_as_float(0x7f800000), bt = 0.f, btu = 0.f, bcross = 0.f;
-    int bk = 0;
-    for (int k = 0; k < L.n_seg; ++k) {
+  unsigned long long mask = 0ull;
+  const int nb = B.n_blk;
+  for (int i = 0; i < nb; ++i) {
+    const float4 g = B.blk_gbox[i];
+    if (t.x >= g.x && t.x <= g.z && t.y >= g.y && t.y <= g.w) mask |= 1ull << i;
+  }
+  const float kInf = __int_as_float(0x7f800000);
+  int l = -1, n_seg = 0, seg_off = 0, bk = 0;
+  float best = kInf, btu = 0.f, hw2 = 0.f;
+  for (;;) {
+    const int i = mask ? (__ffsll(static_cast<long long>(mask)) - 1) : -1;
+    const uint32_t info = i >= 0 ? B.blk_info[i] : 0xffu;
+    const int li = static_cast<int>(info & 0xffu);
+    if (li != l) {
+      // lane l is finished: is the point on it?
+      if (l >= 0 && best <= hw2) {
+        const bool interior = !(bk == 0 && btu < 0.f) && !(bk == n_seg - 1 && btu > 1.f);
+        if (interior) {
+          const CwSeg g = B.segs[seg_off + bk];
+          const float bt = fminf(fmaxf(btu, 0.f), 1.f);
+          const float wx = t.x - g.x0, wy = t.y - g.y0;
+          const float cross = g.dx * wy - g.dy * wx;
+          t.lane = l;
+          t.s = g.s0 + bt * g.len;
+          const float d = sqrtf(best);
+          t.lat = cross < 0.f ? -d : d;
+          return;
+        }
+      }
+      if (i < 0) return;
+      l = li;
+      const CwLaneHdr L = B.lanes[l];
+      n_seg = L.n_seg;
+      seg_off = L.seg_off;
+      hw2 = L.hw2;
+      best = kInf;
+    }
+    mask &= mask - 1ull;
+    const float4 bb = B.blk_box[i];
+    const float gx = fmaxf(fmaxf(bb.x - t.x, t.x - bb.z), 0.f);
+    const float gy = fmaxf(fmaxf(bb.y - t.y, t.y - bb.w), 0.f);
+    if (gx * gx + gy * gy > best) continue;
+    const int b0 = static_cast<int>((info >> 8) & 0xffu);
+    const int b1 = b0 + static_cast<int>(info >> 16);
+    const CwSeg* seg = B.segs + seg_off;
+    for (int k = b0; k < b1; ++k) {
       const float4 p = reinterpret_cast<const float4*>(seg + k)[0];
-      const float4 m = reinterpret_cast<const float4*>(seg + k)[1];
+      const float inv = seg[k].inv_len2;
       const float wx = t.x - p.x, wy = t.y - p.y;
-      const float tu = (wx * p.z + wy * p.w) * m.x;
+      const float tu = (wx * p.z + wy * p.w) * inv;
       const float tc = fminf(fmaxf(tu, 0.f), 1.f);
       const float ex = wx - tc * p.z, ey = wy - tc * p.w;
       const float d2 = ex * ex + ey * ey;
       if (d2 < best) {
-        best = d2; bk = k; bt = tc; btu = tu;
-        bcross = p.z * wy - p.w * wx;
+        best = d2;
+        bk = k;
+        btu = tu;
       }
-    }
-    const bool interior = !(bk == 0 && btu < 0.f) && !(bk == L.n_seg - 1 && btu > 1.f);
-    if (interior && best <= L.hw2) {
-      t.lane = l;
-      t.s = seg[bk].s0 + bt * seg[bk].len;
-      const float d = sqrtf(best);
-      t.lat = bcross < 0.f ? -d : d;
-      return;
     }
   }
 }

@@ -1,5 +1,6 @@
 // Continuous-world host API (include/brm.h, brm_cw_*): scenario blobs, staging and the
 // batched MvmctsState surface.  Kernels live in cw_kernels.cu.
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 
@@ -9,7 +10,7 @@
 
 namespace brm {
 
-int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, const brm_cw_states& leaves,
+int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
                       const brm_rollout_params& rp, const brm_cw_rollout_out& out);
 int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_cw_states& in,
                     const brm_cw_states* out, const uint8_t* actions, float* rewards,
@@ -24,7 +25,7 @@ struct CwEngine {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = kCwThreads;
 
 bool rule_specific(const brm_rule& r) {
   for (int a = 0; a < r.n_aps; ++a)
@@ -137,7 +138,7 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
                                   yb != ya ? static_cast<float>((xb - xa) / (yb - ya)) : 0.f);
   }
   // lane centre lines -> per-segment records
-  int off = 0;
+  int off = 0, n_blk = 0;
   for (int l = 0; l < s.n_lanes; ++l) {
     const brm_cw_lane& L = s.lanes[l];
     BRM_REQUIRE(L.n_pts >= 2 && L.n_pts <= BRM_CW_MAX_PTS, "brm_cw_configure: lane %d has %d points", l, L.n_pts);
@@ -167,7 +168,31 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
       s0 += std::sqrt(l2);
     }
     H.length = static_cast<float>(s0);
+    // bounding boxes for the exact pruning in cw_frenet (grown a little: a larger box only
+    // prunes less, never differently)
+    const double kSlack = 1e-3;
+    const double grow = L.half_width + 2.0 * kSlack;
+    for (int b0 = 0; b0 < L.n_pts - 1; b0 += kCwBlk) {
+      const int b1 = std::min(b0 + kCwBlk, L.n_pts - 1);
+      double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+      for (int k = b0; k <= b1; ++k) {
+        x0 = std::min(x0, static_cast<double>(L.pts[k][0]));
+        x1 = std::max(x1, static_cast<double>(L.pts[k][0]));
+        y0 = std::min(y0, static_cast<double>(L.pts[k][1]));
+        y1 = std::max(y1, static_cast<double>(L.pts[k][1]));
+      }
+      BRM_REQUIRE(n_blk < kCwMaxBlkTotal, "brm_cw_configure: too many lane segments (more than %d blocks)",
+                  kCwMaxBlkTotal);
+      B->blk_box[n_blk] = make_float4(static_cast<float>(x0 - kSlack), static_cast<float>(y0 - kSlack),
+                                      static_cast<float>(x1 + kSlack), static_cast<float>(y1 + kSlack));
+      B->blk_gbox[n_blk] = make_float4(static_cast<float>(x0 - grow), static_cast<float>(y0 - grow),
+                                       static_cast<float>(x1 + grow), static_cast<float>(y1 + grow));
+      B->blk_info[n_blk] = static_cast<uint32_t>(l) | (static_cast<uint32_t>(b0) << 8) |
+                           (static_cast<uint32_t>(b1 - b0) << 16);
+      ++n_blk;
+    }
   }
+  B->n_blk = n_blk;
   B->total_bytes = static_cast<int32_t>(offsetof(CwBlob, segs) + static_cast<size_t>(off) * sizeof(CwSeg));
   return BRM_OK;
 }
@@ -421,7 +446,7 @@ int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   CwEngine* c = cw_of(e);
   const int A = c->ctx.c.A, M = c->ctx.c.M, R = c->ctx.c.R, V = c->ctx.c.V;
-  if (leaves->mem == BRM_MEM_DEVICE) return cw_launch_rollout(e, c->ctx, *leaves, *rp, *out);
+  if (leaves->mem == BRM_MEM_DEVICE) return cw_launch_rollout(e, c->ctx, c->n_scenarios, *leaves, *rp, *out);
   const size_t L = leaves->n, N = L * static_cast<size_t>(rp->rollouts_per_leaf);
   Stager st(e);
   brm_cw_states d;
@@ -436,7 +461,7 @@ int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout
   if (out->ro_agents) BRM_TRY(st.alloc(N * A * 4, &o.ro_agents));
   if (out->ro_flags) BRM_TRY(st.alloc(N * A, &o.ro_flags));
   if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
-  BRM_TRY(cw_launch_rollout(e, c->ctx, d, *rp, o));
+  BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, d, *rp, o));
   BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * M * V));
   if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * M * R));
   if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));

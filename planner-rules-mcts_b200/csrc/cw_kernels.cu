@@ -1,11 +1,12 @@
 // Continuous-world kernels (sm_100a):
 //   K3 cw_rollout_kernel   fused random rollouts (mvmcts::RandomHeuristic over
-//                          MvmctsState::Execute): lane = agent, floor(32/A) rollouts / warp
-//   K4 cw_execute_kernel   one Execute for n states
-//   K6 cw_replay_kernel    replay of given action sequences with a full trace
-//      cw_query_kernel     CheckTerminal / GetNumActions / GetTerminalReward
-// Every CTA stages the scenario blob of the leaf it works on into shared memory with a
-// TMA bulk copy (re-staged only when the scenario changes).
+//                          MvmctsState::Execute): lane = agent, floor(32/A) rollouts in
+//                          flight per warp, finished rollouts are replaced at once
+//   K4 cw_batch_kernel<EXECUTE>  one Execute for n states
+//   K6 cw_batch_kernel<REPLAY>   replay of given action sequences with a full trace
+//      cw_batch_kernel<QUERY>    CheckTerminal / GetNumActions / GetTerminalReward
+// Every CTA stages the scenario blob it works on into shared memory with a TMA bulk copy
+// (re-staged only when the scenario changes).
 #include "common.cuh"
 #include "cw_device.cuh"
 #include "philox.cuh"
@@ -15,10 +16,12 @@ namespace brm {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = kCwThreads;
 constexpr int kWarps = kThreads / 32;
+constexpr double kFixScale = 1048576.0;  // 2^20: fixed-point scale of the per-leaf return sums
 
 // shared memory layout: [blob_cap bytes blob][R*kThreads q][R*kThreads viol]
+//                       (+ rollout kernel: [R*kThreads u32 violation totals][kWarps*A leaf poses])
 struct CwSmem {
   const CwBlob* B;
   uint8_t* q;     // this thread's column
@@ -91,128 +94,228 @@ struct CwRolloutArgs {
   CwCommon c;
   brm_cw_states leaves;
   brm_cw_rollout_out out;
-  double* part_returns;  // [cta_units*kWarps][M*V]
+  long long* returns_fx;  // [leaves][M*V] fixed-point (2^-20) sums, zeroed before the launch
   uint64_t seed, rollout_base;
   int32_t rollouts_per_leaf, max_steps, first_exp;
-  int32_t chunks_per_leaf;  // CTA-units per leaf, each kWarps*G rollouts
-  int64_t cta_units;
+  int32_t single_scenario;  // 1: every leaf lives in scenario 0 -> warps split the flat rollout range
   float gamma;
 };
 
-__global__ void __launch_bounds__(kThreads) cw_rollout_kernel(const CwRolloutArgs args) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+// the pose of a leaf's agents, kept per warp so that a finished rollout can be replaced
+// without going back to global memory or redoing the lane projection
+struct CwPose {
+  float x, y, th, v, cs, sn, s, lat;
+  int lane;
+  uint32_t flags;
+};
+
+// All rollouts idx in [seg_begin, seg_end) of one leaf, executed by one warp.  Up to G
+// rollouts are in flight (one per lane group); when one ends its group immediately takes
+// the next index, so lanes only idle at the very end of the segment.
+__device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const CwBlob& B, const CwSmem& sm,
+                                               uint32_t* viol_tot, CwPose* pose_w, int64_t leaf,
+                                               int seg_begin, int seg_end) {
   const CwCommon& c = args.c;
-  const CwSmem sm = cw_smem(smem, c);
-  const CwBlob& B = *sm.B;
-  const int lane = threadIdx.x & 31, widx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
   const int a = lane % A, g = lane / A, base = g * A;
   const bool real = g < G;
-  int cur_scn = -1;
-  uint32_t phase = 0;
+  const uint32_t full = 0xffffffffu;
 
-  for (int64_t unit = blockIdx.x; unit < args.cta_units; unit += gridDim.x) {
-    const int64_t leaf = unit / args.chunks_per_leaf;
-    const int chunk = static_cast<int>(unit - leaf * args.chunks_per_leaf);
-    cw_stage(smem, &bar, c, args.leaves.scenario[leaf], cur_scn, phase);
-    const int idx = (chunk * kWarps + widx) * G + g;
-    const bool active = real && idx < args.rollouts_per_leaf;
-    const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
-    const uint64_t rid = args.rollout_base + local;
-
-    CwAgent t;
-    cw_load_agent(args.leaves, leaf, a, active, t);
-    cw_load_rules(args.leaves, c, leaf, a, active, sm, false);
-    if (t.flags & BRM_CW_PRESENT) cw_frenet(B, t);
-    int horizon = args.leaves.horizon[leaf];
-    bool done = !active || args.leaves.terminal[leaf] != 0;
-    float acc[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
-    float disc = args.first_exp ? args.gamma : 1.f;
-    uint32_t agent_steps = 0;
-    int steps = 0;
-    Philox4 blk;
-    blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
-    for (int k = 0;; ++k) {
-      const bool live = !done && k < args.max_steps;
-      if (!__any_sync(0xffffffffu, live)) break;
-      const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
-      uint32_t act = 0;
-      if (a < M) {
-        if ((k & 3) == 0) blk = action_block(args.seed, rid, k, a);
-        act = draw_action(pick_word(blk, k), movable ? B.n_prims[a] : 1u);
-      }
-      const float in_v = t.v, in_th = t.th;
-      const uint32_t in_flags = t.flags;
-      if (live && movable) {
-        cw_integrate(B, t, a, act);
-        cw_frenet(B, t);
-        ++agent_steps;
-      }
-      CwStepOut o;
-      cw_evaluate<false>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                         kThreads, o);
-      if (live) {
-#pragma unroll
-        for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * o.r[v];
-        disc *= args.gamma;
-        --horizon;
-        ++steps;
-        if (o.terminal) done = true;
-      }
+  // leaf pose -> per-warp shared copy (lanes of group 0 load and project it)
+  {
+    CwAgent t0;
+    cw_load_agent(args.leaves, leaf, a, g == 0, t0);
+    if (g == 0 && (t0.flags & BRM_CW_PRESENT)) cw_frenet(B, t0);
+    if (g == 0) {
+      CwPose p;
+      p.x = t0.x; p.y = t0.y; p.th = t0.th; p.v = t0.v; p.cs = t0.cs; p.sn = t0.sn;
+      p.s = t0.s; p.lat = t0.lat; p.lane = t0.lane; p.flags = t0.flags;
+      pose_w[a] = p;
     }
-    {
+  }
+  __syncwarp();
+  const int horizon0 = args.leaves.horizon[leaf];
+  const bool leaf_terminal = args.leaves.terminal[leaf] != 0;
+  for (int sl = 0; sl < R; ++sl) viol_tot[sl * kThreads] = 0u;
+
+  CwAgent t;
+  t.flags = 0; t.lane = -1;
+  t.x = t.y = t.th = t.v = t.s = t.lat = 0.f; t.cs = 1.f; t.sn = 0.f;
+  t.ex = t.ey = t.eth = t.ev = 0.f;
+  float acc[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
+  double acc_tot[BRM_MAX_REWARD] = {0.0, 0.0, 0.0, 0.0};
+  float disc = 1.f;
+  int horizon = 0, k = 0, idx = 0;
+  uint64_t rid = 0;
+  uint32_t agent_steps = 0;
+  bool busy = false, done = false;
+  int next = seg_begin;  // warp-uniform: next rollout index nobody has taken yet
+  Philox4 blk;
+  blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+
+  for (;;) {
+    // ---- hand new rollouts to idle groups (ego lanes vote, ranks give distinct indices)
+    const uint32_t idle = __ballot_sync(full, real && !busy && a == 0);
+    if (idle) {
+      const int cand = next + __popc(idle & ((1u << base) - 1u));
+      if (real && !busy && cand < seg_end) {
+        idx = cand;
+        rid = args.rollout_base + static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
+        const CwPose p = pose_w[a];
+        t.x = p.x; t.y = p.y; t.th = p.th; t.v = p.v; t.cs = p.cs; t.sn = p.sn;
+        t.s = p.s; t.lat = p.lat; t.lane = p.lane; t.flags = p.flags;
+        t.ex = t.ey = t.eth = t.ev = 0.f;
+        for (int sl = 0; sl < R; ++sl) {
+          sm.q[sl * kThreads] = (a < M) ? args.leaves.q[(static_cast<int64_t>(a) * R + sl) * args.leaves.n + leaf] : 0;
+          sm.viol[sl * kThreads] = 0;
+        }
+#pragma unroll
+        for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] = 0.f;
+        disc = args.first_exp ? args.gamma : 1.f;
+        horizon = horizon0;
+        k = 0;
+        busy = true;
+        done = leaf_terminal;
+      }
+      next += __popc(idle);
+    }
+    if (!__any_sync(full, busy)) break;
+
+    // ---- one Execute for every busy group
+    const bool live = busy && !done && k < args.max_steps;
+    const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
+    uint32_t act = 0;
+    if (live && a < M) {
+      if ((k & 3) == 0) blk = action_block(args.seed, rid, k, a);
+      act = draw_action(pick_word(blk, k), movable ? B.n_prims[a] : 1u);
+    }
+    const float in_v = t.v, in_th = t.th;
+    const uint32_t in_flags = t.flags;
+    if (live && movable) {
+      cw_integrate(B, t, a, act);
+      cw_frenet(B, t);
+      ++agent_steps;
+    }
+    CwStepOut o;
+    cw_evaluate<false>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                       kThreads, o);
+    if (live) {
+#pragma unroll
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * o.r[v];
+      disc *= args.gamma;
+      --horizon;
+      ++k;
+      if (o.terminal) done = true;
+    }
+    // ---- rollouts that just ended: terminal reward, totals, optional per-rollout outputs
+    if (busy && (done || k >= args.max_steps)) {
       float tr[BRM_MAX_REWARD];
-      cw_terminal_reward(B, t, a, active, sm.q, kThreads, tr);
+      cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
 #pragma unroll
-      for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * tr[v];
-    }
-    // optional per-rollout outputs
-    if (active) {
+      for (int v = 0; v < BRM_MAX_REWARD; ++v) {
+        acc[v] += disc * tr[v];
+        if (a < M) acc_tot[v] += static_cast<double>(acc[v]);
+      }
+      const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
       if (a < M) {
         if (args.out.ro_returns)
           for (int v = 0; v < V; ++v) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
         for (int sl = 0; sl < R; ++sl) {
-          if (args.out.ro_viol) args.out.ro_viol[(local * M + a) * R + sl] = sm.viol[sl * kThreads];
+          const uint8_t vv = sm.viol[sl * kThreads];
+          viol_tot[sl * kThreads] += vv;
+          if (args.out.ro_viol) args.out.ro_viol[(local * M + a) * R + sl] = vv;
           if (args.out.ro_q) args.out.ro_q[(local * M + a) * R + sl] = sm.q[sl * kThreads];
         }
       }
       if (args.out.ro_agents)
         reinterpret_cast<float4*>(args.out.ro_agents)[local * A + a] = make_float4(t.x, t.y, t.th, t.v);
       if (args.out.ro_flags) args.out.ro_flags[local * A + a] = static_cast<uint8_t>(t.flags);
-      if (args.out.ro_steps && a == 0) args.out.ro_steps[local] = steps;
-    }
-    // warp-level reduction over the G rollouts of this warp: lanes of group 0 collect
-    const bool contrib = active && a < M;
-    for (int v = 0; v < V; ++v) {
-      double x = contrib ? static_cast<double>(acc[v]) : 0.0;
-      for (int gg = 1; gg < G; ++gg) {
-        const double y = __shfl_sync(0xffffffffu, x, (lane + gg * A) & 31);
-        if (g == 0) x += y;
-      }
-      // careful: x of group 0 must not be polluted before others read theirs: lanes of
-      // group gg only ever read, group 0 only accumulates values of groups > 0
-      if (g == 0 && a < M) args.part_returns[(unit * kWarps + widx) * (M * V) + a * V + v] = x;
-    }
-    if (args.out.viol_sum) {
-      for (int sl = 0; sl < R; ++sl) {
-        uint32_t x = contrib ? sm.viol[sl * kThreads] : 0u;
-        for (int gg = 1; gg < G; ++gg) {
-          const uint32_t y = __shfl_sync(0xffffffffu, x, (lane + gg * A) & 31);
-          if (g == 0) x += y;
-        }
-        if (g == 0 && a < M && x)
-          atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + a) * R + sl]),
-                    static_cast<unsigned long long>(x));
-      }
-    }
-    if (args.out.agent_steps) {
-      const uint32_t tot = __reduce_add_sync(0xffffffffu, agent_steps);
-      if (lane == 0 && tot)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
-                  static_cast<unsigned long long>(tot));
+      if (args.out.ro_steps && a == 0) args.out.ro_steps[local] = k;
+      busy = false;
+      t.flags = 0;  // an idle group must not look present to anybody
     }
   }
+
+  // ---- warp-level reduction over the groups; lanes of group 0 publish with integer atomics
+  // (fixed point: the per-leaf sum does not depend on the order in which warps arrive)
+  const bool contrib = real && a < M;
+  for (int v = 0; v < V; ++v) {
+    double x = contrib ? acc_tot[v] : 0.0;
+    for (int gg = 1; gg < G; ++gg) {
+      const double y = __shfl_sync(full, x, (lane + gg * A) & 31);
+      if (g == 0) x += y;
+    }
+    if (g == 0 && a < M)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&args.returns_fx[(leaf * M + a) * V + v]),
+                static_cast<unsigned long long>(__double2ll_rn(x * kFixScale)));
+  }
+  if (args.out.viol_sum) {
+    for (int sl = 0; sl < R; ++sl) {
+      uint32_t x = contrib ? viol_tot[sl * kThreads] : 0u;
+      for (int gg = 1; gg < G; ++gg) {
+        const uint32_t y = __shfl_sync(full, x, (lane + gg * A) & 31);
+        if (g == 0) x += y;
+      }
+      if (g == 0 && a < M && x)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + a) * R + sl]),
+                  static_cast<unsigned long long>(x));
+    }
+  }
+  if (args.out.agent_steps) {
+    const uint32_t tot = __reduce_add_sync(full, agent_steps);
+    if (lane == 0 && tot)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
+                static_cast<unsigned long long>(tot));
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kernel(const CwRolloutArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const CwCommon& c = args.c;
+  const CwSmem sm = cw_smem(smem, c);
+  const CwBlob& B = *sm.B;
+  const int widx = threadIdx.x >> 5;
+  uint32_t* viol_tot = reinterpret_cast<uint32_t*>(smem + c.blob_cap + 2 * c.R * kThreads) + threadIdx.x;
+  CwPose* pose_w = reinterpret_cast<CwPose*>(smem + c.blob_cap + 6 * c.R * kThreads) + widx * BRM_CW_MAX_AGENTS;
+  int cur_scn = -1;
+  uint32_t phase = 0;
+  const int n = args.rollouts_per_leaf;
+  if (args.single_scenario) {
+    // one scenario: the flat rollout range [0, leaves*n) is cut into one contiguous piece per
+    // warp of the grid (equal to +-1 rollout), pieces are walked leaf by leaf
+    cw_stage(smem, &bar, c, 0, cur_scn, phase);
+    const int64_t N = static_cast<int64_t>(args.leaves.n) * n;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kWarps + widx;
+    const int64_t tw = static_cast<int64_t>(gridDim.x) * kWarps;
+    int64_t r0 = N * gw / tw;
+    const int64_t r1 = N * (gw + 1) / tw;
+    while (r0 < r1) {
+      const int64_t leaf = r0 / n;
+      const int b = static_cast<int>(r0 - leaf * n);
+      const int64_t take = min(static_cast<int64_t>(n - b), r1 - r0);
+      cw_run_segment(args, B, sm, viol_tot, pose_w, leaf, b, b + static_cast<int>(take));
+      r0 += take;
+    }
+  } else {
+    // several scenarios: one leaf per CTA at a time (the blob is CTA-wide), its rollouts are
+    // split evenly over the warps
+    for (int64_t leaf = blockIdx.x; leaf < args.leaves.n; leaf += gridDim.x) {
+      cw_stage(smem, &bar, c, args.leaves.scenario[leaf], cur_scn, phase);
+      const int b = static_cast<int>(static_cast<int64_t>(n) * widx / kWarps);
+      const int e = static_cast<int>(static_cast<int64_t>(n) * (widx + 1) / kWarps);
+      if (b < e) cw_run_segment(args, B, sm, viol_tot, pose_w, leaf, b, e);
+    }
+  }
+}
+
+// fixed point -> double
+__global__ void cw_finalize_returns_kernel(const long long* __restrict__ fx, double* __restrict__ out,
+                                           int64_t count) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = static_cast<double>(fx[i]) * (1.0 / kFixScale);
 }
 
 // ------------------------------------------------------------------ K4 / K6 / queries
@@ -246,9 +349,8 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
   const int64_t n = args.in.n;
   int cur_scn = -1;
   uint32_t phase = 0;
-  // A CTA walks over blocks of kWarps*G consecutive states; all states of one block must
-  // live in the same scenario for the shared blob, so the host sorts / groups batches by
-  // scenario and pads: here we simply re-stage per warp-unit when needed.
+  // A CTA walks over blocks of kWarps*G consecutive states; the batch is homogeneous in
+  // scenario (checked by the host API), so the blob is staged once.
   const int64_t cta_units = (args.warp_units + kWarps - 1) / kWarps;
   for (int64_t cu = blockIdx.x; cu < cta_units; cu += gridDim.x) {
     const int64_t first_state = cu * kWarps * G;
@@ -393,16 +495,19 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
 
 }  // namespace
 
-void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t nvals,
-                        double* out, int32_t n_leaves);
+size_t cw_rollout_smem_bytes(const CwCommon& c) {
+  return static_cast<size_t>(c.blob_cap) + 6u * static_cast<size_t>(c.R) * kThreads +
+         static_cast<size_t>(kWarps) * BRM_CW_MAX_AGENTS * sizeof(CwPose);
+}
 
-int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, const brm_cw_states& leaves,
+int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
                       const brm_rollout_params& rp, const brm_cw_rollout_out& out) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(cw_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  const int M = ctx.c.M, V = ctx.c.V, R = ctx.c.R;
   CwRolloutArgs a;
   a.c = ctx.c;
   a.leaves = leaves;
@@ -413,27 +518,39 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, const brm_cw_states
   a.max_steps = rp.max_steps;
   a.first_exp = rp.first_discount_exp;
   a.gamma = static_cast<float>(rp.discount_factor);
-  const int per_cta = kWarps * ctx.c.G;
-  a.chunks_per_leaf = (rp.rollouts_per_leaf + per_cta - 1) / per_cta;
-  a.cta_units = static_cast<int64_t>(leaves.n) * a.chunks_per_leaf;
-  const int M = ctx.c.M, V = ctx.c.V, R = ctx.c.R;
-  const size_t part_bytes = static_cast<size_t>(a.cta_units) * kWarps * M * V * sizeof(double);
-  int rc = e->ensure_ws(part_bytes);
+  a.single_scenario = n_scenarios == 1 ? 1 : 0;
+  const size_t fx_count = static_cast<size_t>(leaves.n) * M * V;
+  int rc = e->ensure_ws(fx_count * sizeof(long long));
   if (rc != BRM_OK) return rc;
-  a.part_returns = static_cast<double*>(e->d_ws);
+  a.returns_fx = static_cast<long long*>(e->d_ws);
+  BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, fx_count * sizeof(long long), e->stream));
   if (out.viol_sum)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
                                    e->stream));
   if (out.agent_steps)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
                                    e->stream));
-  int64_t grid = a.cta_units;
-  const int64_t cap = static_cast<int64_t>(e->sm_count) * 4;
-  if (grid > cap) grid = cap;
+  // persistent grid: exactly the number of CTAs that are resident at once (SMs x occupancy),
+  // so there is no partial second wave
+  const size_t smem = cw_rollout_smem_bytes(ctx.c);
+  int per_sm = 0;
+  BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel, kThreads, smem));
+  int64_t grid = static_cast<int64_t>(e->sm_count) * (per_sm > 0 ? per_sm : 1);
+  const int64_t total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
+  if (a.single_scenario) {
+    // at least one rollout per lane group, otherwise shrink the grid
+    const int64_t need = (total + static_cast<int64_t>(kWarps) * ctx.c.G - 1) / (static_cast<int64_t>(kWarps) * ctx.c.G);
+    if (grid > need) grid = need;
+  } else if (grid > leaves.n) {
+    grid = leaves.n;
+  }
+  if (grid < 1) grid = 1;
   e->time_begin();
-  cw_rollout_kernel<<<static_cast<int>(grid), kThreads, ctx.smem_bytes, e->stream>>>(a);
+  cw_rollout_kernel<<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
   e->launches++;
-  launch_leaf_reduce(e, a.part_returns, a.chunks_per_leaf * kWarps, M * V, out.returns_sum, leaves.n);
+  cw_finalize_returns_kernel<<<static_cast<int>((fx_count + 255) / 256), 256, 0, e->stream>>>(
+      a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count));
+  e->launches++;
   e->time_end();
   BRM_CUDA_CHECK(cudaGetLastError());
   return BRM_OK;

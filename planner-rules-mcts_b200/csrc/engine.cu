@@ -23,19 +23,24 @@ __global__ void root_stats_kernel(int32_t n_leaves, int32_t A, int32_t n_actions
                                   const uint8_t* __restrict__ first_action,
                                   const double* __restrict__ returns_sum, int32_t rollouts_per_leaf,
                                   double* __restrict__ stats) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output element; lanes stride over the leaves and the partial sums are
+  // combined in a fixed butterfly order, so the result is deterministic
+  const int elem = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int total = A * n_actions * (1 + V);
-  if (tid >= total) return;
-  const int c = tid % (1 + V);
-  const int act = (tid / (1 + V)) % n_actions;
-  const int a = tid / ((1 + V) * n_actions);
+  if (elem >= total) return;
+  const int c = elem % (1 + V);
+  const int act = (elem / (1 + V)) % n_actions;
+  const int a = elem / ((1 + V) * n_actions);
   double x = 0.0;
-  for (int l = 0; l < n_leaves; ++l) {
+  for (int l = lane; l < n_leaves; l += 32) {
     if (first_action[l * A + a] != act) continue;
     x += (c == 0) ? static_cast<double>(rollouts_per_leaf)
                   : returns_sum[(static_cast<int64_t>(l) * A + a) * V + (c - 1)];
   }
-  stats[tid] += x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if (lane == 0) stats[elem] += x;
 }
 
 }  // namespace brm
@@ -204,7 +209,7 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
   const size_t rs_bytes = static_cast<size_t>(n_leaves) * n_agents * reward_vec_size * sizeof(double);
   const size_t st_bytes = static_cast<size_t>(total) * sizeof(double);
   if (mem == BRM_MEM_DEVICE) {
-    brm::root_stats_kernel<<<(total + 127) / 128, 128, 0, e->stream>>>(
+    brm::root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(
         n_leaves, n_agents, n_actions, reward_vec_size, leaf_first_action, returns_sum,
         rollouts_per_leaf, stats);
     e->launches++;
@@ -219,7 +224,7 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
   BRM_CUDA_CHECK(cudaMemcpyAsync(d_fa, leaf_first_action, fa_bytes, cudaMemcpyHostToDevice, e->stream));
   BRM_CUDA_CHECK(cudaMemcpyAsync(d_rs, returns_sum, rs_bytes, cudaMemcpyHostToDevice, e->stream));
   BRM_CUDA_CHECK(cudaMemcpyAsync(d_st, stats, st_bytes, cudaMemcpyHostToDevice, e->stream));
-  brm::root_stats_kernel<<<(total + 127) / 128, 128, 0, e->stream>>>(
+  brm::root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(
       n_leaves, n_agents, n_actions, reward_vec_size, d_fa, d_rs, rollouts_per_leaf, d_st);
   e->launches++;
   BRM_CUDA_CHECK(cudaGetLastError());

@@ -246,7 +246,8 @@ def test_full_size_properties(built):
         a, b = half[2 * l], half[2 * l + 1]
         assert np.array_equal(a["viol_sum"][0] + b["viol_sum"][0], full["viol_sum"][l])
         assert int(a["agent_steps"][0] + b["agent_steps"][0]) == int(full["agent_steps"][l])
-        np.testing.assert_allclose(a["returns_sum"][0] + b["returns_sum"][0], full["returns_sum"][l], rtol=1e-9, atol=1e-6)
+        # per-leaf sums are accumulated in 2^-20 fixed point (order-independent integer atomics)
+        np.testing.assert_allclose(a["returns_sum"][0] + b["returns_sum"][0], full["returns_sum"][l], rtol=1e-9, atol=1e-4)
     dl = leaves.cuda(0)
     out = dict(returns_sum=torch.zeros((L, 4, 3), dtype=torch.float64, device="cuda"),
                viol_sum=torch.zeros((L, 4, eng.R), dtype=torch.int64, device="cuda"),
