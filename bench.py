@@ -286,11 +286,15 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the rollout engine has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     if world > 1:
+        # NCCL_DEBUG=VERSION prints a banner on stdout, which must carry only the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import __graft_entry__ as g
     g.build(only_missing=True)
+    from planner_rules_mcts_b200 import parallel
 
     kind = args.workload
     # a dedicated (non-default) torch stream: the engine enqueues on it, and the torch events
@@ -316,7 +320,7 @@ def run_gpu(args):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def rollout_kwargs(step_idx):
-        base = (rank * 1_000_003 + step_idx) * rollouts_per_step
+        base = parallel.rollout_base(rank, step_idx, rollouts_per_step)  # disjoint Philox streams
         kw = dict(seed=1000, rollout_base=base, max_steps=w["max_steps"], discount_factor=w["gamma"])
         return kw
 
@@ -325,7 +329,7 @@ def run_gpu(args):
         eng.rollout(d_leaves, n, out=out, **rollout_kwargs(step_idx))
         eng.root_stats_reduce(d_first, out["returns_sum"], n, stats, n_actions=w["n_actions"])
         if world > 1:
-            dist.all_reduce(stats)  # root-parallel merge: one small NCCL allreduce (sum)
+            parallel.merge_root_stats(stats)  # root-parallel merge: one small NCCL allreduce (sum)
         steps_acc.add_(out["agent_steps"].sum())
 
     for i in range(args.warmup):

@@ -1,0 +1,85 @@
+"""include/brm_state.hpp: the C++ StateInterface adapter compiles against the C ABI, refuses
+to run without a GPU, and on a GPU reproduces what the Python mirror computes."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import planner_rules_mcts_b200 as brm
+from planner_rules_mcts_b200 import _abi, scenarios
+from planner_rules_mcts_b200.continuous import CW_LABELS
+from planner_rules_mcts_b200.gridworld import GW_LABELS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "planner-rules-mcts_b200")
+EXE = os.path.join(ROOT, "build", "adapter_test")
+
+
+@pytest.fixture(scope="module")
+def exe(built):
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+                    "-L", PKG, "-lbrm", "-Wl,-rpath," + PKG], check=True)
+    return EXE
+
+
+def run(exe, *args):
+    r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    return r.returncode, r.stdout
+
+
+def test_adapter_compiles_and_refuses_without_gpu(exe):
+    import torch
+    rc, out = run(exe, "nogpu")
+    assert rc == 0, out
+    if not torch.cuda.is_available():
+        assert "error code -2" in out and "no CPU fallback" in out
+
+
+@pytest.mark.gpu
+def test_adapter_gridworld_matches_python_mirror(exe, tmp_path):
+    rules = brm.make_default_rules()
+    arr = (_abi.Rule * len(rules))(*[r.to_abi(GW_LABELS) for r in rules])
+    path = tmp_path / "rules.bin"
+    path.write_bytes(bytes(arr))
+    n = 512
+    rc, out = run(exe, "gw", str(path), str(n))
+    assert rc == 0, out
+    eng = brm.GridWorldEngine(device=0)
+    s = brm.GridWorldState(eng)
+    rewards = []
+    lines = out.splitlines()
+    step = 0
+    while not s.IsTerminal() and step < 20:
+        s = s.Execute([1 if step < 2 else 0, 0, 0], rewards)
+        s.ResetDepth()
+        x = s.GetAgentStates()[:, 0]
+        want = "step %d x %d %d %d r0 %.17g %.17g %.17g" % (step, x[0], x[1], x[2], *rewards[0])
+        assert lines[step] == want
+        step += 1
+    assert lines[step].startswith("terminal 1 steps 8 num_actions 1 Ego: x=8")
+    res = eng.rollout(eng.base_test_env_batch(2), n, seed=1000, max_steps=30, discount_factor=0.95)
+    means = res["returns_sum"] / n
+    got = [l for l in lines if l.startswith("leaf")]
+    assert len(got) == 6
+    for l in range(2):
+        for a in range(3):
+            assert got[l * 3 + a] == "leaf %d agent %d mean %.17g %.17g %.17g" % (l, a, *means[l, a])
+
+
+@pytest.mark.gpu
+def test_adapter_continuous_reference_pins(exe, tmp_path):
+    scn = scenarios.straight_road_test_world()
+    path = tmp_path / "scn.bin"
+    path.write_bytes(bytes(scn.to_abi()))
+    rc, out = run(exe, "cw", str(path))
+    assert rc == 0, out
+    lines = out.splitlines()
+    assert lines[0] == "terminal0 0 num_actions 3"
+    assert lines[1] == "a0 terminal 0 total 0"            # test/single_agent_test.cpp:143
+    assert lines[2] == "a1 terminal 1 total -800"          # :152
+    assert lines[3] == "a2 terminal 1 total -1000 num_actions 1"  # :159
+    assert lines[4] == "execute on terminal: error -4"     # BARK_EXPECT_TRUE(!IsTerminal()), :59
