@@ -41,6 +41,8 @@ struct alignas(16) CwBlob {
   uint8_t slot_rule[BRM_CW_MAX_SLOTS];
   int8_t slot_rank[BRM_CW_MAX_SLOTS];  // rank of the bound other agent among the others, -1: ego rule
   brm_rule rules[BRM_MAX_RULES];
+  uint4 slot_rec[BRM_CW_MAX_SLOTS];  // compact per-slot record read by cw_evaluate
+  float c2, t_total, _p4, _p5;       // closed form of the Euler sub-steps without steering
   float4 road_edge[BRM_CW_MAX_ROAD];  // (ya, yb, xa, m = (xb-xa)/(yb-ya))
   // exact pruning of the nearest-segment search: (xmin, ymin, xmax, ymax) of every lane
   // (grown by its half width) and of every block of kCwBlk consecutive segments
@@ -92,9 +94,9 @@ struct CwStepOut {
 // nearly equal speeds.  With the compensation the fp32 state stays within ~1 ulp of the
 // exactly accumulated value.
 __device__ __forceinline__ void kahan_add(float& sum, float& c, float term) {
-  const float y = term - c;
-  const float t = sum + y;
-  c = (t - sum) - y;
+  const float y = __fsub_rn(term, c);
+  const float t = __fadd_rn(sum, y);
+  c = __fsub_rn(__fsub_rn(t, sum), y);
   sum = t;
 }
 
@@ -106,21 +108,25 @@ __device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a,
   float cs = t.cs, sn = t.sn;
   const int n_sub = B.n_sub;
   if (k == 0.0f) {
-    // no steering: theta stays bit-identical, so cos/sin are loop invariants
-    for (int n = 0; n < n_sub; ++n) {
-      const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
-      kahan_add(x, ex, h * (v * cs));
-      kahan_add(y, ey, h * (v * sn));
-      kahan_add(v, ev, h * acc);
-    }
+    // no steering: theta never changes, so the explicit-Euler sub-steps telescope exactly:
+    //   v_n = v0 + a t_n,  x_N = x0 + cos(theta) * sum_n h_n v_n = x0 + cos(theta) (v0 T + a C2)
+    // with T = sum_n h_n and C2 = sum_n h_n t_n (t_n = time at the start of sub-step n), both
+    // computed on the host in double.  Same scheme as the reference's loop, one rounding
+    // instead of fifteen.
+    // explicit _rn intrinsics: the compiler may not contract them differently in different
+    // kernels, so rollout, replay and single-step kernels produce the same bits
+    const float d = __fmaf_rn(v, B.t_total, __fmul_rn(acc, B.c2));
+    kahan_add(x, ex, __fmul_rn(cs, d));
+    kahan_add(y, ey, __fmul_rn(sn, d));
+    kahan_add(v, ev, __fmul_rn(acc, B.t_total));
   } else {
     for (int n = 0; n < n_sub; ++n) {
       const float h = (n == n_sub - 1) ? B.h_last : B.h_sub;
       if (n > 0) sincosf(th, &sn, &cs);
-      kahan_add(x, ex, h * (v * cs));
-      kahan_add(y, ey, h * (v * sn));
-      kahan_add(th, eth, h * (v * k));
-      kahan_add(v, ev, h * acc);
+      kahan_add(x, ex, __fmul_rn(h, __fmul_rn(v, cs)));
+      kahan_add(y, ey, __fmul_rn(h, __fmul_rn(v, sn)));
+      kahan_add(th, eth, __fmul_rn(h, __fmul_rn(v, k)));
+      kahan_add(v, ev, __fmul_rn(h, acc));
     }
     sincosf(th, &sn, &cs);
   }
@@ -230,17 +236,23 @@ __device__ __forceinline__ void cw_corners(const CwBlob& B, const CwAgent& t, in
 // strictly inside the rectangle
 __device__ __forceinline__ bool cw_out_of_map(const CwBlob& B, const CwAgent& t, int a,
                                               const float (&cx)[4], const float (&cy)[4]) {
-  bool out = false;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) out = !cw_point_in_road(B, cx[k], cy[k]) || out;
+  // one pass over the road edges: crossing-number parity of the four corners (the same
+  // test as cw_point_in_road) and "edge start vertex strictly inside the rectangle"
+  uint32_t inside = 0;
+  bool vertex_in = false;
   const float f = B.front[a], r = B.rear[a], h = B.hw[a];
   for (int e = 0; e < B.n_road; ++e) {
     const float4 g = B.road_edge[e];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool cross = ((g.x > cy[k]) != (g.y > cy[k])) && (cx[k] < g.w * (cy[k] - g.x) + g.z);
+      inside ^= (cross ? 1u : 0u) << k;
+    }
     const float dx = g.z - t.x, dy = g.x - t.y;
     const float lx = dx * t.cs + dy * t.sn, ly = -dx * t.sn + dy * t.cs;
-    out = (lx > -r && lx < f && fabsf(ly) < h) || out;
+    vertex_in = (lx > -r && lx < f && fabsf(ly) < h) || vertex_in;
   }
-  return out;
+  return inside != 0xFu || vertex_in;
 }
 
 __device__ __forceinline__ bool cw_at_goal(const CwBlob& B, const CwAgent& t, int a,
@@ -397,29 +409,33 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
     if (!(B.ego_only && a != 0)) {  // :104-108
       float rr[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
       for (int sl = 0; sl < B.R; ++sl) {
-        const brm_rule& rule = B.rules[B.slot_rule[sl]];
-        const int rank = B.slot_rank[sl];
+        // one 16-byte record per slot: x = label kinds of the 4 APs (a byte each),
+        // y = n_aps | priority << 8 | init << 16 | on_violation << 24,
+        // z = rule | (rank + 1) << 8, w = weight
+        const uint4 rec = B.slot_rec[sl];
+        const int rank = static_cast<int>((rec.z >> 8) & 0xffu) - 1;
         const int other = rank < 0 ? 0 : (rank < a ? rank : rank + 1);
-        const int n_aps = rule.n_aps;
+        const uint32_t n_aps = rec.y & 0xffu;
+        // label word of this slot: ego kinds in bits 0..7, the bound agent's kinds in 8..10
+        const uint32_t W = w0 | (((merged_mask >> other) & 1u) << BRM_CW_LABEL_MERGED_X) |
+                           (((front_mask >> other) & 1u) << BRM_CW_LABEL_IN_DIRECT_FRONT_X) |
+                           (((near_mask >> other) & 1u) << BRM_CW_LABEL_NEAR_X);
         uint32_t letter = 0;
-        for (int k = 0; k < n_aps; ++k) {
-          const uint32_t kind = rule.ap_label[k];
-          uint32_t val;
-          if (kind < 8) val = (w0 >> kind) & 1u;
-          else if (kind == BRM_CW_LABEL_MERGED_X) val = (merged_mask >> other) & 1u;
-          else if (kind == BRM_CW_LABEL_IN_DIRECT_FRONT_X) val = (front_mask >> other) & 1u;
-          else val = (near_mask >> other) & 1u;
-          letter |= val << (n_aps - 1 - k);
+#pragma unroll
+        for (uint32_t k = 0; k < BRM_MAX_APS; ++k) {
+          const uint32_t bit = (W >> ((rec.x >> (8 * k)) & 0xffu)) & 1u;
+          if (k < n_aps) letter |= bit << (n_aps - 1 - k);
         }
         const uint32_t cur = q[sl * col_stride];
-        uint32_t nxt = rule.trans[(cur << n_aps) + letter];
+        uint32_t nxt = B.rules[rec.z & 0xffu].trans[(cur << n_aps) + letter];
         if (nxt == BRM_VIOLATION) {
           viol[sl * col_stride] += 1;
-          nxt = rule.on_violation ? cur : rule.init_state;
-          const int pr = rule.priority;
+          nxt = (rec.y >> 24) ? cur : ((rec.y >> 16) & 0xffu);
+          const uint32_t pr = (rec.y >> 8) & 0xffu;
+          const float wgt = __uint_as_float(rec.w);
 #pragma unroll
           for (int v = 0; v < BRM_MAX_REWARD; ++v)
-            if (v == pr) rr[v] += rule.weight;
+            if (v == static_cast<int>(pr)) rr[v] += wgt;
         }
         q[sl * col_stride] = static_cast<uint8_t>(nxt);
       }

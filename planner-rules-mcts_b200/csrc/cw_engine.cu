@@ -64,6 +64,19 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
   B->n_sub = n_sub;
   B->h_sub = static_cast<float>(hs);
   B->h_last = static_cast<float>(dt - (n_sub - 1) * hs);
+  {
+    // closed form of the sub-stepped Euler scheme for primitives without steering
+    // (cw_integrate): T = sum h_n, C2 = sum h_n t_n, with the float-rounded step sizes the
+    // kernel would otherwise use
+    double T = 0.0, C2 = 0.0;
+    for (int n = 0; n < n_sub; ++n) {
+      const double h = (n == n_sub - 1) ? static_cast<double>(B->h_last) : static_cast<double>(B->h_sub);
+      C2 += h * T;
+      T += h;
+    }
+    B->t_total = static_cast<float>(T);
+    B->c2 = static_cast<float>(C2);
+  }
   B->dt = p.prediction_time_span;
   B->inv_dt = 1.0f / p.prediction_time_span;
   B->w_coll = p.collision_weight;
@@ -125,6 +138,14 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
       BRM_REQUIRE(R < BRM_CW_MAX_SLOTS, "brm_cw_configure: more than %d rule states per agent", BRM_CW_MAX_SLOTS);
       B->slot_rule[R] = static_cast<uint8_t>(k);
       B->slot_rank[R] = rule_specific(r) ? static_cast<int8_t>(j) : -1;
+      uint4 rec;
+      rec.x = 0;
+      for (int a = 0; a < r.n_aps; ++a) rec.x |= static_cast<uint32_t>(r.ap_label[a]) << (8 * a);
+      rec.y = static_cast<uint32_t>(r.n_aps) | (static_cast<uint32_t>(r.priority) << 8) |
+              (static_cast<uint32_t>(r.init_state) << 16) | (static_cast<uint32_t>(r.on_violation ? 1 : 0) << 24);
+      rec.z = static_cast<uint32_t>(k) | (static_cast<uint32_t>(rule_specific(r) ? j + 1 : 0) << 8);
+      memcpy(&rec.w, &r.weight, sizeof(float));
+      B->slot_rec[R] = rec;
       ++R;
     }
   }

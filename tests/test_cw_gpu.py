@@ -271,3 +271,24 @@ def test_errors(built):
     other = scenarios.highway_scenario()
     with pytest.raises(brm.BrmError):
         brm.RulesMctsEngine([scn, other], device=0)  # shapes differ
+
+
+def test_replay_matches_committed_golden_traces(built):
+    """CUDA kernels vs tests/golden/cw_golden.npz (FP64 oracle traces frozen in the repo)."""
+    import os
+    from tests.golden.make_cw_golden import SCENARIOS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cw_golden.npz"))
+    for name, make in SCENARIOS.items():
+        scn = make()
+        eng = brm.RulesMctsEngine([scn], device=0)
+        acts = g[name + "/actions"]
+        B = acts.shape[0]
+        batch = eng.make_batch(np.broadcast_to(scn.initial_state, (B,) + scn.initial_state.shape))
+        tr = eng.replay(batch, acts)
+        compared = 0
+        for b in range(B):
+            o = {k: g[name + "/" + k][b] for k in
+                 ["states", "flags", "terminal", "q", "viol", "rewards", "labels", "frenet", "margin", "term_reward"]}
+            o["steps"] = int(g[name + "/steps"][b])
+            compared += compare_trace(tr, b, o, scn)
+        assert compared > 0.8 * int(g[name + "/steps"].sum())

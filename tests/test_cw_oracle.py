@@ -121,3 +121,23 @@ def test_float_instantiation_tracks_double(orc):
     same = (d["steps"] == f["steps"]) & (d["viol"] == f["viol"]).all(axis=(1, 2))
     assert same.mean() > 0.98
     np.testing.assert_allclose(f["states"][same], d["states"][same], rtol=1e-4, atol=1e-2)
+
+
+def test_oracle_reproduces_committed_golden_traces(orc):
+    """tests/golden/cw_golden.npz freezes the FP64 oracle's traces (regression guard; these are
+    the oracle's own outputs, not the reference's -- see tests/golden/make_cw_golden.py)."""
+    import os
+    from tests.golden.make_cw_golden import SCENARIOS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cw_golden.npz"))
+    for name, make in SCENARIOS.items():
+        scn = make()
+        cfg = oracle_config(scn)
+        acts = g[name + "/actions"]
+        for b in range(acts.shape[0]):
+            o = orc.replay(cfg, scn.initial_state, FL(len(scn.agents)), scn.params.HORIZON, acts[b])
+            k = int(g[name + "/steps"][b])
+            assert o["steps"] == k
+            for key in ["flags", "terminal", "q", "viol", "labels"]:
+                assert np.array_equal(o[key][:k], g[name + "/" + key][b][:k]), (name, b, key)
+            for key in ["states", "rewards", "frenet"]:
+                np.testing.assert_allclose(o[key][:k], g[name + "/" + key][b][:k], rtol=1e-12, atol=1e-12)
