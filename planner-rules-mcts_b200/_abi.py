@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbrm.so")
+# BRM_LIB_PATH selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("BRM_LIB_PATH") or os.path.join(HERE, "libbrm.so")
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_TERMINAL, ERR_NOT_CONFIGURED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1

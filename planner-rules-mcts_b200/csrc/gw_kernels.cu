@@ -15,7 +15,13 @@ namespace brm {
 
 namespace {
 
-constexpr int kRolloutThreads = 256;
+#ifndef BRM_GW_THREADS
+#define BRM_GW_THREADS 256
+#endif
+#ifndef BRM_GW_MIN_CTAS
+#define BRM_GW_MIN_CTAS 2
+#endif
+constexpr int kRolloutThreads = BRM_GW_THREADS;
 
 template <int A>
 __device__ __forceinline__ void gw_load_state(const brm_gw_states& S, int R, int64_t i,
@@ -52,7 +58,7 @@ struct GwRolloutArgs {
 };
 
 template <int A>
-__global__ void __launch_bounds__(kRolloutThreads)
+__global__ void __launch_bounds__(kRolloutThreads, BRM_GW_MIN_CTAS)
 gw_rollout_kernel(const GwRolloutArgs args) {
   __shared__ GwBlob sB;
   __shared__ __align__(8) uint64_t bar;
@@ -431,7 +437,7 @@ int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_roll
     BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
                                    e->stream));
   // persistent grid: a multiple of the SM count, 4 CTAs of 8 warps per SM
-  const int grid = grid_for(e, a.units * 32, kRolloutThreads, 4);
+  const int grid = grid_for(e, a.units * 32, kRolloutThreads, BRM_GW_MIN_CTAS);
   e->time_begin();
   rc = dispatch_agents<RolloutLauncher>(A, e, a, grid);
   if (rc != BRM_OK) return rc;
