@@ -206,8 +206,11 @@ struct GwExecArgs {
   const GwBlob* blob;
 };
 
+#ifndef BRM_GW_EXEC_MIN_CTAS
+#define BRM_GW_EXEC_MIN_CTAS 4  /* measured on B200: 4 (64 regs) > 3 > 5 > 6 > 8 */
+#endif
 template <int A>
-__global__ void __launch_bounds__(256) gw_execute_kernel(const GwExecArgs args) {
+__global__ void __launch_bounds__(256, BRM_GW_EXEC_MIN_CTAS) gw_execute_kernel(const GwExecArgs args) {
   __shared__ GwBlob sB;
   __shared__ __align__(8) uint64_t bar;
   stage_blob(&sB, args.blob, static_cast<uint32_t>(sizeof(GwBlob)), &bar, 0, true);
@@ -456,7 +459,7 @@ int gw_launch_execute(brm_engine* e, const brm_gw_states& in, const uint8_t* act
   a.actions = actions;
   a.rewards = rewards;
   a.blob = e->d_gw_blob;
-  const int grid = grid_for(e, in.n, 256, 8);
+  const int grid = grid_for(e, in.n, 256, BRM_GW_EXEC_MIN_CTAS * 4);
   int rc = dispatch_agents<ExecLauncher>(e->gw_blob.A, e, a, grid);
   if (rc != BRM_OK) return rc;
   e->launches++;
