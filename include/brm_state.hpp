@@ -272,8 +272,10 @@ class MvmctsState {
   }
   const std::vector<float>& GetAgentStates() const { return agents_; }
   const std::vector<uint8_t>& GetMultiAgentRuleState() const { return q_; }
+  const std::shared_ptr<RulesMctsContext>& Context() const { return ctx_; }
 
  private:
+  friend class RulesMctsRolloutEvaluator;
   static brm_cw_states view(MvmctsState* s, uint32_t* viol) {
     brm_cw_states b;
     b.n = 1;
@@ -294,6 +296,62 @@ class MvmctsState {
   int32_t horizon_;
   uint8_t terminal_;
   std::vector<uint8_t> q_;
+};
+
+// Replaces mvmcts::RandomHeuristic::GetHeuristicValues for a batch of MvmctsState leaves
+// (instantiated in the reference at src/behavior_rules_mcts.hpp:188-189).
+class RulesMctsRolloutEvaluator {
+ public:
+  RulesMctsRolloutEvaluator(std::shared_ptr<RulesMctsContext> ctx, const brm_rollout_params& rp)
+      : ctx_(std::move(ctx)), rp_(rp) {}
+
+  // returns [leaf][agent] -> Reward (mean over rollouts_per_leaf rollouts)
+  std::vector<std::vector<Reward>> Evaluate(const std::vector<std::shared_ptr<MvmctsState>>& leaves,
+                                            uint64_t rollout_base) {
+    const int A = ctx_->A, M = ctx_->M, V = ctx_->V, R = ctx_->R;
+    const size_t L = leaves.size();
+    std::vector<int32_t> scenario(L), horizon(L);
+    std::vector<float> agents(static_cast<size_t>(A) * L * 4);
+    std::vector<uint8_t> flags(static_cast<size_t>(A) * L), terminal(L), q(static_cast<size_t>(M) * R * L);
+    for (size_t l = 0; l < L; ++l) {
+      const MvmctsState& s = *leaves[l];
+      scenario[l] = s.scenario_;
+      horizon[l] = s.horizon_;
+      terminal[l] = s.terminal_;
+      for (int a = 0; a < A; ++a) {
+        std::memcpy(&agents[(static_cast<size_t>(a) * L + l) * 4], &s.agents_[4 * a], 4 * sizeof(float));
+        flags[static_cast<size_t>(a) * L + l] = s.flags_[a];
+      }
+      for (int a = 0; a < M; ++a)
+        for (int r = 0; r < R; ++r) q[(static_cast<size_t>(a) * R + r) * L + l] = s.q_[a * R + r];
+    }
+    brm_cw_states b;
+    b.n = static_cast<int32_t>(L);
+    b.mem = BRM_MEM_HOST;
+    b.scenario = scenario.data();
+    b.agents = agents.data();
+    b.flags = flags.data();
+    b.horizon = horizon.data();
+    b.terminal = terminal.data();
+    b.q = q.data();
+    b.viol = nullptr;
+    std::vector<double> sums(L * M * V);
+    brm_cw_rollout_out out;
+    std::memset(&out, 0, sizeof(out));
+    out.returns_sum = sums.data();
+    brm_rollout_params rp = rp_;
+    rp.rollout_base = rollout_base;
+    check(brm_cw_rollout(ctx_->engine->get(), &b, &rp, &out));
+    std::vector<std::vector<Reward>> res(L, std::vector<Reward>(M, Reward(V, 0.0)));
+    for (size_t l = 0; l < L; ++l)
+      for (int a = 0; a < M; ++a)
+        for (int v = 0; v < V; ++v) res[l][a][v] = sums[(l * M + a) * V + v] / rp.rollouts_per_leaf;
+    return res;
+  }
+
+ private:
+  std::shared_ptr<RulesMctsContext> ctx_;
+  brm_rollout_params rp_;
 };
 
 }  // namespace brm

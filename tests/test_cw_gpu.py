@@ -292,3 +292,42 @@ def test_replay_matches_committed_golden_traces(built):
             o["steps"] = int(g[name + "/steps"][b])
             compared += compare_trace(tr, b, o, scn)
         assert compared > 0.8 * int(g[name + "/steps"].sum())
+
+
+@pytest.mark.parametrize("n_agents,n_mcts,n", [(1, 1, 333), (2, 1, 100), (7, 7, 65), (16, 16, 50), (16, 3, 31)])
+def test_edge_shapes_rollouts_match_oracle(built, orc, n_agents, n_mcts, n):
+    """Extreme shapes: one agent, the 16-agent maximum (2 rollouts per warp), rollout counts that
+    do not divide the lane groups, a mix of controlled and passive agents; many rule slots."""
+    rng = np.random.default_rng(n_agents * 17 + n_mcts)
+    base = scenarios.straight_road_test_world(n_others=0)
+    p = brm.RulesMctsStateParameters(REWARD_VECTOR_SIZE=3, HORIZON=12)
+    prim = [(0.0, 0.0), (2.0, 0.0), (-3.0, 0.0), (0.0, 0.03)]
+    agents = []
+    for i in range(n_agents):
+        agents.append(brm.AgentModel(primitives=prim if i < n_mcts else [(0.5, 0.0)], front=3.0, rear=1.0,
+                                     half_width=0.9, goal=(150.0, 400.0, -7.0, 0.0) if i == 0 else None))
+    rules = [RuleMonitor.MakeRule("G !collision_ego", -100.0, 0),
+             RuleMonitor.MakeRule("G safe_distance_front", -1.0, 1),
+             RuleMonitor.MakeRule("G !(near_x#0 & in_direct_front_x#0)", -1.0, 1)]
+    state = np.zeros((n_agents, 4), np.float32)
+    for i in range(n_agents):
+        lane_y = -1.75 if i % 2 == 0 else -5.25
+        state[i] = ((i // 2) * 14.0 + rng.uniform(0, 3), lane_y, 0.0, rng.uniform(4, 9))
+    scn = brm.Scenario(p, agents, n_mcts, base.lanes, base.road, rules, state)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    assert eng.R == 2 + (n_agents - 1)
+    cfg = oracle_config(scn)
+    out = eng.rollout(eng.initial_batch(), n, seed=5, max_steps=30, detail=True)
+    ref = orc.rollout_detail(cfg, scn.initial_state, FL(n_agents), 12, 5, 0, n, 30, p.DISCOUNT_FACTOR)
+    safe = ref["margin"] >= GUARD
+    same = ((out["ro_steps"] == ref["steps"]) & (out["ro_viol"] == ref["viol"]).all(axis=(1, 2)) &
+            (out["ro_q"] == ref["q"]).all(axis=(1, 2)) & (out["ro_flags"] == ref["flags"]).all(axis=1))
+    assert same[safe].all() and same.mean() > 0.97
+    assert close(out["ro_agents"][same], ref["states"][same], atol=ATOL_POS)
+    assert close(out["ro_returns"][same], ref["returns"][same], rtol=2e-5, atol=1e-3)
+    assert int(out["agent_steps"][0]) > 0
+    # leaves that are already terminal produce only the (discounted) terminal reward
+    term = eng.make_batch(state[None], horizon=0)
+    assert term.terminal[0] == 1
+    z = eng.rollout(term, 8, seed=1)
+    assert z["agent_steps"][0] == 0 and np.all(z["viol_sum"] == 0)
