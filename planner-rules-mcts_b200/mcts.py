@@ -1,0 +1,156 @@
+"""Host-side multi-agent MCTS that drives the device engine.
+
+The tree stays on the host, as north_star asks; every iteration expands one joint action with
+one batched `Execute` and evaluates the new node with ONE device launch of
+`rollouts_per_expansion` random rollouts (the mvmcts::RandomHeuristic call of the reference's
+iteration, src/behavior_rules_mcts.hpp:188-189,232).  Selection is decoupled UCT: every agent
+keeps its own per-action visit counts and value-vector sums and picks its action
+independently (untried actions first, then UCB on normalised values); vector values are
+compared in thresholded lexicographic order.  The reference's statistics classes
+(`ThresUCTStatistic`, `ThresGreedyStatistic`; un-vendored lexmamcts@24ab42ca) are not available,
+so the exact tie-breaking and exploration schedule are this module's own ("parity unpinned");
+what IS pinned are the planner-level behaviours of test/single_agent_test.cpp:229-270.
+"""
+import math
+
+import numpy as np
+
+from . import parallel
+
+
+class _Node:
+    __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q")
+
+    def __init__(self, state, n_actions, V):
+        self.state = state
+        self.terminal = bool(state.terminal[0])
+        self.n_actions = [int(k) for k in n_actions]
+        self.children = {}
+        self.N = [np.zeros(k) for k in self.n_actions]
+        self.Q = [np.zeros((k, V)) for k in self.n_actions]
+
+
+class MctsParameters:
+    """The mvmcts::MvmctsParameters fields the reference sets (src/util.cpp:23-89)."""
+
+    def __init__(self, V, discount_factor=0.9, exploration_constant=1.42, lower_bound=None, upper_bound=None,
+                 threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000):
+        self.DISCOUNT_FACTOR = discount_factor
+        self.EXPLORATION_CONSTANT = exploration_constant
+        lb = [-1.0] * V
+        lb[-1] = -1000.0                      # src/util.cpp:58-59
+        self.LOWER_BOUND = np.asarray(lower_bound if lower_bound is not None else lb, np.float64)
+        self.UPPER_BOUND = np.asarray(upper_bound if upper_bound is not None else [0.0] * V, np.float64)
+        self.THRESHOLD = None if threshold is None else np.asarray(threshold, np.float64)
+        self.MAX_NUMBER_OF_ITERATIONS = max_rollout_steps
+        self.rollouts_per_expansion = rollouts_per_expansion
+        self.seed = seed
+
+
+class Mcts:
+    """`Search(state, max_iterations)` / `ReturnBestAction()` / `GetRootStats()` -- the call
+    surface BehaviorRulesMcts::Plan uses on mvmcts::Mvmcts (src/behavior_rules_mcts.hpp:232-249)."""
+
+    def __init__(self, engine, params: MctsParameters):
+        self.engine = engine
+        self.p = params
+        self.root = None
+        self.iterations = 0
+        self._next_rollout = 0
+
+    # -- helpers -----------------------------------------------------------------------
+    def _make_node(self, state):
+        return _Node(state, self.engine.get_num_actions(state)[:, 0], self.engine.V)
+
+    def _lex_better(self, a, b):
+        """a better than b in thresholded lexicographic order."""
+        thr = self.p.THRESHOLD
+        for k in range(len(a)):
+            x, y = a[k], b[k]
+            if thr is not None:
+                x, y = min(x, thr[k]), min(y, thr[k])
+            if abs(x - y) > 1e-12:
+                return x > y
+        return False
+
+    def _select(self, node):
+        ja = []
+        span = np.maximum(self.p.UPPER_BOUND - self.p.LOWER_BOUND, 1e-9)
+        for a, k in enumerate(node.n_actions):
+            untried = np.flatnonzero(node.N[a] == 0)
+            if len(untried):
+                ja.append(int(untried[0]))
+                continue
+            total = node.N[a].sum()
+            mean = node.Q[a] / node.N[a][:, None]
+            norm = (mean - self.p.LOWER_BOUND) / span
+            bonus = self.p.EXPLORATION_CONSTANT * np.sqrt(2.0 * math.log(total) / node.N[a])
+            ucb = norm + bonus[:, None]
+            best = 0
+            for act in range(1, k):
+                if self._lex_better(ucb[act], ucb[best]):
+                    best = act
+            ja.append(best)
+        return tuple(ja)
+
+    def _evaluate(self, node):
+        """RandomHeuristic: mean discounted return of random rollouts from the node."""
+        n = self.p.rollouts_per_expansion
+        out = self.engine.rollout(node.state, n, seed=self.p.seed, rollout_base=self._next_rollout,
+                                  max_steps=self.p.MAX_NUMBER_OF_ITERATIONS,
+                                  discount_factor=self.p.DISCOUNT_FACTOR, first_discount_exp=0)
+        self._next_rollout += n
+        return out["returns_sum"][0] / n  # [M][V]
+
+    # -- search ----------------------------------------------------------------------------
+    def Search(self, state, max_iterations):
+        self.root = self._make_node(state)
+        if self.root.terminal:
+            raise RuntimeError("Current state is terminal! Aborting!")  # src/behavior_rules_mcts.hpp:208-209
+        gamma = self.p.DISCOUNT_FACTOR
+        M, V = self.engine.M, self.engine.V
+        for _ in range(max_iterations):
+            node, path = self.root, []
+            while True:
+                if node.terminal:
+                    value = self.engine.terminal_reward(node.state)[:, :, 0].astype(np.float64)
+                    break
+                ja = self._select(node)
+                if ja in node.children:
+                    child, r = node.children[ja]
+                    path.append((node, ja, r))
+                    node = child
+                    continue
+                nxt, rew = self.engine.execute(node.state, np.array(ja, np.uint8).reshape(M, 1))
+                child = self._make_node(nxt)
+                r = rew[:, :, 0].astype(np.float64)
+                node.children[ja] = (child, r)
+                path.append((node, ja, r))
+                value = self._evaluate(child)
+                break
+            for nd, ja, r in reversed(path):
+                value = r + gamma * value
+                for a in range(M):
+                    nd.N[a][ja[a]] += 1
+                    nd.Q[a][ja[a]] += value[a]
+            self.iterations += 1
+        return self
+
+    def GetRootStats(self):
+        """Packed root statistics [M][n_actions][1+V] (what ranks allreduce)."""
+        M, V = self.engine.M, self.engine.V
+        k = max(self.root.n_actions)
+        s = np.zeros((M, k, 1 + V))
+        for a in range(M):
+            s[a, :self.root.n_actions[a], 0] = self.root.N[a]
+            s[a, :self.root.n_actions[a], 1:] = self.root.Q[a]
+        return s
+
+    def ReturnBestAction(self, merge=True):
+        stats = self.GetRootStats()
+        if merge:
+            parallel.merge_root_stats(stats)  # root-parallel: sum over ranks
+        return [int(x) for x in parallel.best_actions(stats, self.p.THRESHOLD)]
+
+    def NumIterations(self):
+        return self.iterations
