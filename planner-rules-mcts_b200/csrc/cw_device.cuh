@@ -40,6 +40,7 @@ struct alignas(16) CwBlob {
   float v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
   float near2, inv_dt, _p2, _p3;
   float front[BRM_CW_MAX_AGENTS], rear[BRM_CW_MAX_AGENTS], hw[BRM_CW_MAX_AGENTS];
+  float rad[BRM_CW_MAX_AGENTS];  // circumscribed radius of the rectangle (a hair more), about its centre
   float goal[BRM_CW_MAX_AGENTS][6];
   uint8_t has_goal[BRM_CW_MAX_AGENTS], n_prims[BRM_CW_MAX_AGENTS];
   float prim_a[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];
@@ -301,6 +302,9 @@ __device__ __forceinline__ bool cw_rect_overlap(const CwBlob& B, const CwAgent& 
   const float eiy = B.hw[a], ejy = B.hw[j];
   const float dx = (p.x + oj * p.cs) - (t.x + oi * t.cs);
   const float dy = (p.y + oj * p.sn) - (t.y + oi * t.sn);
+  // circumscribed circles apart: the rectangles cannot touch (exact early-out; most pairs)
+  const float rr = B.rad[a] + B.rad[j];
+  if (dx * dx + dy * dy > rr * rr) return false;
   const float cd = fabsf(t.cs * p.cs + t.sn * p.sn), sd = fabsf(t.sn * p.cs - t.cs * p.sn);
   bool hit = fabsf(dx * t.cs + dy * t.sn) <= eix + ejx * cd + ejy * sd;
   hit = (fabsf(-dx * t.sn + dy * t.cs) <= eiy + ejx * sd + ejy * cd) && hit;
@@ -422,6 +426,10 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
         const int rank = static_cast<int>((rec.z >> 8) & 0xffu) - 1;
         const int other = rank < 0 ? 0 : (rank < a ? rank : rank + 1);
         const uint32_t n_aps = rec.y & 0xffu;
+        const uint32_t cur = q[sl * col_stride];
+        // absorbing state without violations (e.g. the ZIP monitor once its antecedent has
+        // failed): nothing can change any more, skip the letter and the table
+        if ((rec.z >> (16 + cur)) & 1u) continue;
         // label word of this slot: ego kinds in bits 0..7, the bound agent's kinds in 8..10
         const uint32_t W = w0 | (((merged_mask >> other) & 1u) << BRM_CW_LABEL_MERGED_X) |
                            (((front_mask >> other) & 1u) << BRM_CW_LABEL_IN_DIRECT_FRONT_X) |
@@ -432,7 +440,6 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
           const uint32_t bit = (W >> ((rec.x >> (8 * k)) & 0xffu)) & 1u;
           if (k < n_aps) letter |= bit << (n_aps - 1 - k);
         }
-        const uint32_t cur = q[sl * col_stride];
         uint32_t nxt = B.rules[rec.z & 0xffu].trans[(cur << n_aps) + letter];
         if (nxt == BRM_VIOLATION) {
           viol[sl * col_stride] += 1;

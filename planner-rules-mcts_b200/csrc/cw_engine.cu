@@ -102,6 +102,10 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
     B->front[i] = ag.front;
     B->rear[i] = ag.rear;
     B->hw[i] = ag.half_width;
+    {
+      const double ex = 0.5 * (static_cast<double>(ag.front) + ag.rear), ey = ag.half_width;
+      B->rad[i] = static_cast<float>(std::sqrt(ex * ex + ey * ey) * (1.0 + 1e-5) + 1e-4);
+    }
     B->has_goal[i] = ag.has_goal ? 1 : 0;
     for (int k = 0; k < 6; ++k) B->goal[i][k] = ag.goal[k];
     B->n_prims[i] = static_cast<uint8_t>(ag.n_prims);
@@ -144,6 +148,12 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
       rec.y = static_cast<uint32_t>(r.n_aps) | (static_cast<uint32_t>(r.priority) << 8) |
               (static_cast<uint32_t>(r.init_state) << 16) | (static_cast<uint32_t>(r.on_violation ? 1 : 0) << 24);
       rec.z = static_cast<uint32_t>(k) | (static_cast<uint32_t>(rule_specific(r) ? j + 1 : 0) << 8);
+      // bits 16..31: states that loop to themselves on every letter (absorbing, no violation)
+      for (int q = 0; q < r.n_states; ++q) {
+        bool sink = true;
+        for (int l = 0; l < (1 << r.n_aps); ++l) sink = sink && r.trans[q * (1 << r.n_aps) + l] == q;
+        if (sink) rec.z |= 1u << (16 + q);
+      }
       memcpy(&rec.w, &r.weight, sizeof(float));
       B->slot_rec[R] = rec;
       ++R;
