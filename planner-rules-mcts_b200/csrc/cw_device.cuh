@@ -1,8 +1,11 @@
 // Device-side continuous-world step: MvmctsState::Execute
-// (/root/reference/src/rules_mcts_state.cpp:57-128) with one lane = one agent of one
-// rollout.  floor(32/A) rollouts share a warp; agents of a rollout exchange poses with
-// warp shuffles, pairwise predicates (collision, preceding agent, near) are evaluated
-// by every lane against its group, the rule automata of an agent step in its lane.
+// (/root/reference/src/rules_mcts_state.cpp:57-128) with one lane = one MCTS agent of one
+// rollout.  floor(32/M) rollouts share a warp (M = agents in the reference's agent_idx
+// list); the agents that are only simulated (constant-acceleration prediction, not in
+// agent_idx) are dealt round-robin to the lanes of their rollout, which keep them in
+// shared-memory columns and step them in a loop.  Agents of a rollout exchange poses with
+// warp shuffles, pairwise predicates (collision, preceding agent, near) are evaluated by
+// every lane against its group, the rule automata of an agent step in its lane.
 // The scenario blob (parameters, lane polylines, road polygon, automaton tables) sits in
 // shared memory, staged by a TMA bulk copy.
 #pragma once
@@ -35,7 +38,7 @@ constexpr int kCwMaxBlkTotal = BRM_CW_MAX_LANES * kCwMaxBlk;            // 64: o
 
 struct alignas(16) CwBlob {
   int32_t A, M, V, R, n_lanes, n_road, n_rules, n_sub;
-  int32_t ego_only, total_bytes, n_blk, _p1;
+  int32_t ego_only, total_bytes, n_blk, Ps;  // Ps: passive-agent slots per lane = ceil((A-M)/M)
   float w_coll, w_oom, w_pot, w_acc, w_rad, w_vel, w_lane, dt;
   float v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
   float near2, inv_dt, _p2, _p3;
@@ -43,6 +46,8 @@ struct alignas(16) CwBlob {
   float rad[BRM_CW_MAX_AGENTS];  // circumscribed radius of the rectangle (a hair more), about its centre
   float goal[BRM_CW_MAX_AGENTS][6];
   uint8_t has_goal[BRM_CW_MAX_AGENTS], n_prims[BRM_CW_MAX_AGENTS];
+  // passive agent j >= M lives in slot pas_slot[j] of the lane with agent index pas_owner[j]
+  uint8_t pas_owner[BRM_CW_MAX_AGENTS], pas_slot[BRM_CW_MAX_AGENTS];
   float prim_a[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];
   float prim_k[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];  // tan(delta) / wheel_base
   uint8_t slot_rule[BRM_CW_MAX_SLOTS];
@@ -71,7 +76,8 @@ struct CwCommon {
   const int32_t* blob_bytes;  // used bytes of each blob (multiple of 16)
   size_t blob_stride;
   int32_t blob_cap;           // bytes reserved for the blob in shared memory
-  int32_t A, M, V, R, G;      // G = rollouts (states) per warp
+  int32_t A, M, V, R, G;      // G = rollouts (states) per warp = 32 / M
+  int32_t Ps;                 // passive-agent slots per lane
 };
 struct CwLaunchCtx {
   CwCommon c;
@@ -294,6 +300,48 @@ __device__ __forceinline__ CwPeer cw_fetch(const CwAgent& t, int src) {
   return p;
 }
 
+// ---- passive agents: kCwPasWords words per slot in this thread's shared-memory column
+constexpr int kCwPasWords = 13;
+
+__device__ __forceinline__ void cw_pas_store(float* col, int slot, const CwAgent& t) {
+  float* p = col + slot * kCwPasWords * kCwThreads;
+  p[0 * kCwThreads] = t.x;  p[1 * kCwThreads] = t.y;  p[2 * kCwThreads] = t.th;  p[3 * kCwThreads] = t.v;
+  p[4 * kCwThreads] = t.cs; p[5 * kCwThreads] = t.sn; p[6 * kCwThreads] = t.s;
+  p[7 * kCwThreads] = t.ex; p[8 * kCwThreads] = t.ey; p[9 * kCwThreads] = t.eth; p[10 * kCwThreads] = t.ev;
+  p[11 * kCwThreads] = __int_as_float((t.lane << 8) | static_cast<int>(t.flags));
+  p[12 * kCwThreads] = t.lat;
+}
+
+__device__ __forceinline__ void cw_pas_load(const float* col, int slot, CwAgent& t) {
+  const float* p = col + slot * kCwPasWords * kCwThreads;
+  t.x = p[0 * kCwThreads];  t.y = p[1 * kCwThreads];  t.th = p[2 * kCwThreads];  t.v = p[3 * kCwThreads];
+  t.cs = p[4 * kCwThreads]; t.sn = p[5 * kCwThreads]; t.s = p[6 * kCwThreads];
+  t.ex = p[7 * kCwThreads]; t.ey = p[8 * kCwThreads]; t.eth = p[9 * kCwThreads]; t.ev = p[10 * kCwThreads];
+  const int packed = __float_as_int(p[11 * kCwThreads]);
+  t.lane = packed >> 8;
+  t.flags = static_cast<uint32_t>(packed) & 0xffu;
+  t.lat = p[12 * kCwThreads];
+}
+
+// pose of passive agent j of my rollout, read straight from its owner lane's shared-memory
+// column (the lanes of a rollout sit next to each other, so the column is `owner - a` away);
+// the owner's stores must be ordered before this by a __syncwarp()
+__device__ __forceinline__ CwPeer cw_fetch_passive(const CwBlob& B, const float* pas, int j, int a, bool real) {
+  const float* p = pas + (real ? static_cast<int>(B.pas_owner[j]) - a : 0) +
+                   static_cast<int>(B.pas_slot[j]) * kCwPasWords * kCwThreads;
+  CwPeer r;
+  r.x = p[0 * kCwThreads];
+  r.y = p[1 * kCwThreads];
+  r.v = p[3 * kCwThreads];
+  r.cs = p[4 * kCwThreads];
+  r.sn = p[5 * kCwThreads];
+  r.s = p[6 * kCwThreads];
+  const int packed = __float_as_int(p[11 * kCwThreads]);
+  r.lane = packed >> 8;
+  r.flags = static_cast<uint32_t>(packed) & 0xffu;
+  return r;
+}
+
 // separating-axis test of my rectangle against peer j's
 __device__ __forceinline__ bool cw_rect_overlap(const CwBlob& B, const CwAgent& t, int a,
                                                 const CwPeer& p, int j) {
@@ -320,11 +368,11 @@ __device__ __forceinline__ bool cw_rect_overlap(const CwBlob& B, const CwAgent& 
 //   live    : my group executes this step
 //   in_*    : my agent's v, theta, flags BEFORE the kinematic step
 //   q, viol : this thread's column of the per-slot automaton state / violation counters
-template <bool WITH_LABELS>
+template <bool WITH_LABELS, bool PASSIVE>
 __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, int base, bool real,
                                             bool live, float in_v, float in_th, uint32_t in_flags,
                                             int horizon_after, uint8_t* q, uint8_t* viol,
-                                            int col_stride, CwStepOut& o) {
+                                            int col_stride, const float* pas, CwStepOut& o) {
   const int A = B.A, M = B.M, V = B.V;
   const bool present = real && (t.flags & BRM_CW_PRESENT);
   const bool evaluated = live && present && (in_flags & BRM_CW_VALID) && a < M;
@@ -339,16 +387,15 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
     oom = cw_out_of_map(B, t, a, cx, cy);
     goal = cw_at_goal(B, t, a, cx, cy);
   }
-  // pairwise predicates against the agents of my group
+  // pairwise predicates against the agents of my rollout
   bool coll = false;
   int jf = -1;
-  float gf = 0.f;
+  float gf = 0.f, vf = 0.f;
   uint32_t merged_mask = 0, near_mask = 0;
   const float my_len = (t.lane >= 0) ? B.lanes[t.lane].length : 0.f;
   const int my_succ = (t.lane >= 0) ? B.lanes[t.lane].succ : -2;
-  for (int j = 0; j < A; ++j) {
-    const CwPeer p = cw_fetch(t, base + j);
-    if (j == a || !(p.flags & BRM_CW_PRESENT) || !present) continue;
+  auto pair = [&](int j, const CwPeer& p) {
+    if (j == a || !(p.flags & BRM_CW_PRESENT) || !present) return;
     coll = cw_rect_overlap(B, t, a, p, j) || coll;
     // gap along my corridor: own lane, then its successor
     if (t.lane >= 0 && p.lane >= 0) {
@@ -364,14 +411,22 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
       if (has && g > 0.f && (jf < 0 || g < gf)) {
         jf = j;
         gf = g;
+        vf = p.v;
       }
     }
     if (p.lane >= 0 && p.s >= B.lanes[p.lane].s_point) merged_mask |= 1u << j;
     const float dx = p.x - t.x, dy = p.y - t.y;
     if (dx * dx + dy * dy < B.near2) near_mask |= 1u << j;
+  };
+  // MCTS agents sit in the registers of the lanes of my group
+  for (int j = 0; j < M; ++j) pair(j, cw_fetch(t, base + j));
+  if (PASSIVE) {
+    // the other agents in the shared-memory slots of those lanes (ascending j: ties in the
+    // preceding-agent search resolve as in one loop over all agents)
+    __syncwarp();
+    for (int j = M; j < A; ++j) pair(j, cw_fetch_passive(B, pas, j, a, real));
+    __syncwarp();
   }
-  // speed of the preceding agent (one more shuffle, executed by all lanes)
-  const float vf = __shfl_sync(0xffffffffu, t.v, base + (jf < 0 ? 0 : jf));
 
   if (evaluated) {
     o.r[0] += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92

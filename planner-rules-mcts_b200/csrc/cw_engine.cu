@@ -115,6 +115,15 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
                                            static_cast<double>(p.wheel_base));
     }
   }
+  // passive agents (not in the MCTS agent list) are dealt round-robin to the M lanes of a rollout
+  {
+    const int M = s.n_mcts_agents, P = s.n_agents - M;
+    B->Ps = (P + M - 1) / M;
+    for (int j = M; j < s.n_agents; ++j) {
+      B->pas_owner[j] = static_cast<uint8_t>((j - M) % M);
+      B->pas_slot[j] = static_cast<uint8_t>((j - M) / M);
+    }
+  }
   // rule slots of an agent: rules in order, agent-specific ones once per other world agent
   // ascending (BehaviorRulesMcts::MakeRuleStates, src/behavior_rules_mcts.hpp:295-322)
   int R = 0;
@@ -370,8 +379,10 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
   c->ctx.c.M = M;
   c->ctx.c.V = V;
   c->ctx.c.R = R;
-  c->ctx.c.G = 32 / A;
-  c->ctx.smem_bytes = static_cast<size_t>(cap) + 2u * static_cast<size_t>(R) * kThreads;
+  c->ctx.c.G = 32 / M;  // one lane per MCTS agent
+  c->ctx.c.Ps = (A - M + M - 1) / M;
+  c->ctx.smem_bytes = static_cast<size_t>(cap) + 2u * static_cast<size_t>(R) * kThreads +
+                      static_cast<size_t>(c->ctx.c.Ps) * kCwPasWords * sizeof(float) * kThreads;
   e->cw = c;
   return BRM_OK;
 }

@@ -1,7 +1,8 @@
 // Continuous-world kernels (sm_100a):
 //   K3 cw_rollout_kernel   fused random rollouts (mvmcts::RandomHeuristic over
-//                          MvmctsState::Execute): lane = agent, floor(32/A) rollouts in
-//                          flight per warp, finished rollouts are replaced at once
+//                          MvmctsState::Execute): lane = MCTS agent, floor(32/M) rollouts in
+//                          flight per warp, finished rollouts are replaced at once; agents
+//                          that are only simulated live in shared-memory slots of the lanes
 //   K4 cw_batch_kernel<EXECUTE>  one Execute for n states
 //   K6 cw_batch_kernel<REPLAY>   replay of given action sequences with a full trace
 //      cw_batch_kernel<QUERY>    CheckTerminal / GetNumActions / GetTerminalReward
@@ -20,19 +21,26 @@ constexpr int kThreads = kCwThreads;
 constexpr int kWarps = kThreads / 32;
 constexpr double kFixScale = 1048576.0;  // 2^20: fixed-point scale of the per-leaf return sums
 
-// shared memory layout: [blob_cap bytes blob][R*kThreads q][R*kThreads viol]
-//                       (+ rollout kernel: [R*kThreads u32 violation totals][kWarps*A leaf poses])
+// shared memory layout: [blob_cap bytes blob][R*T q][R*T viol][Ps*kCwPasWords*T floats passive agents]
+//                       (+ rollout kernel: [R*T u32 violation totals][kWarps*A leaf poses])
 struct CwSmem {
   const CwBlob* B;
   uint8_t* q;     // this thread's column
   uint8_t* viol;  // this thread's column
+  float* pas;     // this thread's column of passive-agent slots
 };
+
+__device__ __forceinline__ size_t cw_common_bytes(const CwCommon& c) {
+  return static_cast<size_t>(c.blob_cap) + 2u * c.R * kThreads +
+         static_cast<size_t>(c.Ps) * kCwPasWords * sizeof(float) * kThreads;
+}
 
 __device__ __forceinline__ CwSmem cw_smem(uint8_t* smem, const CwCommon& c) {
   CwSmem s;
   s.B = reinterpret_cast<const CwBlob*>(smem);
   s.q = smem + c.blob_cap + threadIdx.x;
   s.viol = smem + c.blob_cap + c.R * kThreads + threadIdx.x;
+  s.pas = reinterpret_cast<float*>(smem + c.blob_cap + 2 * c.R * kThreads) + threadIdx.x;
   return s;
 }
 
@@ -58,8 +66,23 @@ __device__ __forceinline__ void cw_stage(uint8_t* smem, uint64_t* bar, const CwC
   cur_scn = scn;
 }
 
-__device__ __forceinline__ void cw_load_agent(const brm_cw_states& S, int64_t i, int a, bool on,
-                                              CwAgent& t) {
+// lane -> (rollout group, MCTS agent)
+struct CwMap {
+  int lane, a, g, base;
+  bool real;
+};
+
+__device__ __forceinline__ CwMap cw_map(const CwCommon& c) {
+  CwMap m;
+  m.lane = threadIdx.x & 31;
+  m.a = m.lane % c.M;
+  m.g = m.lane / c.M;
+  m.base = m.g * c.M;
+  m.real = m.g < c.G;
+  return m;
+}
+
+__device__ __forceinline__ void cw_clear_agent(CwAgent& t) {
   t.x = t.y = t.th = t.v = 0.f;
   t.cs = 1.f;
   t.sn = 0.f;
@@ -67,11 +90,32 @@ __device__ __forceinline__ void cw_load_agent(const brm_cw_states& S, int64_t i,
   t.lane = -1;
   t.s = t.lat = 0.f;
   t.ex = t.ey = t.eth = t.ev = 0.f;
+}
+
+// agent `agent` of state i of batch S (no lane projection yet)
+__device__ __forceinline__ void cw_load_agent(const brm_cw_states& S, int64_t i, int agent, bool on,
+                                              CwAgent& t) {
+  cw_clear_agent(t);
   if (on) {
-    const float4 v = reinterpret_cast<const float4*>(S.agents)[static_cast<int64_t>(a) * S.n + i];
+    const float4 v = reinterpret_cast<const float4*>(S.agents)[static_cast<int64_t>(agent) * S.n + i];
     t.x = v.x; t.y = v.y; t.th = v.z; t.v = v.w;
-    t.flags = S.flags[static_cast<int64_t>(a) * S.n + i];
+    t.flags = S.flags[static_cast<int64_t>(agent) * S.n + i];
     sincosf(t.th, &t.sn, &t.cs);
+  }
+}
+
+// whole state i for my lane: my MCTS agent into registers, my passive agents into their slots
+__device__ __forceinline__ void cw_load_state(const brm_cw_states& S, const CwBlob& B, const CwCommon& c,
+                                              const CwMap& m, const CwSmem& sm, int64_t i, bool on,
+                                              CwAgent& t) {
+  cw_load_agent(S, i, m.a, on, t);
+  if (t.flags & BRM_CW_PRESENT) cw_frenet(B, t);
+  for (int slot = 0; slot < c.Ps; ++slot) {
+    const int j = c.M + slot * c.M + m.a;
+    CwAgent p;
+    cw_load_agent(S, i, j < c.A ? j : 0, on && j < c.A, p);
+    if (p.flags & BRM_CW_PRESENT) cw_frenet(B, p);
+    cw_pas_store(sm.pas, slot, p);
   }
 }
 
@@ -79,7 +123,7 @@ __device__ __forceinline__ void cw_load_rules(const brm_cw_states& S, const CwCo
                                               int a, bool on, const CwSmem& sm, bool with_viol) {
   for (int sl = 0; sl < c.R; ++sl) {
     uint8_t q = 0, v = 0;
-    if (on && a < c.M) {
+    if (on) {
       const int64_t o = (static_cast<int64_t>(a) * c.R + sl) * S.n + i;
       q = S.q[o];
       if (with_viol && S.viol) v = static_cast<uint8_t>(S.viol[o]);
@@ -87,6 +131,26 @@ __device__ __forceinline__ void cw_load_rules(const brm_cw_states& S, const CwCo
     sm.q[sl * kThreads] = q;
     sm.viol[sl * kThreads] = v;
   }
+}
+
+// Predict for my passive agents: they follow primitive 0 of their own table
+// (BehaviorConstantAcceleration in the reference's prediction settings)
+__device__ __forceinline__ uint32_t cw_move_passive(const CwBlob& B, const CwCommon& c, const CwMap& m,
+                                                    const CwSmem& sm, bool live) {
+  uint32_t moved = 0;
+  for (int slot = 0; slot < c.Ps; ++slot) {
+    const int j = c.M + slot * c.M + m.a;
+    if (!live || j >= c.A) continue;
+    CwAgent p;
+    cw_pas_load(sm.pas, slot, p);
+    if ((p.flags & BRM_CW_PRESENT) && (p.flags & BRM_CW_VALID)) {
+      cw_integrate(B, p, j, 0u);
+      cw_frenet(B, p);
+      cw_pas_store(sm.pas, slot, p);
+      ++moved;
+    }
+  }
+  return moved;
 }
 
 // ------------------------------------------------------------------ K3 rollout
@@ -109,29 +173,36 @@ struct CwPose {
   uint32_t flags;
 };
 
+__device__ __forceinline__ void cw_from_pose(const CwPose& p, CwAgent& t) {
+  t.x = p.x; t.y = p.y; t.th = p.th; t.v = p.v; t.cs = p.cs; t.sn = p.sn;
+  t.s = p.s; t.lat = p.lat; t.lane = p.lane; t.flags = p.flags;
+  t.ex = t.ey = t.eth = t.ev = 0.f;
+}
+
 // All rollouts idx in [seg_begin, seg_end) of one leaf, executed by one warp.  Up to G
 // rollouts are in flight (one per lane group); when one ends its group immediately takes
 // the next index, so lanes only idle at the very end of the segment.
+template <bool PASSIVE>
 __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const CwBlob& B, const CwSmem& sm,
                                                uint32_t* viol_tot, CwPose* pose_w, int64_t leaf,
                                                int seg_begin, int seg_end) {
   const CwCommon& c = args.c;
-  const int lane = threadIdx.x & 31;
+  const CwMap m = cw_map(c);
+  const int lane = m.lane, a = m.a, g = m.g, base = m.base;
+  const bool real = m.real;
   const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
-  const int a = lane % A, g = lane / A, base = g * A;
-  const bool real = g < G;
   const uint32_t full = 0xffffffffu;
 
-  // leaf pose -> per-warp shared copy (lanes of group 0 load and project it)
+  // leaf pose of every agent -> per-warp shared copy (lane l < A loads and projects agent l)
   {
     CwAgent t0;
-    cw_load_agent(args.leaves, leaf, a, g == 0, t0);
-    if (g == 0 && (t0.flags & BRM_CW_PRESENT)) cw_frenet(B, t0);
-    if (g == 0) {
+    cw_load_agent(args.leaves, leaf, lane < A ? lane : 0, lane < A, t0);
+    if (t0.flags & BRM_CW_PRESENT) cw_frenet(B, t0);
+    if (lane < A) {
       CwPose p;
       p.x = t0.x; p.y = t0.y; p.th = t0.th; p.v = t0.v; p.cs = t0.cs; p.sn = t0.sn;
       p.s = t0.s; p.lat = t0.lat; p.lane = t0.lane; p.flags = t0.flags;
-      pose_w[a] = p;
+      pose_w[lane] = p;
     }
   }
   __syncwarp();
@@ -140,9 +211,7 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
   for (int sl = 0; sl < R; ++sl) viol_tot[sl * kThreads] = 0u;
 
   CwAgent t;
-  t.flags = 0; t.lane = -1;
-  t.x = t.y = t.th = t.v = t.s = t.lat = 0.f; t.cs = 1.f; t.sn = 0.f;
-  t.ex = t.ey = t.eth = t.ev = 0.f;
+  cw_clear_agent(t);
   float acc[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
   double acc_tot[BRM_MAX_REWARD] = {0.0, 0.0, 0.0, 0.0};
   float disc = 1.f;
@@ -162,12 +231,18 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
       if (real && !busy && cand < seg_end) {
         idx = cand;
         rid = args.rollout_base + static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
-        const CwPose p = pose_w[a];
-        t.x = p.x; t.y = p.y; t.th = p.th; t.v = p.v; t.cs = p.cs; t.sn = p.sn;
-        t.s = p.s; t.lat = p.lat; t.lane = p.lane; t.flags = p.flags;
-        t.ex = t.ey = t.eth = t.ev = 0.f;
+        cw_from_pose(pose_w[a], t);
+        if (PASSIVE) {
+          for (int slot = 0; slot < c.Ps; ++slot) {
+            const int j = M + slot * M + a;
+            CwAgent p;
+            cw_clear_agent(p);
+            if (j < A) cw_from_pose(pose_w[j], p);
+            cw_pas_store(sm.pas, slot, p);
+          }
+        }
         for (int sl = 0; sl < R; ++sl) {
-          sm.q[sl * kThreads] = (a < M) ? args.leaves.q[(static_cast<int64_t>(a) * R + sl) * args.leaves.n + leaf] : 0;
+          sm.q[sl * kThreads] = args.leaves.q[(static_cast<int64_t>(a) * R + sl) * args.leaves.n + leaf];
           sm.viol[sl * kThreads] = 0;
         }
 #pragma unroll
@@ -186,7 +261,7 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
     const bool live = busy && !done && k < args.max_steps;
     const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
     uint32_t act = 0;
-    if (live && a < M) {
+    if (live) {
       if ((k & 3) == 0) blk = action_block(args.seed, rid, k, a);
       act = draw_action(pick_word(blk, k), movable ? B.n_prims[a] : 1u);
     }
@@ -197,9 +272,10 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
       cw_frenet(B, t);
       ++agent_steps;
     }
+    if (PASSIVE) agent_steps += cw_move_passive(B, c, m, sm, live);
     CwStepOut o;
-    cw_evaluate<false>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                       kThreads, o);
+    cw_evaluate<false, PASSIVE>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                       kThreads, sm.pas, o);
     if (live) {
 #pragma unroll
       for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * o.r[v];
@@ -215,22 +291,31 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
 #pragma unroll
       for (int v = 0; v < BRM_MAX_REWARD; ++v) {
         acc[v] += disc * tr[v];
-        if (a < M) acc_tot[v] += static_cast<double>(acc[v]);
+        acc_tot[v] += static_cast<double>(acc[v]);
       }
       const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
-      if (a < M) {
-        if (args.out.ro_returns)
-          for (int v = 0; v < V; ++v) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
-        for (int sl = 0; sl < R; ++sl) {
-          const uint8_t vv = sm.viol[sl * kThreads];
-          viol_tot[sl * kThreads] += vv;
-          if (args.out.ro_viol) args.out.ro_viol[(local * M + a) * R + sl] = vv;
-          if (args.out.ro_q) args.out.ro_q[(local * M + a) * R + sl] = sm.q[sl * kThreads];
-        }
+      if (args.out.ro_returns)
+        for (int v = 0; v < V; ++v) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
+      for (int sl = 0; sl < R; ++sl) {
+        const uint8_t vv = sm.viol[sl * kThreads];
+        viol_tot[sl * kThreads] += vv;
+        if (args.out.ro_viol) args.out.ro_viol[(local * M + a) * R + sl] = vv;
+        if (args.out.ro_q) args.out.ro_q[(local * M + a) * R + sl] = sm.q[sl * kThreads];
       }
       if (args.out.ro_agents)
         reinterpret_cast<float4*>(args.out.ro_agents)[local * A + a] = make_float4(t.x, t.y, t.th, t.v);
       if (args.out.ro_flags) args.out.ro_flags[local * A + a] = static_cast<uint8_t>(t.flags);
+      if (PASSIVE && (args.out.ro_agents || args.out.ro_flags)) {
+        for (int slot = 0; slot < c.Ps; ++slot) {
+          const int j = M + slot * M + a;
+          if (j >= A) continue;
+          CwAgent p;
+          cw_pas_load(sm.pas, slot, p);
+          if (args.out.ro_agents)
+            reinterpret_cast<float4*>(args.out.ro_agents)[local * A + j] = make_float4(p.x, p.y, p.th, p.v);
+          if (args.out.ro_flags) args.out.ro_flags[local * A + j] = static_cast<uint8_t>(p.flags);
+        }
+      }
       if (args.out.ro_steps && a == 0) args.out.ro_steps[local] = k;
       busy = false;
       t.flags = 0;  // an idle group must not look present to anybody
@@ -239,25 +324,24 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
 
   // ---- warp-level reduction over the groups; lanes of group 0 publish with integer atomics
   // (fixed point: the per-leaf sum does not depend on the order in which warps arrive)
-  const bool contrib = real && a < M;
   for (int v = 0; v < V; ++v) {
-    double x = contrib ? acc_tot[v] : 0.0;
+    double x = real ? acc_tot[v] : 0.0;
     for (int gg = 1; gg < G; ++gg) {
-      const double y = __shfl_sync(full, x, (lane + gg * A) & 31);
+      const double y = __shfl_sync(full, x, (lane + gg * M) & 31);
       if (g == 0) x += y;
     }
-    if (g == 0 && a < M)
+    if (g == 0)
       atomicAdd(reinterpret_cast<unsigned long long*>(&args.returns_fx[(leaf * M + a) * V + v]),
                 static_cast<unsigned long long>(__double2ll_rn(x * kFixScale)));
   }
   if (args.out.viol_sum) {
     for (int sl = 0; sl < R; ++sl) {
-      uint32_t x = contrib ? viol_tot[sl * kThreads] : 0u;
+      uint32_t x = real ? viol_tot[sl * kThreads] : 0u;
       for (int gg = 1; gg < G; ++gg) {
-        const uint32_t y = __shfl_sync(full, x, (lane + gg * A) & 31);
+        const uint32_t y = __shfl_sync(full, x, (lane + gg * M) & 31);
         if (g == 0) x += y;
       }
-      if (g == 0 && a < M && x)
+      if (g == 0 && x)
         atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + a) * R + sl]),
                   static_cast<unsigned long long>(x));
     }
@@ -271,6 +355,7 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
   __syncwarp();
 }
 
+template <bool PASSIVE>
 __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kernel(const CwRolloutArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -278,8 +363,9 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
   const CwSmem sm = cw_smem(smem, c);
   const CwBlob& B = *sm.B;
   const int widx = threadIdx.x >> 5;
-  uint32_t* viol_tot = reinterpret_cast<uint32_t*>(smem + c.blob_cap + 2 * c.R * kThreads) + threadIdx.x;
-  CwPose* pose_w = reinterpret_cast<CwPose*>(smem + c.blob_cap + 6 * c.R * kThreads) + widx * BRM_CW_MAX_AGENTS;
+  uint8_t* extra = smem + cw_common_bytes(c);
+  uint32_t* viol_tot = reinterpret_cast<uint32_t*>(extra) + threadIdx.x;
+  CwPose* pose_w = reinterpret_cast<CwPose*>(extra + 4 * c.R * kThreads) + widx * c.A;
   int cur_scn = -1;
   uint32_t phase = 0;
   const int n = args.rollouts_per_leaf;
@@ -296,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
       const int64_t leaf = r0 / n;
       const int b = static_cast<int>(r0 - leaf * n);
       const int64_t take = min(static_cast<int64_t>(n - b), r1 - r0);
-      cw_run_segment(args, B, sm, viol_tot, pose_w, leaf, b, b + static_cast<int>(take));
+      cw_run_segment<PASSIVE>(args, B, sm, viol_tot, pose_w, leaf, b, b + static_cast<int>(take));
       r0 += take;
     }
   } else {
@@ -306,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
       cw_stage(smem, &bar, c, args.leaves.scenario[leaf], cur_scn, phase);
       const int b = static_cast<int>(static_cast<int64_t>(n) * widx / kWarps);
       const int e = static_cast<int>(static_cast<int64_t>(n) * (widx + 1) / kWarps);
-      if (b < e) cw_run_segment(args, B, sm, viol_tot, pose_w, leaf, b, e);
+      if (b < e) cw_run_segment<PASSIVE>(args, B, sm, viol_tot, pose_w, leaf, b, e);
     }
   }
 }
@@ -319,7 +405,7 @@ __global__ void cw_finalize_returns_kernel(const long long* __restrict__ fx, dou
 }
 
 // ------------------------------------------------------------------ K4 / K6 / queries
-// states are mapped G per warp, lane = agent
+// states are mapped G per warp, lane = MCTS agent
 struct CwBatchArgs {
   CwCommon c;
   brm_cw_states in, out;
@@ -342,10 +428,11 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
   const CwCommon& c = args.c;
   const CwSmem sm = cw_smem(smem, c);
   const CwBlob& B = *sm.B;
-  const int lane = threadIdx.x & 31, widx = threadIdx.x >> 5;
+  const CwMap m = cw_map(c);
+  const int widx = threadIdx.x >> 5;
   const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
-  const int a = lane % A, g = lane / A, base = g * A;
-  const bool real = g < G;
+  const int a = m.a, g = m.g, base = m.base;
+  const bool real = m.real;
   const int64_t n = args.in.n;
   int cur_scn = -1;
   uint32_t phase = 0;
@@ -359,9 +446,8 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
     const bool on = real && i < n;
     const int64_t ii = on ? i : 0;
     CwAgent t;
-    cw_load_agent(args.in, ii, a, on, t);
+    cw_load_state(args.in, B, c, m, sm, ii, on, t);
     cw_load_rules(args.in, c, ii, a, on, sm, true);
-    if (t.flags & BRM_CW_PRESENT) cw_frenet(B, t);
     int horizon = on ? args.in.horizon[ii] : 0;
 
     if (MODE == MODE_QUERY) {
@@ -371,8 +457,9 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
         cw_corners(B, t, a, cx, cy);
         const bool present = on && (t.flags & BRM_CW_PRESENT);
         bool coll = false;
+        __syncwarp();
         for (int j = 0; j < A; ++j) {
-          const CwPeer p = cw_fetch(t, base + j);
+          const CwPeer p = j < M ? cw_fetch(t, base + j) : cw_fetch_passive(B, sm.pas, j, a, real);
           if (j == a || !(p.flags & BRM_CW_PRESENT) || !present) continue;
           coll = cw_rect_overlap(B, t, a, p, j) || coll;
         }
@@ -382,7 +469,7 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
           args.in.terminal[i] = term ? 1 : 0;
         }
       }
-      if (on && a < M) {
+      if (on) {
         if (args.num_actions) {
           const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
           args.num_actions[static_cast<int64_t>(a) * n + i] = movable ? B.n_prims[a] : 1;
@@ -399,7 +486,7 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
     if (MODE == MODE_EXECUTE) {
       const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
       uint32_t act = 0;
-      if (on && a < M) act = args.actions[static_cast<int64_t>(a) * n + i];
+      if (on) act = args.actions[static_cast<int64_t>(a) * n + i];
       if (!movable) act = 0;
       const float in_v = t.v, in_th = t.th;
       const uint32_t in_flags = t.flags;
@@ -407,28 +494,36 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
         cw_integrate(B, t, a, act);
         cw_frenet(B, t);
       }
+      cw_move_passive(B, c, m, sm, on);
       CwStepOut o;
-      cw_evaluate<false>(B, t, a, base, real, on, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                         kThreads, o);
+      cw_evaluate<false, true>(B, t, a, base, real, on, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                         kThreads, sm.pas, o);
       if (on) {
         reinterpret_cast<float4*>(args.out.agents)[static_cast<int64_t>(a) * n + i] =
             make_float4(t.x, t.y, t.th, t.v);
         args.out.flags[static_cast<int64_t>(a) * n + i] = static_cast<uint8_t>(t.flags);
+        for (int slot = 0; slot < c.Ps; ++slot) {
+          const int j = M + slot * M + a;
+          if (j >= A) continue;
+          CwAgent p;
+          cw_pas_load(sm.pas, slot, p);
+          reinterpret_cast<float4*>(args.out.agents)[static_cast<int64_t>(j) * n + i] =
+              make_float4(p.x, p.y, p.th, p.v);
+          args.out.flags[static_cast<int64_t>(j) * n + i] = static_cast<uint8_t>(p.flags);
+        }
         if (a == 0) {
           args.out.horizon[i] = horizon - 1;
           args.out.terminal[i] = o.terminal ? 1 : 0;
           args.out.scenario[i] = args.in.scenario[i];
         }
-        if (a < M) {
-          for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = o.r[v];
-          for (int sl = 0; sl < R; ++sl) {
-            const int64_t off = (static_cast<int64_t>(a) * R + sl) * n + i;
-            args.out.q[off] = sm.q[sl * kThreads];
-            if (args.out.viol) {
-              const uint32_t prev = args.in.viol ? args.in.viol[off] : 0u;
-              const uint32_t inc = static_cast<uint8_t>(sm.viol[sl * kThreads] - static_cast<uint8_t>(prev));
-              args.out.viol[off] = prev + inc;
-            }
+        for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = o.r[v];
+        for (int sl = 0; sl < R; ++sl) {
+          const int64_t off = (static_cast<int64_t>(a) * R + sl) * n + i;
+          args.out.q[off] = sm.q[sl * kThreads];
+          if (args.out.viol) {
+            const uint32_t prev = args.in.viol ? args.in.viol[off] : 0u;
+            const uint32_t inc = static_cast<uint8_t>(sm.viol[sl * kThreads] - static_cast<uint8_t>(prev));
+            args.out.viol[off] = prev + inc;
           }
         }
       }
@@ -448,16 +543,17 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
         const int64_t bt = ii * T + k;
         const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
         uint32_t act = 0;
-        if (live && a < M && movable) act = args.actions[bt * M + a];
+        if (live && movable) act = args.actions[bt * M + a];
         const float in_v = t.v, in_th = t.th;
         const uint32_t in_flags = t.flags;
         if (live && movable) {
           cw_integrate(B, t, a, act);
           cw_frenet(B, t);
         }
+        cw_move_passive(B, c, m, sm, live);
         CwStepOut o;
-        cw_evaluate<true>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                          kThreads, o);
+        cw_evaluate<true, true>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
+                          kThreads, sm.pas, o);
         if (live) {
           --horizon;
           ++steps;
@@ -467,27 +563,35 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
           fo[0] = static_cast<float>(t.lane);
           fo[1] = t.s;
           fo[2] = t.lat;
+          for (int slot = 0; slot < c.Ps; ++slot) {
+            const int j = M + slot * M + a;
+            if (j >= A) continue;
+            CwAgent p;
+            cw_pas_load(sm.pas, slot, p);
+            reinterpret_cast<float4*>(args.tr.agents_out)[bt * A + j] = make_float4(p.x, p.y, p.th, p.v);
+            args.tr.flags_out[bt * A + j] = static_cast<uint8_t>(p.flags);
+            float* fp = args.tr.frenet_out + (bt * A + j) * 3;
+            fp[0] = static_cast<float>(p.lane);
+            fp[1] = p.s;
+            fp[2] = p.lat;
+          }
           if (a == 0) args.tr.terminal_out[bt] = o.terminal ? 1 : 0;
-          if (a < M) {
-            for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = o.r[v];
-            for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = o.w[w];
-            for (int sl = 0; sl < R; ++sl) {
-              viol32[sl] += sm.viol[sl * kThreads];
-              sm.viol[sl * kThreads] = 0;
-              args.tr.q_out[(bt * M + a) * R + sl] = sm.q[sl * kThreads];
-              args.tr.viol_out[(bt * M + a) * R + sl] = viol32[sl];
-            }
+          for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = o.r[v];
+          for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = o.w[w];
+          for (int sl = 0; sl < R; ++sl) {
+            viol32[sl] += sm.viol[sl * kThreads];
+            sm.viol[sl * kThreads] = 0;
+            args.tr.q_out[(bt * M + a) * R + sl] = sm.q[sl * kThreads];
+            args.tr.viol_out[(bt * M + a) * R + sl] = viol32[sl];
           }
           if (o.terminal) done = true;
         }
       }
       if (on) {
         if (a == 0) args.tr.steps_out[i] = steps;
-        if (a < M) {
-          float tr[BRM_MAX_REWARD];
-          cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
-          for (int v = 0; v < V; ++v) args.tr.term_reward_out[(i * M + a) * V + v] = tr[v];
-        }
+        float tr[BRM_MAX_REWARD];
+        cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
+        for (int v = 0; v < V; ++v) args.tr.term_reward_out[(i * M + a) * V + v] = tr[v];
       }
     }
   }
@@ -495,16 +599,17 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
 
 }  // namespace
 
-size_t cw_rollout_smem_bytes(const CwCommon& c) {
-  return static_cast<size_t>(c.blob_cap) + 6u * static_cast<size_t>(c.R) * kThreads +
-         static_cast<size_t>(kWarps) * BRM_CW_MAX_AGENTS * sizeof(CwPose);
+size_t cw_rollout_smem_bytes(const CwLaunchCtx& ctx) {
+  return ctx.smem_bytes + 4u * static_cast<size_t>(ctx.c.R) * kThreads +
+         static_cast<size_t>(kWarps) * ctx.c.A * sizeof(CwPose);
 }
 
 int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
                       const brm_rollout_params& rp, const brm_cw_rollout_out& out) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cw_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   const int M = ctx.c.M, V = ctx.c.V, R = ctx.c.R;
@@ -532,9 +637,15 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
                                    e->stream));
   // persistent grid: exactly the number of CTAs that are resident at once (SMs x occupancy),
   // so there is no partial second wave
-  const size_t smem = cw_rollout_smem_bytes(ctx.c);
+  const size_t smem = cw_rollout_smem_bytes(ctx);
   int per_sm = 0;
-  BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel, kThreads, smem));
+  // agents outside the MCTS list (kept in shared-memory slots) or not: two instances of the kernel
+  const bool passive = ctx.c.Ps > 0;
+  if (passive)
+    BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<true>, kThreads, smem));
+  else
+    BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<false>, kThreads, smem));
+  if (getenv("BRM_DEBUG")) fprintf(stderr, "[brm] cw_rollout: smem %zu B/CTA, %d CTAs/SM\n", smem, per_sm);
   int64_t grid = static_cast<int64_t>(e->sm_count) * (per_sm > 0 ? per_sm : 1);
   const int64_t total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
   if (a.single_scenario) {
@@ -546,7 +657,10 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   }
   if (grid < 1) grid = 1;
   e->time_begin();
-  cw_rollout_kernel<<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
+  if (passive)
+    cw_rollout_kernel<true><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
+  else
+    cw_rollout_kernel<false><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
   e->launches++;
   cw_finalize_returns_kernel<<<static_cast<int>((fx_count + 255) / 256), 256, 0, e->stream>>>(
       a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count));

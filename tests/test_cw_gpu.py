@@ -294,7 +294,8 @@ def test_replay_matches_committed_golden_traces(built):
         assert compared > 0.8 * int(g[name + "/steps"].sum())
 
 
-@pytest.mark.parametrize("n_agents,n_mcts,n", [(1, 1, 333), (2, 1, 100), (7, 7, 65), (16, 16, 50), (16, 3, 31)])
+@pytest.mark.parametrize("n_agents,n_mcts,n", [(1, 1, 333), (2, 1, 100), (7, 7, 65), (16, 16, 50), (16, 3, 31),
+                                               (16, 1, 40), (5, 2, 77)])
 def test_edge_shapes_rollouts_match_oracle(built, orc, n_agents, n_mcts, n):
     """Extreme shapes: one agent, the 16-agent maximum (2 rollouts per warp), rollout counts that
     do not divide the lane groups, a mix of controlled and passive agents; many rule slots."""
