@@ -113,6 +113,18 @@ __device__ __forceinline__ void kahan_add(float& sum, float& c, float term) {
   sum = t;
 }
 
+// reward vectors are four named scalars (an array indexed by a runtime priority would be
+// placed in local memory): component `idx` += val
+struct CwVec {
+  float c0, c1, c2, c3;
+};
+__device__ __forceinline__ void vec_add_at(CwVec& r, int idx, float val) {
+  r.c0 = idx == 0 ? r.c0 + val : r.c0;
+  r.c1 = idx == 1 ? r.c1 + val : r.c1;
+  r.c2 = idx == 2 ? r.c2 + val : r.c2;
+  r.c3 = idx == 3 ? r.c3 + val : r.c3;
+}
+
 __device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a, uint32_t prim) {
   const float acc = B.prim_a[a][prim];
   const float k = B.prim_k[a][prim];
@@ -254,8 +266,13 @@ __device__ __forceinline__ bool cw_out_of_map(const CwBlob& B, const CwAgent& t,
   uint32_t inside = 0;
   bool vertex_in = false;
   const float f = B.front[a], r = B.rear[a], h = B.hw[a];
+  const float ylo = fminf(fminf(cy[0], cy[1]), fminf(cy[2], cy[3]));
+  const float yhi = fmaxf(fmaxf(cy[0], cy[1]), fmaxf(cy[2], cy[3]));
   for (int e = 0; e < B.n_road; ++e) {
     const float4 g = B.road_edge[e];
+    // an edge whose y range misses the rectangle's: no corner ray crosses it (both
+    // comparisons below agree for every corner) and its start vertex is outside
+    if (fminf(g.x, g.y) > yhi || fmaxf(g.x, g.y) < ylo) continue;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool cross = ((g.x > cy[k]) != (g.y > cy[k])) && (cx[k] < g.w * (cy[k] - g.x) + g.z);
@@ -376,8 +393,7 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
   const int A = B.A, M = B.M, V = B.V;
   const bool present = real && (t.flags & BRM_CW_PRESENT);
   const bool evaluated = live && present && (in_flags & BRM_CW_VALID) && a < M;
-#pragma unroll
-  for (int v = 0; v < BRM_MAX_REWARD; ++v) o.r[v] = 0.f;
+  CwVec r = {0.f, 0.f, 0.f, 0.f};
   o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
 
   bool oom = false, goal = false;
@@ -429,8 +445,8 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
   }
 
   if (evaluated) {
-    o.r[0] += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92
-    o.r[0] += (oom ? 1.f : 0.f) * B.w_oom;    // :94-96
+    r.c0 += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92
+    r.c0 += (oom ? 1.f : 0.f) * B.w_oom;    // :94-96
     // GetActionCost (:202-248)
     {
       const float acc = (t.v - in_v) * B.inv_dt;
@@ -445,9 +461,8 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
       const float pot_new = -B.w_pot * B.dt * fabsf(t.v - B.v_des);
       const float pot_cur = -B.w_pot * B.dt * fabsf(in_v - B.v_des);
       const float pot = B.gamma * pot_new - pot_cur;
-#pragma unroll
-      for (int v = 0; v < BRM_MAX_REWARD; ++v)
-        if (v == V - 1) o.r[v] = (o.r[v] + cost) + pot;
+      vec_add_at(r, V - 1, cost);
+      vec_add_at(r, V - 1, pot);
     }
     // labels (EvaluateRules, :165-185)
     uint32_t w0 = 0;
@@ -472,7 +487,7 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
       o.w[0] = w0; o.w[1] = merged_mask; o.w[2] = front_mask; o.w[3] = near_mask;
     }
     if (!(B.ego_only && a != 0)) {  // :104-108
-      float rr[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
+      CwVec rr = {0.f, 0.f, 0.f, 0.f};
       for (int sl = 0; sl < B.R; ++sl) {
         // one 16-byte record per slot: x = label kinds of the 4 APs (a byte each),
         // y = n_aps | priority << 8 | init << 16 | on_violation << 24,
@@ -500,26 +515,19 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
           viol[sl * col_stride] += 1;
           nxt = (rec.y >> 24) ? cur : ((rec.y >> 16) & 0xffu);
           const uint32_t pr = (rec.y >> 8) & 0xffu;
-          const float wgt = __uint_as_float(rec.w);
-#pragma unroll
-          for (int v = 0; v < BRM_MAX_REWARD; ++v)
-            if (v == static_cast<int>(pr)) rr[v] += wgt;
+          vec_add_at(rr, static_cast<int>(pr), __uint_as_float(rec.w));
         }
         q[sl * col_stride] = static_cast<uint8_t>(nxt);
       }
-#pragma unroll
-      for (int v = 0; v < BRM_MAX_REWARD; ++v) o.r[v] += rr[v];
+      r.c0 += rr.c0; r.c1 += rr.c1; r.c2 += rr.c2; r.c3 += rr.c3;
     }
-    if (goal) {  // :110-113
-#pragma unroll
-      for (int v = 0; v < BRM_MAX_REWARD; ++v)
-        if (v == V - 1) o.r[v] += B.goal_reward;
-    }
+    if (goal) vec_add_at(r, V - 1, B.goal_reward);  // :110-113
     if (coll) t.flags &= ~static_cast<uint32_t>(BRM_CW_VALID);  // :116-120
   }
   // CheckTerminal of the new state (:266-285), decided by the ego lane of the group
   const bool ego_term = !present || horizon_after == 0 || oom || coll || goal;
   o.terminal = __shfl_sync(0xffffffffu, ego_term ? 1 : 0, base) != 0;
+  o.r[0] = r.c0; o.r[1] = r.c1; o.r[2] = r.c2; o.r[3] = r.c3;
 }
 
 // GetTerminalReward (:148-164) for my agent
@@ -529,14 +537,13 @@ __device__ __forceinline__ void cw_terminal_reward(const CwBlob& B, const CwAgen
 #pragma unroll
   for (int v = 0; v < BRM_MAX_REWARD; ++v) r[v] = 0.f;
   if (!real || a >= B.M || !(t.flags & BRM_CW_PRESENT)) return;
+  CwVec acc = {0.f, 0.f, 0.f, 0.f};
   for (int sl = 0; sl < B.R; ++sl) {
     const brm_rule& rule = B.rules[B.slot_rule[sl]];
     const float pen = rule.accepting[q[sl * col_stride]] ? 0.f : rule.weight;
-    const int pr = rule.priority;
-#pragma unroll
-    for (int v = 0; v < BRM_MAX_REWARD; ++v)
-      if (v == pr) r[v] += pen;
+    vec_add_at(acc, rule.priority, pen);
   }
+  r[0] = acc.c0; r[1] = acc.c1; r[2] = acc.c2; r[3] = acc.c3;
 }
 
 }  // namespace brm

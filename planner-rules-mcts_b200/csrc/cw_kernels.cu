@@ -295,7 +295,9 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
       }
       const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
       if (args.out.ro_returns)
-        for (int v = 0; v < V; ++v) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
+#pragma unroll
+        for (int v = 0; v < BRM_MAX_REWARD; ++v)
+          if (v < V) args.out.ro_returns[(local * M + a) * V + v] = acc[v];
       for (int sl = 0; sl < R; ++sl) {
         const uint8_t vv = sm.viol[sl * kThreads];
         viol_tot[sl * kThreads] += vv;
@@ -324,7 +326,9 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
 
   // ---- warp-level reduction over the groups; lanes of group 0 publish with integer atomics
   // (fixed point: the per-leaf sum does not depend on the order in which warps arrive)
-  for (int v = 0; v < V; ++v) {
+#pragma unroll
+  for (int v = 0; v < BRM_MAX_REWARD; ++v) {
+    if (v >= V) break;
     double x = real ? acc_tot[v] : 0.0;
     for (int gg = 1; gg < G; ++gg) {
       const double y = __shfl_sync(full, x, (lane + gg * M) & 31);
