@@ -8,6 +8,8 @@
 //      cw_batch_kernel<QUERY>    CheckTerminal / GetNumActions / GetTerminalReward
 // Every CTA stages the scenario blob it works on into shared memory with a TMA bulk copy
 // (re-staged only when the scenario changes).
+#include <algorithm>
+
 #include "common.cuh"
 #include "cw_device.cuh"
 #include "philox.cuh"
@@ -19,7 +21,7 @@ namespace {
 
 constexpr int kThreads = kCwThreads;
 constexpr int kWarps = kThreads / 32;
-constexpr double kFixScale = 1048576.0;  // 2^20: fixed-point scale of the per-leaf return sums
+constexpr double kFixScale = 16777216.0;  // 2^24: fixed-point scale of the per-leaf return sums
 
 // shared memory layout: [blob_cap bytes blob][R*T q][R*T viol][Ps*kCwPasWords*T floats passive agents]
 //                       (+ rollout kernel: [R*T u32 violation totals][kWarps*A leaf poses])
@@ -158,10 +160,13 @@ struct CwRolloutArgs {
   CwCommon c;
   brm_cw_states leaves;
   brm_cw_rollout_out out;
-  long long* returns_fx;  // [leaves][M*V] fixed-point (2^-20) sums, zeroed before the launch
+  long long* returns_fx;             // [leaves][M*V] fixed-point sums, zeroed before the launch
+  unsigned long long* work_counter;  // next unclaimed rollout (one scenario) / unit (several), zeroed
   uint64_t seed, rollout_base;
   int32_t rollouts_per_leaf, max_steps, first_exp;
-  int32_t single_scenario;  // 1: every leaf lives in scenario 0 -> warps split the flat rollout range
+  int32_t single_scenario;  // 1: every leaf lives in scenario 0 -> warps draw from the flat rollout range
+  int32_t chunk;            // rollouts a warp claims at a time (multiple of G)
+  int32_t parts;            // several scenarios: a leaf's rollouts are handed out in `parts` units
   float gamma;
 };
 
@@ -179,58 +184,106 @@ __device__ __forceinline__ void cw_from_pose(const CwPose& p, CwAgent& t) {
   t.ex = t.ey = t.eth = t.ev = 0.f;
 }
 
-// All rollouts idx in [seg_begin, seg_end) of one leaf, executed by one warp.  Up to G
-// rollouts are in flight (one per lane group); when one ends its group immediately takes
-// the next index, so lanes only idle at the very end of the segment.
-template <bool PASSIVE>
-__device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const CwBlob& B, const CwSmem& sm,
-                                               uint32_t* viol_tot, CwPose* pose_w, int64_t leaf,
-                                               int seg_begin, int seg_end) {
+// What a lane has accumulated for the leaf its recent rollouts belonged to.  Returns are
+// converted to fixed point per rollout, so the integer sums do not depend on which warp ran
+// which rollout or in which order (bitwise reproducible under dynamic scheduling).
+struct CwLaneAcc {
+  long long fx[BRM_MAX_REWARD];
+  int leaf;
+  uint32_t steps;
+};
+
+__device__ __forceinline__ void cw_acc_flush(const CwRolloutArgs& args, CwLaneAcc& acc, uint32_t* viol_tot, int a) {
+  const int M = args.c.M, V = args.c.V, R = args.c.R;
+  if (acc.leaf >= 0) {
+#pragma unroll
+    for (int v = 0; v < BRM_MAX_REWARD; ++v)
+      if (v < V && acc.fx[v])
+        atomicAdd(reinterpret_cast<unsigned long long*>(&args.returns_fx[(static_cast<int64_t>(acc.leaf) * M + a) * V + v]),
+                  static_cast<unsigned long long>(acc.fx[v]));
+    if (args.out.viol_sum) {
+      for (int sl = 0; sl < R; ++sl) {
+        const uint32_t x = viol_tot[sl * kThreads];
+        if (x)
+          atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(static_cast<int64_t>(acc.leaf) * M + a) * R + sl]),
+                    static_cast<unsigned long long>(x));
+      }
+    }
+    if (args.out.agent_steps && acc.steps)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[acc.leaf]),
+                static_cast<unsigned long long>(acc.steps));
+  }
+#pragma unroll
+  for (int v = 0; v < BRM_MAX_REWARD; ++v) acc.fx[v] = 0;
+  for (int sl = 0; sl < R; ++sl) viol_tot[sl * kThreads] = 0u;
+  acc.steps = 0;
+}
+
+// One warp runs rollouts until `fetch` has no more work and all its lane groups are done.
+// Up to G rollouts are in flight (one per lane group); when one ends its group takes the
+// next rollout id of the warp's current range at once, and an empty range is replaced by
+// `fetch(lo, hi)` (warp-uniform; a range [lo, hi) of flat rollout ids inside ONE leaf, or
+// lo >= hi when the work is exhausted).  Lanes therefore only idle at the very end.
+template <bool PASSIVE, class Fetch>
+__device__ __forceinline__ void cw_run_warp(const CwRolloutArgs& args, const CwBlob& B, const CwSmem& sm,
+                                            uint32_t* viol_tot, CwPose* pose_w, CwLaneAcc& lacc, Fetch fetch) {
   const CwCommon& c = args.c;
   const CwMap m = cw_map(c);
-  const int lane = m.lane, a = m.a, g = m.g, base = m.base;
+  const int lane = m.lane, a = m.a, base = m.base;
   const bool real = m.real;
-  const int A = c.A, M = c.M, V = c.V, R = c.R, G = c.G;
+  const int A = c.A, M = c.M, V = c.V, R = c.R;
   const uint32_t full = 0xffffffffu;
-
-  // leaf pose of every agent -> per-warp shared copy (lane l < A loads and projects agent l)
-  {
-    CwAgent t0;
-    cw_load_agent(args.leaves, leaf, lane < A ? lane : 0, lane < A, t0);
-    if (t0.flags & BRM_CW_PRESENT) cw_frenet(B, t0);
-    if (lane < A) {
-      CwPose p;
-      p.x = t0.x; p.y = t0.y; p.th = t0.th; p.v = t0.v; p.cs = t0.cs; p.sn = t0.sn;
-      p.s = t0.s; p.lat = t0.lat; p.lane = t0.lane; p.flags = t0.flags;
-      pose_w[lane] = p;
-    }
-  }
-  __syncwarp();
-  const int horizon0 = args.leaves.horizon[leaf];
-  const bool leaf_terminal = args.leaves.terminal[leaf] != 0;
-  for (int sl = 0; sl < R; ++sl) viol_tot[sl * kThreads] = 0u;
+  const int n = args.rollouts_per_leaf;
 
   CwAgent t;
   cw_clear_agent(t);
   float acc[BRM_MAX_REWARD] = {0.f, 0.f, 0.f, 0.f};
-  double acc_tot[BRM_MAX_REWARD] = {0.0, 0.0, 0.0, 0.0};
   float disc = 1.f;
-  int horizon = 0, k = 0, idx = 0;
-  uint64_t rid = 0;
-  uint32_t agent_steps = 0;
+  int horizon = 0, k = 0;
+  int flat = 0, my_leaf = -1;  // the rollout my group runs (flat id < 2^31, checked by the launcher)
+  uint32_t steps = 0;
   bool busy = false, done = false;
-  int next = seg_begin;  // warp-uniform: next rollout index nobody has taken yet
   Philox4 blk;
   blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+  // warp-uniform: unclaimed part of the current range, the leaf it lies in and that leaf's data
+  int lo = 0, hi = 0, leaf = -1;
+  int horizon0 = 0;
+  bool leaf_terminal = false, exhausted = false;
 
   for (;;) {
-    // ---- hand new rollouts to idle groups (ego lanes vote, ranks give distinct indices)
-    const uint32_t idle = __ballot_sync(full, real && !busy && a == 0);
-    if (idle) {
-      const int cand = next + __popc(idle & ((1u << base) - 1u));
-      if (real && !busy && cand < seg_end) {
-        idx = cand;
-        rid = args.rollout_base + static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
+    // ---- hand new rollouts to idle groups (ego lanes vote, ranks give distinct ids)
+    for (;;) {
+      const uint32_t idle = __ballot_sync(full, real && !busy && a == 0);
+      if (!idle || exhausted) break;
+      if (lo >= hi) {
+        fetch(lo, hi);
+        if (lo >= hi) {
+          exhausted = true;
+          break;
+        }
+        const int lf = lo / n;
+        if (lf != leaf) {
+          // leaf pose of every agent -> per-warp shared copy (lane l < A loads and projects agent l)
+          leaf = lf;
+          CwAgent t0;
+          cw_load_agent(args.leaves, leaf, lane < A ? lane : 0, lane < A, t0);
+          if (t0.flags & BRM_CW_PRESENT) cw_frenet(B, t0);
+          __syncwarp();
+          if (lane < A) {
+            CwPose p;
+            p.x = t0.x; p.y = t0.y; p.th = t0.th; p.v = t0.v; p.cs = t0.cs; p.sn = t0.sn;
+            p.s = t0.s; p.lat = t0.lat; p.lane = t0.lane; p.flags = t0.flags;
+            pose_w[lane] = p;
+          }
+          __syncwarp();
+          horizon0 = args.leaves.horizon[leaf];
+          leaf_terminal = args.leaves.terminal[leaf] != 0;
+        }
+      }
+      const int cand = lo + __popc(idle & ((1u << base) - 1u));
+      if (real && !busy && cand < hi) {
+        flat = cand;
+        my_leaf = leaf;
         cw_from_pose(pose_w[a], t);
         if (PASSIVE) {
           for (int slot = 0; slot < c.Ps; ++slot) {
@@ -250,14 +303,16 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
         disc = args.first_exp ? args.gamma : 1.f;
         horizon = horizon0;
         k = 0;
+        steps = 0;
         busy = true;
         done = leaf_terminal;
       }
-      next += __popc(idle);
+      lo = min(hi, lo + __popc(idle));
     }
     if (!__any_sync(full, busy)) break;
 
     // ---- one Execute for every busy group
+    const uint64_t rid = args.rollout_base + static_cast<uint64_t>(flat);
     const bool live = busy && !done && k < args.max_steps;
     const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
     uint32_t act = 0;
@@ -270,12 +325,12 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
     if (live && movable) {
       cw_integrate(B, t, a, act);
       cw_frenet(B, t);
-      ++agent_steps;
+      ++steps;
     }
-    if (PASSIVE) agent_steps += cw_move_passive(B, c, m, sm, live);
+    if (PASSIVE) steps += cw_move_passive(B, c, m, sm, live);
     CwStepOut o;
     cw_evaluate<false, PASSIVE>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                       kThreads, sm.pas, o);
+                                kThreads, sm.pas, o);
     if (live) {
 #pragma unroll
       for (int v = 0; v < BRM_MAX_REWARD; ++v) acc[v] += disc * o.r[v];
@@ -286,14 +341,19 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
     }
     // ---- rollouts that just ended: terminal reward, totals, optional per-rollout outputs
     if (busy && (done || k >= args.max_steps)) {
+      if (my_leaf != lacc.leaf) {
+        cw_acc_flush(args, lacc, viol_tot, a);
+        lacc.leaf = my_leaf;
+      }
       float tr[BRM_MAX_REWARD];
       cw_terminal_reward(B, t, a, true, sm.q, kThreads, tr);
 #pragma unroll
       for (int v = 0; v < BRM_MAX_REWARD; ++v) {
         acc[v] += disc * tr[v];
-        acc_tot[v] += static_cast<double>(acc[v]);
+        lacc.fx[v] += __double2ll_rn(static_cast<double>(acc[v]) * kFixScale);
       }
-      const uint64_t local = static_cast<uint64_t>(leaf) * args.rollouts_per_leaf + idx;
+      lacc.steps += steps;
+      const uint64_t local = static_cast<uint64_t>(flat);
       if (args.out.ro_returns)
 #pragma unroll
         for (int v = 0; v < BRM_MAX_REWARD; ++v)
@@ -323,39 +383,6 @@ __device__ __forceinline__ void cw_run_segment(const CwRolloutArgs& args, const 
       t.flags = 0;  // an idle group must not look present to anybody
     }
   }
-
-  // ---- warp-level reduction over the groups; lanes of group 0 publish with integer atomics
-  // (fixed point: the per-leaf sum does not depend on the order in which warps arrive)
-#pragma unroll
-  for (int v = 0; v < BRM_MAX_REWARD; ++v) {
-    if (v >= V) break;
-    double x = real ? acc_tot[v] : 0.0;
-    for (int gg = 1; gg < G; ++gg) {
-      const double y = __shfl_sync(full, x, (lane + gg * M) & 31);
-      if (g == 0) x += y;
-    }
-    if (g == 0)
-      atomicAdd(reinterpret_cast<unsigned long long*>(&args.returns_fx[(leaf * M + a) * V + v]),
-                static_cast<unsigned long long>(__double2ll_rn(x * kFixScale)));
-  }
-  if (args.out.viol_sum) {
-    for (int sl = 0; sl < R; ++sl) {
-      uint32_t x = real ? viol_tot[sl * kThreads] : 0u;
-      for (int gg = 1; gg < G; ++gg) {
-        const uint32_t y = __shfl_sync(full, x, (lane + gg * M) & 31);
-        if (g == 0) x += y;
-      }
-      if (g == 0 && x)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + a) * R + sl]),
-                  static_cast<unsigned long long>(x));
-    }
-  }
-  if (args.out.agent_steps) {
-    const uint32_t tot = __reduce_add_sync(full, agent_steps);
-    if (lane == 0 && tot)
-      atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
-                static_cast<unsigned long long>(tot));
-  }
   __syncwarp();
 }
 
@@ -363,42 +390,76 @@ template <bool PASSIVE>
 __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kernel(const CwRolloutArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned long long s_unit;  // several scenarios: the unit the CTA works on ...
+  __shared__ int s_next, s_end;          // ... and the unclaimed part of its rollouts (leaf-local ids)
   const CwCommon& c = args.c;
   const CwSmem sm = cw_smem(smem, c);
   const CwBlob& B = *sm.B;
-  const int widx = threadIdx.x >> 5;
+  const int widx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* extra = smem + cw_common_bytes(c);
   uint32_t* viol_tot = reinterpret_cast<uint32_t*>(extra) + threadIdx.x;
   CwPose* pose_w = reinterpret_cast<CwPose*>(extra + 4 * c.R * kThreads) + widx * c.A;
   int cur_scn = -1;
   uint32_t phase = 0;
   const int n = args.rollouts_per_leaf;
+  const int a = lane % c.M;
+  CwLaneAcc lacc;
+  lacc.leaf = -1;
+  cw_acc_flush(args, lacc, viol_tot, a);  // zero
   if (args.single_scenario) {
-    // one scenario: the flat rollout range [0, leaves*n) is cut into one contiguous piece per
-    // warp of the grid (equal to +-1 rollout), pieces are walked leaf by leaf
+    // one scenario: warps claim chunks of the flat rollout range [0, leaves*n) from a global
+    // counter as they run dry (rollout lengths differ a lot between leaves, a static split
+    // leaves warps idle at the end)
     cw_stage(smem, &bar, c, 0, cur_scn, phase);
-    const int64_t N = static_cast<int64_t>(args.leaves.n) * n;
-    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kWarps + widx;
-    const int64_t tw = static_cast<int64_t>(gridDim.x) * kWarps;
-    int64_t r0 = N * gw / tw;
-    const int64_t r1 = N * (gw + 1) / tw;
-    while (r0 < r1) {
-      const int64_t leaf = r0 / n;
-      const int b = static_cast<int>(r0 - leaf * n);
-      const int64_t take = min(static_cast<int64_t>(n - b), r1 - r0);
-      cw_run_segment<PASSIVE>(args, B, sm, viol_tot, pose_w, leaf, b, b + static_cast<int>(take));
-      r0 += take;
-    }
+    const int N = static_cast<int>(args.leaves.n) * n;
+    int c_lo = 0, c_hi = 0;  // claimed, not yet handed to the lane groups
+    auto fetch = [&](int& lo, int& hi) {
+      if (c_lo >= c_hi) {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(args.work_counter, static_cast<unsigned long long>(args.chunk));
+        v = __shfl_sync(0xffffffffu, v, 0);
+        c_lo = static_cast<int>(min(v, static_cast<unsigned long long>(N)));
+        c_hi = min(c_lo + args.chunk, N);
+      }
+      // hand out the part that lies in one leaf
+      lo = c_lo;
+      hi = min(c_hi, (c_lo / n + 1) * n);
+      c_lo = hi;
+    };
+    cw_run_warp<PASSIVE>(args, B, sm, viol_tot, pose_w, lacc, fetch);
   } else {
-    // several scenarios: one leaf per CTA at a time (the blob is CTA-wide), its rollouts are
-    // split evenly over the warps
-    for (int64_t leaf = blockIdx.x; leaf < args.leaves.n; leaf += gridDim.x) {
+    // several scenarios: the blob is CTA-wide, so a CTA works on one leaf at a time.  Units
+    // (a leaf's rollouts, or one of `parts` slices of them) are claimed from a global counter;
+    // inside a unit the warps draw G rollouts at a time from a shared-memory counter.
+    const int n_units = static_cast<int>(args.leaves.n) * args.parts;
+    for (;;) {
+      __syncthreads();  // everybody is done with the previous unit's counters
+      if (threadIdx.x == 0) {
+        const unsigned long long u = atomicAdd(args.work_counter, 1ull);
+        s_unit = u;
+        if (u < static_cast<unsigned long long>(n_units)) {
+          const int part = static_cast<int>(u % args.parts);
+          s_next = static_cast<int>(static_cast<int64_t>(n) * part / args.parts);
+          s_end = static_cast<int>(static_cast<int64_t>(n) * (part + 1) / args.parts);
+        }
+      }
+      __syncthreads();
+      if (s_unit >= static_cast<unsigned long long>(n_units)) break;
+      const int leaf = static_cast<int>(s_unit) / args.parts;
       cw_stage(smem, &bar, c, args.leaves.scenario[leaf], cur_scn, phase);
-      const int b = static_cast<int>(static_cast<int64_t>(n) * widx / kWarps);
-      const int e = static_cast<int>(static_cast<int64_t>(n) * (widx + 1) / kWarps);
-      if (b < e) cw_run_segment<PASSIVE>(args, B, sm, viol_tot, pose_w, leaf, b, e);
+      const int end = s_end;
+      auto fetch = [&](int& lo, int& hi) {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&s_next, c.G);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        const int b = min(v, end), e = min(v + c.G, end);
+        lo = leaf * n + b;
+        hi = leaf * n + e;
+      };
+      cw_run_warp<PASSIVE>(args, B, sm, viol_tot, pose_w, lacc, fetch);
     }
   }
+  cw_acc_flush(args, lacc, viol_tot, a);
 }
 
 // fixed point -> double
@@ -629,18 +690,19 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   a.gamma = static_cast<float>(rp.discount_factor);
   a.single_scenario = n_scenarios == 1 ? 1 : 0;
   const size_t fx_count = static_cast<size_t>(leaves.n) * M * V;
-  int rc = e->ensure_ws(fx_count * sizeof(long long));
+  int rc = e->ensure_ws((fx_count + 1) * sizeof(long long));
   if (rc != BRM_OK) return rc;
   a.returns_fx = static_cast<long long*>(e->d_ws);
-  BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, fx_count * sizeof(long long), e->stream));
+  a.work_counter = reinterpret_cast<unsigned long long*>(a.returns_fx + fx_count);
+  BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, (fx_count + 1) * sizeof(long long), e->stream));
   if (out.viol_sum)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
                                    e->stream));
   if (out.agent_steps)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
                                    e->stream));
-  // persistent grid: exactly the number of CTAs that are resident at once (SMs x occupancy),
-  // so there is no partial second wave
+  // persistent grid: at most the number of CTAs that are resident at once (SMs x occupancy);
+  // the CTAs claim their work from a counter
   const size_t smem = cw_rollout_smem_bytes(ctx);
   int per_sm = 0;
   // agents outside the MCTS list (kept in shared-memory slots) or not: two instances of the kernel
@@ -652,14 +714,31 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   if (getenv("BRM_DEBUG")) fprintf(stderr, "[brm] cw_rollout: smem %zu B/CTA, %d CTAs/SM\n", smem, per_sm);
   int64_t grid = static_cast<int64_t>(e->sm_count) * (per_sm > 0 ? per_sm : 1);
   const int64_t total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
+  BRM_REQUIRE(total + 4 * 32 < (1ll << 31), "brm_cw_rollout: %lld rollouts in one call (limit 2^31)",
+              static_cast<long long>(total));
+  const int64_t round = static_cast<int64_t>(kWarps) * ctx.c.G;  // rollouts a CTA has in flight
+  a.chunk = ctx.c.G;
+  a.parts = 1;
   if (a.single_scenario) {
     // at least one rollout per lane group, otherwise shrink the grid
-    const int64_t need = (total + static_cast<int64_t>(kWarps) * ctx.c.G - 1) / (static_cast<int64_t>(kWarps) * ctx.c.G);
+    const int64_t need = (total + round - 1) / round;
     if (grid > need) grid = need;
-  } else if (grid > leaves.n) {
-    grid = leaves.n;
+    // a warp claims 1..4 rounds of rollouts at a time, about a quarter of its share
+    const int64_t share = total / (grid * kWarps * ctx.c.G);
+    a.chunk = ctx.c.G * static_cast<int>(std::min<int64_t>(4, std::max<int64_t>(1, share / 4)));
+  } else {
+    // cut the leaves into slices (at least one round of the CTA each) until there are about
+    // two units per resident CTA to balance with (measured on the W workload: 1 / 2 / 3 / 4
+    // slices per leaf -> 1.46 / 1.89 / 2.02 / 1.89 G agent-steps/s)
+    while (static_cast<int64_t>(leaves.n) * a.parts < 2 * grid &&
+           rp.rollouts_per_leaf / (a.parts + 1) >= round)
+      ++a.parts;
+    const int64_t units = static_cast<int64_t>(leaves.n) * a.parts;
+    if (grid > units) grid = units;
   }
   if (grid < 1) grid = 1;
+  if (const char* v = getenv("BRM_CW_CHUNK")) a.chunk = ctx.c.G * atoi(v);   // tuning experiments
+  if (const char* v = getenv("BRM_CW_PARTS")) a.parts = atoi(v);
   e->time_begin();
   if (passive)
     cw_rollout_kernel<true><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
