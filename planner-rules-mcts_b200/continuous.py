@@ -294,6 +294,10 @@ class RulesMctsEngine:
         _abi.check(self.lib.brm_cw_check_terminal(self.engine.handle, C.byref(s)))
         return batch.terminal
 
+    def is_terminal(self, batch):
+        """The terminal flags the states carry (set by Execute / check_terminal)."""
+        return np.asarray(batch.terminal).astype(bool)
+
     def execute(self, batch, actions):
         """MvmctsState::Execute; actions [M][n] uint8 -> (next_batch, rewards [M][V][n] float32)."""
         n = batch.n

@@ -129,6 +129,7 @@ class GridWorldEngine:
         self.engine = engine or _abi.Engine(device, cuda_stream)
         self.lib = self.engine.lib
         self.A = self.params.num_other_agents + 1
+        self.M = self.A  # every GridWorld agent is an MCTS agent
         self.V = self.params.reward_vec_size
         abi_rules = (_abi.Rule * max(1, len(self.rules)))()
         for k, r in enumerate(self.rules):

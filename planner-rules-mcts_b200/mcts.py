@@ -21,9 +21,9 @@ from . import parallel
 class _Node:
     __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q")
 
-    def __init__(self, state, n_actions, V):
+    def __init__(self, state, terminal, n_actions, V):
         self.state = state
-        self.terminal = bool(state.terminal[0])
+        self.terminal = bool(terminal)
         self.n_actions = [int(k) for k in n_actions]
         self.children = {}
         self.N = [np.zeros(k) for k in self.n_actions]
@@ -57,14 +57,19 @@ class Mcts:
         self.root = None
         self.iterations = 0
         self._next_rollout = 0
+        # selection compares normalised values (+ exploration bonus), so the thresholds are
+        # normalised with the same bounds
+        span = np.maximum(self.p.UPPER_BOUND - self.p.LOWER_BOUND, 1e-9)
+        self._thr_norm = None if self.p.THRESHOLD is None else (self.p.THRESHOLD - self.p.LOWER_BOUND) / span
 
     # -- helpers -----------------------------------------------------------------------
     def _make_node(self, state):
-        return _Node(state, self.engine.get_num_actions(state)[:, 0], self.engine.V)
+        return _Node(state, self.engine.is_terminal(state)[0], self.engine.get_num_actions(state)[:, 0],
+                     self.engine.V)
 
     def _lex_better(self, a, b):
         """a better than b in thresholded lexicographic order."""
-        thr = self.p.THRESHOLD
+        thr = self._thr_norm
         for k in range(len(a)):
             x, y = a[k], b[k]
             if thr is not None:
@@ -84,8 +89,8 @@ class Mcts:
             total = node.N[a].sum()
             mean = node.Q[a] / node.N[a][:, None]
             norm = (mean - self.p.LOWER_BOUND) / span
-            bonus = self.p.EXPLORATION_CONSTANT * np.sqrt(2.0 * math.log(total) / node.N[a])
-            ucb = norm + bonus[:, None]
+            bonus = np.sqrt(2.0 * math.log(total) / node.N[a])
+            ucb = norm + bonus[:, None] * np.asarray(self.p.EXPLORATION_CONSTANT, np.float64)
             best = 0
             for act in range(1, k):
                 if self._lex_better(ucb[act], ucb[best]):

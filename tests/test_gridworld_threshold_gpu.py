@@ -1,0 +1,54 @@
+"""The reference's GridWorld threshold suite (test/grid_world_threshold_test.cpp:40-71; configs[0]
+of BASELINE.json) end to end on the device engine: `TestRunner::RunTest(3000, 16)` with the three
+threshold vectors and the same expectations on the final positions.  The tree is the host tree of
+planner_rules_mcts_b200.mcts (decoupled UCT with thresholded lexicographic comparison); every
+Execute / rollout / terminal reward runs in libbrm.so."""
+import numpy as np
+import pytest
+
+from planner_rules_mcts_b200 import gridworld_env as ge
+from planner_rules_mcts_b200.planner import write_state_history_tsv
+
+pytestmark = pytest.mark.gpu
+
+MERGING_POINT = 8
+BIG = np.finfo(np.float64).max
+
+
+@pytest.fixture(scope="module")
+def engine(built):
+    return ge.CrossingTestEnv((0.0, 0.0, BIG)).engine
+
+
+def run(engine, thres, tmp_path=None):
+    env = ge.CrossingTestEnv(thres, engine=engine, seed=1000)   # RandomGenerator seed of the suite's main()
+    runner = ge.TestRunner(env, q_val_fname=None if tmp_path is None else str(tmp_path / "q_val.dat"))
+    res = runner.RunTest(3000, 16)                               # :28
+    return np.array(env.state_history), res, env
+
+
+def test_collision(engine):
+    hist, res, _ = run(engine, (-1.0, -1.0, BIG))                # :41-42
+    assert hist[-1][0] == hist[-1][2]                            # collision of 0 and 2 (:45)
+    assert hist[-1][1] > MERGING_POINT                           # 1 has passed the merging point (:47)
+    assert res.collision
+
+
+def test_pass(engine, tmp_path):
+    hist, res, env = run(engine, (-0.37, -0.37, BIG), tmp_path)  # :51-52
+    last = hist[-1]
+    assert last[0] > MERGING_POINT and last[1] > MERGING_POINT and last[2] > MERGING_POINT  # :55-57
+    assert last[0] < last[2] < last[1]                           # order 1, 2, 0 (:59-60)
+    assert not res.collision and not res.violation
+    # the writers of the reference's runner: state history TSV and one q-value line per decision
+    write_state_history_tsv(str(tmp_path / "hist.tsv"), hist[:, :, None])
+    rows = open(tmp_path / "hist.tsv").read().splitlines()
+    assert rows[0].split("\t") == ["Timestep", "Agent 0", "Agent 1", "Agent 2"] and len(rows) == len(hist) + 1
+    assert len(open(tmp_path / "q_val.dat").read().splitlines()) == len(env.action_history)
+
+
+def test_livelock(engine):
+    hist, res, _ = run(engine, (-0.1, -0.8, BIG))                # :64-65
+    last = hist[-1]
+    assert last[0] < MERGING_POINT and last[1] > MERGING_POINT and last[2] < MERGING_POINT  # :68-70
+    assert not res.collision
