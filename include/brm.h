@@ -350,6 +350,12 @@ int brm_cw_check_terminal(brm_engine* e, brm_cw_states* s);
  * BRM_MEM_HOST batches are checked first: BRM_ERR_TERMINAL if any state is terminal (:59). */
 int brm_cw_execute(brm_engine* e, const brm_cw_states* in, const uint8_t* actions,
                    brm_cw_states* out, float* rewards);
+/* MvmctsState::EvaluateRules() (:186-197), the call BehaviorRulesMcts::Plan makes on the root
+ * state to carry the automata from the last planning step to the current world
+ * (src/behavior_rules_mcts.hpp:211-214): labels of the states as they are, one transition per
+ * rule state of every MCTS agent that is present and VALID.  `out` = `in` with the new automaton
+ * states (and violation counters); rewards [M][V][n] float = the rule penalties only. */
+int brm_cw_evaluate_rules(brm_engine* e, const brm_cw_states* in, brm_cw_states* out, float* rewards);
 /* MvmctsState::GetNumActions (:129-141): out [M][n] */
 int brm_cw_get_num_actions(brm_engine* e, const brm_cw_states* s, uint8_t* out);
 /* MvmctsState::GetTerminalReward (:148-164): out [M][V][n] float */

@@ -249,6 +249,23 @@ class MvmctsState {
     return next;
   }
 
+  // EvaluateRules() (:186-197): transit the automata on the labels of this state; mutates the
+  // rule states like the reference's and returns the rule penalties per agent
+  std::vector<Reward> EvaluateRules() {
+    const int M = ctx_->M, V = ctx_->V, R = ctx_->R;
+    MvmctsState next(*this);
+    std::vector<float> rew(static_cast<size_t>(M) * V);
+    std::vector<uint32_t> viol_out(static_cast<size_t>(M) * R, 0);
+    brm_cw_states in = view(this, nullptr);
+    brm_cw_states out = view(&next, viol_out.data());
+    check(brm_cw_evaluate_rules(ctx_->engine->get(), &in, &out, rew.data()));
+    q_ = next.q_;
+    std::vector<Reward> rewards(M, Reward(V, 0.0));
+    for (int a = 0; a < M; ++a)
+      for (int v = 0; v < V; ++v) rewards[a][v] = rew[static_cast<size_t>(a) * V + v];
+    return rewards;
+  }
+
   ActionIdx GetNumActions(AgentIdx agent_idx) const {  // :129-141
     const uint8_t f = flags_.at(agent_idx);
     return ((f & BRM_CW_PRESENT) && (f & BRM_CW_VALID)) ? static_cast<ActionIdx>(ctx_->n_prims.at(agent_idx)) : 1;

@@ -134,6 +134,7 @@ class CwTrace(C.Structure):
 # every symbol include/brm.h declares (tests/test_abi.py checks the library exports them)
 SYMBOLS = [
     "brm_cw_configure", "brm_cw_rules_per_agent", "brm_cw_check_terminal", "brm_cw_execute",
+    "brm_cw_evaluate_rules",
     "brm_cw_get_num_actions", "brm_cw_terminal_reward", "brm_cw_rollout", "brm_cw_replay",
     "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_synchronize",
     "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
@@ -180,6 +181,7 @@ def load():
     lib.brm_cw_rules_per_agent.argtypes = [vp]
     lib.brm_cw_check_terminal.argtypes = [vp, P(CwStates)]
     lib.brm_cw_execute.argtypes = [vp, P(CwStates), vp, P(CwStates), vp]
+    lib.brm_cw_evaluate_rules.argtypes = [vp, P(CwStates), P(CwStates), vp]
     lib.brm_cw_get_num_actions.argtypes = [vp, P(CwStates), vp]
     lib.brm_cw_terminal_reward.argtypes = [vp, P(CwStates), vp]
     lib.brm_cw_rollout.argtypes = [vp, P(CwStates), P(RolloutParams), P(CwRolloutOut)]

@@ -1,0 +1,264 @@
+"""The stateful planner plugin around the device engine.
+
+`BehaviorRulesMcts` here keeps the bookkeeping of the reference's plugin between planning
+steps (/root/reference/src/behavior_rules_mcts.hpp):
+  * `Plan(delta_time, observed_world)` (:158-255): the nearest agents interact (they become MCTS
+    agents), everybody else is predicted with constant acceleration; rule states of new agents
+    are created, those of agents that left are dropped, the automata are carried from the last
+    planning step to the current world (`EvaluateRules`), the search runs and the ego's best
+    motion primitive is returned as a trajectory;
+  * `MakeRuleStates` (:295-350), `GetNewAgents` (:369-385), `GetAgentIdMap` (:392-414),
+    `AddKnownAgents` (:415-419), `RemoveRuleStates` (:469-502) with the reference's semantics
+    (agent-specific rules are instantiated once per other known agent; the ego is index 0).
+BARK's `ObservedWorld` is replaced by a small value class (valid agents by id, lane centre lines,
+road polygon).  Every planning step configures the device engine for the agents that are present
+(the rule-state layout changes with them) -- a few kilobytes of tables; the search itself is the
+host tree of mcts.py over `Execute` / rollouts on the GPU.
+"""
+import copy
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _abi
+from .continuous import AgentModel, Lane, RulesMctsEngine, RulesMctsStateParameters, Scenario
+from .mcts import Mcts, MctsParameters
+from .planner import PlannerParameters
+
+
+@dataclass
+class ObservedWorld:
+    """What Plan() reads from bark's ObservedWorld: the valid agents (ego included) and the map."""
+    ego_id: int
+    agents: Dict[int, np.ndarray]          # id -> (x, y, theta, v)
+    lanes: List[Lane]
+    road: np.ndarray
+    time: float = 0.0
+
+    def GetEgoAgentId(self):
+        return self.ego_id
+
+    def GetValidAgents(self):
+        return dict(sorted(self.agents.items()))
+
+    def GetValidOtherAgents(self):
+        return {i: s for i, s in sorted(self.agents.items()) if i != self.ego_id}
+
+    def CurrentEgoPosition(self):
+        return np.asarray(self.agents[self.ego_id][:2], np.float64)
+
+    def GetNearestAgents(self, position, num_agents):
+        """The `num_agents` agents closest to `position` (the ego is one of them when the
+        position is its own, as with bark's r-tree query)."""
+        d = sorted((float(np.hypot(*(np.asarray(s[:2], np.float64) - position))), i) for i, s in self.agents.items())
+        return {i: self.agents[i] for _, i in d[:num_agents]}
+
+
+@dataclass
+class PredictionSettings:
+    """bark PredictionSettings: motion primitives (a, delta) of the ego and of the interacting
+    agents; non-interacting agents keep their speed (BehaviorConstantAcceleration, a = 0)."""
+    ego_primitives: List[tuple]
+    others_primitives: Optional[List[tuple]] = None
+    specific_prediction_agents_: set = field(default_factory=set)
+
+
+@dataclass
+class RuleState:
+    """ltl::RuleState as far as the planner looks at it."""
+    rule: int            # index into the agent's rule list (common rules first)
+    agent_ids: tuple     # the other agent an agent-specific rule is bound to, or ()
+    q: int               # automaton state
+    violations: int = 0
+
+
+class BehaviorRulesMcts:
+    def __init__(self, params: PlannerParameters, state_params: RulesMctsStateParameters,
+                 prediction_settings: PredictionSettings, common_rules=(), agent_rules=None,
+                 multi_agent=True, shape: AgentModel = None, ego_goal=None, device=0):
+        self.params = params
+        self.state_params_ = state_params
+        self.prediction_settings_ = prediction_settings
+        self.common_rules_ = list(common_rules)
+        self.agent_rules_ = {k: list(v) for k, v in (agent_rules or {}).items()}
+        self.multi_agent_ = multi_agent
+        self.shape = shape or AgentModel()
+        self.ego_goal = ego_goal
+        self.known_agents_ = set()
+        self.multi_agent_rule_state_: Dict[int, List[RuleState]] = {}
+        self.last_action_ = None
+        self.last_trajectory_ = None
+        self.last_stats = None
+        self._abi_engine = _abi.Engine(device)
+        self._decision = 0
+
+    # -- rules ------------------------------------------------------------------------------
+    def AddCommonRules(self, rules):
+        self.common_rules_.extend(rules)
+
+    def AddAgentRules(self, agent_ids, rules):
+        for i in agent_ids:
+            self.agent_rules_.setdefault(i, []).extend(rules)
+
+    def GetCommonRules(self):
+        return self.common_rules_
+
+    def GetAgentRules(self):
+        return self.agent_rules_
+
+    def _rules_of(self, agent_id):
+        return self.common_rules_ + self.agent_rules_.get(agent_id, [])
+
+    def GetNewAgents(self, agent_map):
+        return sorted(set(int(i) for i in agent_map) - self.known_agents_)
+
+    def AddKnownAgents(self, agent_ids):
+        self.known_agents_.update(agent_ids)
+
+    def MakeRuleStates(self, new_agent_ids):
+        current = sorted(set(new_agent_ids) | self.known_agents_)
+        for agent_id in new_agent_ids:
+            states = self.multi_agent_rule_state_.setdefault(agent_id, [])
+            others = [i for i in current if i != agent_id]
+            for k, rule in enumerate(self._rules_of(agent_id)):
+                states.extend(self._make_rule_state(k, rule, others))
+        # missing permutations of the agents that were already known
+        for agent_id in sorted(self.known_agents_):
+            states = self.multi_agent_rule_state_[agent_id]
+            for k, rule in enumerate(self._rules_of(agent_id)):
+                if rule.IsAgentSpecific():
+                    states.extend(self._make_rule_state(k, rule, list(new_agent_ids)))
+
+    @staticmethod
+    def _make_rule_state(k, rule, others):
+        if rule.IsAgentSpecific():
+            return [RuleState(k, (o,), rule.table.init) for o in others]
+        return [RuleState(k, (), rule.table.init)]
+
+    def RemoveRuleStates(self, current_agents):
+        current = set(current_agents)
+        for agent_id in list(self.multi_agent_rule_state_):
+            if agent_id not in current:       # agent is out of the map
+                self.known_agents_.discard(agent_id)
+                del self.multi_agent_rule_state_[agent_id]
+                continue
+            self.multi_agent_rule_state_[agent_id] = [
+                rs for rs in self.multi_agent_rule_state_[agent_id] if set(rs.agent_ids) <= current]
+
+    def GetAgentIdMap(self, observed_world):
+        ids = [observed_world.GetEgoAgentId()]
+        if self.multi_agent_:
+            ids += [i for i in observed_world.GetValidOtherAgents()
+                    if i not in self.prediction_settings_.specific_prediction_agents_]
+        return ids
+
+    # -- one planning step --------------------------------------------------------------------
+    def _configure(self, observed_world, agent_ids):
+        """Device engine for the agents of this world: MCTS agents first (ego = 0), then the
+        agents that are only predicted."""
+        order = agent_ids + [i for i in observed_world.GetValidAgents() if i not in agent_ids]
+        ps = self.prediction_settings_
+        models = []
+        for k, i in enumerate(order):
+            if k == 0:
+                prim = ps.ego_primitives
+            elif k < len(agent_ids):
+                prim = ps.others_primitives or ps.ego_primitives
+            else:
+                prim = [(0.0, 0.0)]
+            m = copy.copy(self.shape)
+            m.primitives = list(prim)
+            m.goal = self.ego_goal if k == 0 else None
+            models.append(m)
+        state = np.array([observed_world.agents[i] for i in order], np.float32)
+        scn = Scenario(self.state_params_, models, len(agent_ids), observed_world.lanes,
+                       np.asarray(observed_world.road), self.common_rules_, state)
+        return RulesMctsEngine([scn], engine=self._abi_engine), order
+
+    def _slots(self, order, a):
+        """(rule index, bound world agent id or None) of every rule slot of MCTS agent a, in the
+        engine's order: rules in order, agent-specific ones once per other agent ascending."""
+        out = []
+        for k, rule in enumerate(self.common_rules_):
+            if rule.IsAgentSpecific():
+                out += [(k, o) for j, o in enumerate(order) if j != a]
+            else:
+                out.append((k, None))
+        return out
+
+    def Plan(self, delta_time, observed_world: ObservedWorld):
+        nearby = observed_world.GetNearestAgents(observed_world.CurrentEgoPosition(), 3)
+        ps = self.prediction_settings_
+        ps.specific_prediction_agents_ = {i for i in observed_world.GetValidOtherAgents() if i not in nearby}
+        new_agents = self.GetNewAgents(observed_world.GetValidAgents())
+        self.MakeRuleStates(new_agents)
+        self.AddKnownAgents(new_agents)
+        agent_ids = self.GetAgentIdMap(observed_world)
+        self.RemoveRuleStates(list(observed_world.GetValidAgents()))
+        if any(self.agent_rules_.get(i) for i in agent_ids):
+            raise NotImplementedError("per-agent rule sets are not uploaded to the device engine yet")
+
+        engine, order = self._configure(observed_world, agent_ids)
+        M, R = engine.M, engine.R
+        q0 = np.zeros((M, R), np.uint8)
+        index = []
+        for a in range(M):
+            states = {(rs.rule, rs.agent_ids): rs for rs in self.multi_agent_rule_state_[order[a]]}
+            row = [states[(k, () if o is None else (o,))] for k, o in self._slots(order, a)]
+            assert len(row) == R
+            q0[a] = [rs.q for rs in row]
+            index.append(row)
+        root = engine.make_batch(engine.scenarios[0].initial_state[None], q=q0)
+        if root.terminal[0]:
+            raise RuntimeError("Current state is terminal! Aborting!")     # :208-209
+        # transit the automata from the last planning step to the current world (:211-214)
+        root, _ = engine.evaluate_rules(root)
+        for a in range(M):
+            for s, rs in enumerate(index[a]):
+                rs.q = int(root.q[a, s, 0])
+                rs.violations += int(root.viol[a, s, 0])
+        root.viol[:] = 0
+
+        sp = self.state_params_
+        mp = MctsParameters(engine.V, discount_factor=sp.DISCOUNT_FACTOR,
+                            exploration_constant=self.params.UCTExplorationConstant,
+                            threshold=self.params.Threshold,
+                            max_rollout_steps=self.params.MaxNumIterationsRandomHeuristic,
+                            rollouts_per_expansion=self.params.RolloutsPerExpansion,
+                            seed=self.params.RandomSeed + self._decision)
+        self._decision += 1
+        mcts = Mcts(engine, mp).Search(root, self.params.MaxNumIterations)
+        self.last_stats = mcts.GetRootStats()
+        best = mcts.ReturnBestAction()[0]
+        self.last_action_ = best
+        self.mcts_ = mcts
+        self.agent_ids_ = agent_ids
+
+        # the ego's motion primitive over delta_time (ego_model->Plan)
+        ego = observed_world.agents[observed_world.ego_id]
+        tp = copy.copy(sp)
+        tp.PREDICTION_TIME_SPAN = float(delta_time)
+        m = copy.copy(self.shape)
+        m.primitives = list(ps.ego_primitives)
+        one = RulesMctsEngine([Scenario(tp, [m], 1, observed_world.lanes, np.asarray(observed_world.road), [],
+                                        np.asarray(ego, np.float32)[None])], engine=self._abi_engine)
+        b = one.make_batch(one.scenarios[0].initial_state[None])
+        b.terminal[:] = 0   # the primitive is executed whatever CheckTerminal says about the horizon
+        nxt, _ = one.execute(b, np.array([[best]], np.uint8))
+        t0 = observed_world.time
+        traj = np.array([[t0, *map(float, ego)], [t0 + delta_time, *map(float, nxt.agents[0, 0])]])
+        self.last_trajectory_ = traj
+        return traj
+
+    def GetLastAction(self):
+        return self.last_action_
+
+    def GetLastTrajectory(self):
+        return self.last_trajectory_
+
+    def GetMultiAgentRuleState(self):
+        return self.multi_agent_rule_state_
+
+    def GetKnownAgents(self):
+        return sorted(self.known_agents_)

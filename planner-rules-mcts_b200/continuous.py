@@ -315,6 +315,22 @@ class RulesMctsEngine:
                                            _ptr(rewards)))
         return out, rewards
 
+    def evaluate_rules(self, batch):
+        """MvmctsState::EvaluateRules(): one automaton transition on the labels of the states as
+        they are -> (batch with the new rule states, rule penalties [M][V][n] float32)."""
+        n = batch.n
+        if batch.device:
+            import torch
+            out = CwBatch(*[None if getattr(batch, f) is None else torch.empty_like(getattr(batch, f))
+                            for f in CwBatch.FIELDS])
+            rewards = torch.zeros((self.M, self.V, n), dtype=torch.float32, device=batch.agents.device)
+        else:
+            out = CwBatch.zeros(self.A, self.M, self.R, n, batch.viol is not None)
+            rewards = np.zeros((self.M, self.V, n), np.float32)
+        sin, sout = batch.to_abi(), out.to_abi()
+        _abi.check(self.lib.brm_cw_evaluate_rules(self.engine.handle, C.byref(sin), C.byref(sout), _ptr(rewards)))
+        return out, rewards
+
     def get_num_actions(self, batch):
         out = np.zeros((self.M, batch.n), np.uint8)
         s = batch.to_abi()

@@ -83,7 +83,7 @@ struct CwLaunchCtx {
   CwCommon c;
   size_t smem_bytes;
 };
-enum { MODE_EXECUTE = 0, MODE_QUERY = 1, MODE_REPLAY = 2 };
+enum { MODE_EXECUTE = 0, MODE_QUERY = 1, MODE_REPLAY = 2, MODE_RULES = 3 };
 
 // per-lane agent state
 struct CwAgent {
@@ -385,11 +385,14 @@ __device__ __forceinline__ bool cw_rect_overlap(const CwBlob& B, const CwAgent& 
 //   live    : my group executes this step
 //   in_*    : my agent's v, theta, flags BEFORE the kinematic step
 //   q, viol : this thread's column of the per-slot automaton state / violation counters
+//   rules_only : MvmctsState::EvaluateRules() (:186-197) on the state as it is -- labels and
+//                automaton transitions of every MCTS agent, no other reward term, no invalidation
 template <bool WITH_LABELS, bool PASSIVE>
 __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, int base, bool real,
                                             bool live, float in_v, float in_th, uint32_t in_flags,
                                             int horizon_after, uint8_t* q, uint8_t* viol,
-                                            int col_stride, const float* pas, CwStepOut& o) {
+                                            int col_stride, const float* pas, CwStepOut& o,
+                                            bool rules_only = false) {
   const int A = B.A, M = B.M, V = B.V;
   const bool present = real && (t.flags & BRM_CW_PRESENT);
   const bool evaluated = live && present && (in_flags & BRM_CW_VALID) && a < M;
@@ -445,10 +448,10 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
   }
 
   if (evaluated) {
-    r.c0 += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92
-    r.c0 += (oom ? 1.f : 0.f) * B.w_oom;    // :94-96
-    // GetActionCost (:202-248)
-    {
+    if (!rules_only) {
+      r.c0 += (coll ? 1.f : 0.f) * B.w_coll;  // :91-92
+      r.c0 += (oom ? 1.f : 0.f) * B.w_oom;    // :94-96
+      // GetActionCost (:202-248)
       const float acc = (t.v - in_v) * B.inv_dt;
       float cost = B.w_acc * acc * acc * B.dt;
       const float theta_dot = (t.th - in_th) * B.inv_dt;
@@ -486,7 +489,7 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
     if (WITH_LABELS) {
       o.w[0] = w0; o.w[1] = merged_mask; o.w[2] = front_mask; o.w[3] = near_mask;
     }
-    if (!(B.ego_only && a != 0)) {  // :104-108
+    if (rules_only || !(B.ego_only && a != 0)) {  // :104-108
       CwVec rr = {0.f, 0.f, 0.f, 0.f};
       for (int sl = 0; sl < B.R; ++sl) {
         // one 16-byte record per slot: x = label kinds of the 4 APs (a byte each),
@@ -521,8 +524,8 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
       }
       r.c0 += rr.c0; r.c1 += rr.c1; r.c2 += rr.c2; r.c3 += rr.c3;
     }
-    if (goal) vec_add_at(r, V - 1, B.goal_reward);  // :110-113
-    if (coll) t.flags &= ~static_cast<uint32_t>(BRM_CW_VALID);  // :116-120
+    if (goal && !rules_only) vec_add_at(r, V - 1, B.goal_reward);  // :110-113
+    if (coll && !rules_only) t.flags &= ~static_cast<uint32_t>(BRM_CW_VALID);  // :116-120
   }
   // CheckTerminal of the new state (:266-285), decided by the ego lane of the group
   const bool ego_term = !present || horizon_after == 0 || oom || coll || goal;

@@ -442,6 +442,32 @@ int brm_cw_execute(brm_engine* e, const brm_cw_states* in, const uint8_t* action
   return BRM_OK;
 }
 
+int brm_cw_evaluate_rules(brm_engine* e, const brm_cw_states* in, brm_cw_states* out, float* rewards) {
+  BRM_TRY(check_ready(e, "brm_cw_evaluate_rules"));
+  BRM_TRY(check_states(e, in, "brm_cw_evaluate_rules", true));
+  BRM_REQUIRE(out && out->scenario && out->agents && out->flags && out->horizon && out->terminal && out->q,
+              "brm_cw_evaluate_rules: every array of `out` except viol is required");
+  BRM_REQUIRE(rewards, "brm_cw_evaluate_rules: rewards is NULL");
+  BRM_REQUIRE(in->n == out->n && in->mem == out->mem, "brm_cw_evaluate_rules: in/out batch mismatch");
+  BRM_CUDA_CHECK(cudaSetDevice(e->device));
+  CwEngine* c = cw_of(e);
+  const int A = c->ctx.c.A, M = c->ctx.c.M, R = c->ctx.c.R, V = c->ctx.c.V;
+  const size_t n = in->n;
+  if (in->mem == BRM_MEM_DEVICE)
+    return cw_launch_batch(e, c->ctx, MODE_RULES, *in, out, nullptr, rewards, nullptr, nullptr, 0, 0, nullptr);
+  Stager st(e);
+  brm_cw_states d_in, d_out;
+  float* d_rew;
+  BRM_TRY(upload_states(st, *in, A, M, R, &d_in));
+  BRM_TRY(alloc_states(st, *out, A, M, R, &d_out));
+  BRM_TRY(st.alloc(M * V * n, &d_rew, true));
+  BRM_TRY(cw_launch_batch(e, c->ctx, MODE_RULES, d_in, &d_out, nullptr, d_rew, nullptr, nullptr, 0, 0, nullptr));
+  BRM_TRY(download_states(st, d_out, A, M, R, out));
+  BRM_TRY(st.out(rewards, d_rew, M * V * n));
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  return BRM_OK;
+}
+
 static int cw_query(brm_engine* e, const brm_cw_states* s, uint8_t* num_actions, float* term_reward,
                     const char* fn) {
   BRM_TRY(check_ready(e, fn));

@@ -548,21 +548,24 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
       continue;
     }
 
-    if (MODE == MODE_EXECUTE) {
+    if (MODE == MODE_EXECUTE || MODE == MODE_RULES) {
+      // MODE_RULES: EvaluateRules() on the state as it is (no kinematic step, horizon and
+      // terminal flag untouched)
+      constexpr bool kRules = MODE == MODE_RULES;
       const bool movable = (t.flags & BRM_CW_PRESENT) && (t.flags & BRM_CW_VALID);
       uint32_t act = 0;
-      if (on) act = args.actions[static_cast<int64_t>(a) * n + i];
+      if (on && !kRules) act = args.actions[static_cast<int64_t>(a) * n + i];
       if (!movable) act = 0;
       const float in_v = t.v, in_th = t.th;
       const uint32_t in_flags = t.flags;
-      if (on && movable) {
+      if (on && movable && !kRules) {
         cw_integrate(B, t, a, act);
         cw_frenet(B, t);
       }
-      cw_move_passive(B, c, m, sm, on);
+      if (!kRules) cw_move_passive(B, c, m, sm, on);
       CwStepOut o;
       cw_evaluate<false, true>(B, t, a, base, real, on, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
-                         kThreads, sm.pas, o);
+                               kThreads, sm.pas, o, kRules);
       if (on) {
         reinterpret_cast<float4*>(args.out.agents)[static_cast<int64_t>(a) * n + i] =
             make_float4(t.x, t.y, t.th, t.v);
@@ -577,8 +580,8 @@ __global__ void __launch_bounds__(kThreads) cw_batch_kernel(const CwBatchArgs ar
           args.out.flags[static_cast<int64_t>(j) * n + i] = static_cast<uint8_t>(p.flags);
         }
         if (a == 0) {
-          args.out.horizon[i] = horizon - 1;
-          args.out.terminal[i] = o.terminal ? 1 : 0;
+          args.out.horizon[i] = kRules ? horizon : horizon - 1;
+          args.out.terminal[i] = kRules ? args.in.terminal[i] : (o.terminal ? 1 : 0);
           args.out.scenario[i] = args.in.scenario[i];
         }
         for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = o.r[v];
@@ -769,6 +772,7 @@ int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_c
     cudaFuncSetAttribute(cw_batch_kernel<MODE_EXECUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(cw_batch_kernel<MODE_QUERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(cw_batch_kernel<MODE_REPLAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_batch_kernel<MODE_RULES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   CwBatchArgs a;
@@ -789,6 +793,8 @@ int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_c
     cw_batch_kernel<MODE_EXECUTE><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
   else if (mode == MODE_QUERY)
     cw_batch_kernel<MODE_QUERY><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
+  else if (mode == MODE_RULES)
+    cw_batch_kernel<MODE_RULES><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
   else
     cw_batch_kernel<MODE_REPLAY><<<grid, kThreads, ctx.smem_bytes, e->stream>>>(a);
   e->launches++;

@@ -1,0 +1,110 @@
+"""The stateful planner plugin (behavior.py) in a closed loop: rule states are
+created for new agents, carried from one planning step to the next by EvaluateRules on the GPU,
+and dropped with agents that leave (src/behavior_rules_mcts.hpp:158-255,295-350,469-502)."""
+import numpy as np
+import pytest
+
+import planner_rules_mcts_b200 as brm
+from planner_rules_mcts_b200 import behavior, scenarios
+from planner_rules_mcts_b200.ltl import RuleMonitor
+from planner_rules_mcts_b200.planner import PlannerParameters
+
+pytestmark = pytest.mark.gpu
+
+EGO = 7
+PRIMS = [(0.0, 0.0), (1.0, 0.0), (-1.0, 0.0)]
+
+
+def make_world(agents, t=0.0):
+    base = scenarios.straight_road_test_world()
+    return behavior.ObservedWorld(EGO, {i: np.asarray(s, np.float32) for i, s in agents.items()},
+                                  base.lanes, base.road, t)
+
+
+def make_planner(iters=150):
+    rules = [RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0),
+             RuleMonitor.MakeRule("F near_x#0", -1.0, 0)]          # remembers having been near agent #0
+    sp = brm.RulesMctsStateParameters(HORIZON=10, NEAR_DISTANCE=12.0)
+    return behavior.BehaviorRulesMcts(
+        PlannerParameters(MaxNumIterations=iters, RolloutsPerExpansion=8), sp,
+        behavior.PredictionSettings(ego_primitives=PRIMS), common_rules=rules, multi_agent=True,
+        shape=brm.AgentModel(**scenarios.CAR))
+
+
+def test_rule_state_bookkeeping_closed_loop(built):
+    pl = make_planner()
+    F = pl.common_rules_[1].table
+    done = [q for q in range(F.n_states) if F.accepting[q]]       # "has been near" states
+    # ego 7; car 3 comes up fast from behind on the other lane (not near yet) and overtakes whatever
+    # the ego does; 12 far ahead on the other lane, 20 ahead on the ego's lane
+    agents = {EGO: (0.0, -1.75, 0.0, 8.0), 3: (-40.0, -5.25, 0.0, 20.0), 12: (60.0, -5.25, 0.0, 8.0),
+              20: (50.0, -1.75, 0.0, 9.0)}
+    dt = 0.3
+    seen_near_3 = None
+    for step in range(22):
+        if step == 4:
+            agents[31] = (agents[EGO][0] + 90.0, -5.25, 0.0, 9.0)  # a new agent appears
+        if step == 8:
+            del agents[12]                                         # an agent leaves the map
+        w = make_world(agents, step * dt)
+        traj = pl.Plan(dt, w)
+        assert traj.shape == (2, 5) and traj[1, 0] == pytest.approx((step + 1) * dt)
+        ids = pl.agent_ids_
+        assert ids[0] == EGO and len(ids) == 3                    # ego + the two nearest others
+        assert set(ids[1:]) | pl.prediction_settings_.specific_prediction_agents_ == set(agents) - {EGO}
+        # one state per common rule and, for the agent-specific rule, per other known agent
+        assert pl.GetKnownAgents() == sorted(agents)
+        for i in agents:
+            rs = pl.GetMultiAgentRuleState()[i]
+            assert sorted((r.rule, r.agent_ids) for r in rs) == \
+                sorted([(0, ())] + [(1, (o,)) for o in agents if o != i])
+        ego_rs = {r.agent_ids: r for r in pl.GetMultiAgentRuleState()[EGO] if r.rule == 1}
+        gap = agents[3][0] - agents[EGO][0]
+        if seen_near_3 is None and ego_rs[(3,)].q in done:
+            seen_near_3 = step
+            assert abs(gap) < 12.0 + 1e-3
+        if seen_near_3 is not None:
+            assert ego_rs[(3,)].q in done                          # carried across planning steps
+        elif abs(gap) > 12.0 + 1e-3:
+            assert ego_rs[(3,)].q == F.init
+        # world step: ego follows its trajectory, the others keep their speed
+        agents[EGO] = tuple(traj[1, 1:])
+        for i in agents:
+            if i != EGO:
+                x, y, th, v = agents[i]
+                agents[i] = (x + v * dt, y, th, v)
+    assert seen_near_3 is not None                                 # agent 3 came near ...
+    assert agents[3][0] - agents[EGO][0] > 12.0                    # ... and is far ahead again: the state was kept
+    assert agents[20][0] - agents[EGO][0] > 4.0                    # nobody was run into
+    assert 12 not in pl.GetMultiAgentRuleState() and 31 in pl.GetMultiAgentRuleState()
+
+
+def test_terminal_root_is_refused(built):
+    pl = make_planner(10)
+    w = make_world({EGO: (0.0, -1.75, 0.0, 8.0), 3: (2.0, -1.75, 0.0, 3.0)})   # already overlapping
+    with pytest.raises(RuntimeError):
+        pl.Plan(0.3, w)
+
+
+def test_evaluate_rules_matches_execute_transition(built):
+    """brm_cw_evaluate_rules on Execute's successor kinematics with the predecessor's automaton
+    states gives exactly Execute's automaton states (no collision in the step)."""
+    scn = scenarios.merge_scenario()
+    eng = brm.RulesMctsEngine([scn])
+    b = eng.initial_batch([0]).select(np.zeros(64, np.int64))
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        acts = rng.integers(0, 3, size=(eng.M, b.n)).astype(np.uint8)
+        nxt, _ = eng.execute(b, acts)
+        probe = brm.CwBatch(nxt.scenario.copy(), nxt.agents.copy(), nxt.flags.copy(), nxt.horizon.copy(),
+                            nxt.terminal.copy(), b.q.copy(), np.zeros_like(b.viol))
+        out, rew = eng.evaluate_rules(probe)
+        same_flags = (nxt.flags == b.flags).all(axis=0)            # nobody was invalidated in this step
+        assert same_flags.any()
+        assert (out.q[:, :, same_flags] == nxt.q[:, :, same_flags]).all()
+        assert (out.agents == nxt.agents).all() and (out.horizon == nxt.horizon).all()
+        assert (rew <= 0).all()
+        keep = ~nxt.terminal.astype(bool)
+        if not keep.any():
+            break
+        b = nxt.select(np.flatnonzero(keep))
