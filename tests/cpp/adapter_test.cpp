@@ -105,6 +105,11 @@ int main(int argc, char** argv) {
     } catch (const brm::Error& err) {
       std::printf("execute on terminal: error %d\n", err.code);
     }
+    // EvaluateRules() on the collided state: the `G !collision_ego` monitor fires once more
+    brm::MvmctsState s4(*s3);
+    auto rule_rewards = s4.EvaluateRules();
+    std::printf("evaluate_rules on collided state %.9g, on the initial state %.9g\n", rule_rewards[0][0],
+                brm::MvmctsState(s0).EvaluateRules()[0][0]);
     return 0;
   }
   return 1;

@@ -83,3 +83,5 @@ def test_adapter_continuous_reference_pins(exe, tmp_path):
     assert lines[2] == "a1 terminal 1 total -800"          # :152
     assert lines[3] == "a2 terminal 1 total -1000 num_actions 1"  # :159
     assert lines[4] == "execute on terminal: error -4"     # BARK_EXPECT_TRUE(!IsTerminal()), :59
+    # the collided agent is INVALID, so its rules are not evaluated any more (:177); no violation at the start
+    assert lines[5] == "evaluate_rules on collided state 0, on the initial state 0"
