@@ -174,7 +174,8 @@ int32_t brm_gw_rules_per_agent(const brm_engine* e);
 /* GridWorldState::Execute (gridworld/grid_world_state.cpp:45-90) for n states.
  *   actions [A][n] uint8 action indices; rewards [A][V][n] double.
  * Step rewards of agents that were already terminal are 0 (the reference leaves the
- * caller's slot untouched, :59-62). */
+ * caller's slot untouched, :59-62).  `in` and `out` must not overlap (Execute is const and
+ * returns a new state in the reference as well). */
 int brm_gw_execute(brm_engine* e, const brm_gw_states* in, const uint8_t* actions,
                    brm_gw_states* out, double* rewards);
 /* GridWorldState::GetNumActions (:154-159): out [A][n] */

@@ -163,6 +163,8 @@ int brm_gw_execute(brm_engine* e, const brm_gw_states* in, const uint8_t* action
   BRM_TRY(check_states(out, "brm_gw_execute(out)"));
   BRM_REQUIRE(actions && rewards, "brm_gw_execute: actions/rewards is NULL");
   BRM_REQUIRE(in->n == out->n && in->mem == out->mem, "brm_gw_execute: in/out batch mismatch");
+  BRM_REQUIRE(in->agents != out->agents && in->q != out->q && in->term != out->term && in->depth != out->depth,
+              "brm_gw_execute: in and out must not share arrays");
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
   const size_t n = in->n;

@@ -217,39 +217,73 @@ __global__ void __launch_bounds__(256, BRM_GW_EXEC_MIN_CTAS) gw_execute_kernel(c
   const GwBlob& B = sB;
   const int V = B.V, R = B.R;
   const int64_t n = args.in.n;
+  // This kernel streams every state once (HBM-bound): all loads of a state are issued before
+  // anything is stored, through non-aliasing read-only pointers, so that they overlap.
+  // in and out must not overlap (include/brm.h).
+  const int4* __restrict__ in_ag = reinterpret_cast<const int4*>(args.in.agents);
+  const uint8_t* __restrict__ in_q = args.in.q;
+  const uint8_t* __restrict__ in_term = args.in.term;
+  const int32_t* __restrict__ in_depth = args.in.depth;
+  const uint32_t* __restrict__ in_viol = args.in.viol;
+  const uint8_t* __restrict__ in_act = args.actions;
+  int4* __restrict__ out_ag = reinterpret_cast<int4*>(args.out.agents);
+  uint8_t* __restrict__ out_q = args.out.q;
+  uint8_t* __restrict__ out_term = args.out.term;
+  int32_t* __restrict__ out_depth = args.out.depth;
+  uint32_t* __restrict__ out_viol = args.out.viol;
+  double* __restrict__ out_rew = args.rewards;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     GwRegs<A> s;
-    gw_load_state<A>(args.in, R, i, s);
     uint32_t act[A];
+    uint32_t inc[A];  // slots of agent a that recorded a violation in this step (one bit each)
 #pragma unroll
-    for (int a = 0; a < A; ++a) act[a] = args.actions[static_cast<int64_t>(a) * n + i];
-    // carry violation counters through (if tracked)
-    if (args.out.viol && args.in.viol)
-      for (int a = 0; a < A; ++a)
-        for (int r = 0; r < R; ++r) {
-          const int64_t o = (static_cast<int64_t>(a) * R + r) * n + i;
-          args.out.viol[o] = args.in.viol[o];
-        }
+    for (int a = 0; a < A; ++a) {
+      const int4 v = __ldg(&in_ag[a * n + i]);
+      s.x[a] = v.x;
+      s.last[a] = v.y;
+      s.lane[a] = v.z;
+      s.init_lane[a] = v.w;
+      act[a] = __ldg(&in_act[static_cast<int64_t>(a) * n + i]);
+      inc[a] = 0u;
+    }
+    s.term = __ldg(&in_term[i]);
+    s.depth = __ldg(&in_depth[i]);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      uint64_t q = 0;
+      for (int r = 0; r < R; ++r)
+        q |= static_cast<uint64_t>(__ldg(&in_q[(static_cast<int64_t>(a) * R + r) * n + i]) & 15u) << (4 * r);
+      s.q[a] = q;
+    }
     gw_step<A>(
         B, s, act,
         [&](int a, const double(&r)[BRM_MAX_REWARD]) {
-          for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(a) * V + v) * n + i] = r[v];
+          for (int v = 0; v < V; ++v) out_rew[(static_cast<int64_t>(a) * V + v) * n + i] = r[v];
         },
         [&](int a, int sl) {
-          if (args.out.viol) args.out.viol[(static_cast<int64_t>(a) * R + sl) * n + i] += 1u;
+#pragma unroll
+          for (int b = 0; b < A; ++b)
+            if (b == a) inc[b] |= 1u << sl;
         },
         [](int, const GwLabels&) {});
-    int4* ag = reinterpret_cast<int4*>(args.out.agents);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-      ag[a * n + i] = make_int4(s.x[a], s.last[a], s.lane[a], s.init_lane[a]);
+      out_ag[a * n + i] = make_int4(s.x[a], s.last[a], s.lane[a], s.init_lane[a]);
       for (int r = 0; r < R; ++r)
-        args.out.q[(static_cast<int64_t>(a) * R + r) * n + i] =
-            static_cast<uint8_t>((s.q[a] >> (4 * r)) & 15u);
+        out_q[(static_cast<int64_t>(a) * R + r) * n + i] = static_cast<uint8_t>((s.q[a] >> (4 * r)) & 15u);
     }
-    args.out.term[i] = static_cast<uint8_t>(s.term);
-    args.out.depth[i] = s.depth;
+    out_term[i] = static_cast<uint8_t>(s.term);
+    out_depth[i] = s.depth;
+    // violation counters (if tracked): carried through plus this step's violations
+    if (out_viol) {
+#pragma unroll
+      for (int a = 0; a < A; ++a)
+        for (int r = 0; r < R; ++r) {
+          const int64_t o = (static_cast<int64_t>(a) * R + r) * n + i;
+          out_viol[o] = (in_viol ? __ldg(&in_viol[o]) : 0u) + ((inc[a] >> r) & 1u);
+        }
+    }
   }
 }
 
