@@ -90,7 +90,8 @@ class BehaviorRulesMcts:
         self.last_action_ = None
         self.last_trajectory_ = None
         self.last_stats = None
-        self._abi_engine = _abi.Engine(device)
+        self._device = device
+        self._abi_engine = None   # created by the first Plan(): the bookkeeping alone needs no GPU
         self._decision = 0
 
     # -- rules ------------------------------------------------------------------------------
@@ -199,6 +200,8 @@ class BehaviorRulesMcts:
         if any(self.agent_rules_.get(i) for i in agent_ids):
             raise NotImplementedError("per-agent rule sets are not uploaded to the device engine yet")
 
+        if self._abi_engine is None:
+            self._abi_engine = _abi.Engine(self._device)
         engine, order = self._configure(observed_world, agent_ids)
         M, R = engine.M, engine.R
         q0 = np.zeros((M, R), np.uint8)
