@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BRM_ABI_VERSION 1
+#define BRM_ABI_VERSION 2
 
 #define BRM_OK 0
 #define BRM_ERR_INVALID (-1)
@@ -121,6 +121,9 @@ typedef struct {
   double discount_factor;     /* DISCOUNT_FACTOR */
   int32_t first_discount_exp; /* 1: first step reward weighted by gamma (default), 0: by 1 */
   int32_t _pad;
+  /* COOP_FACTOR (src/util.cpp:28-29; 0 in every test of the reference): returns_sum of agent i
+   * is own_i + coop_factor * sum_{j != i} own_j.  Per-rollout outputs (ro_returns) stay unmixed. */
+  double coop_factor;
 } brm_rollout_params;
 
 /* ------------------------------------------------------------- GridWorld ------ */

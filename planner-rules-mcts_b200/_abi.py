@@ -43,6 +43,7 @@ class RolloutParams(C.Structure):
         ("rollouts_per_leaf", C.c_int32), ("max_steps", C.c_int32),
         ("discount_factor", C.c_double),
         ("first_discount_exp", C.c_int32), ("_pad", C.c_int32),
+        ("coop_factor", C.c_double),
     ]
 
 

@@ -345,9 +345,10 @@ class RulesMctsEngine:
 
     # -- rollouts -----------------------------------------------------------------------
     def rollout(self, leaves, rollouts_per_leaf, seed=1000, rollout_base=0, max_steps=30,
-                discount_factor=None, first_discount_exp=1, detail=False, out=None):
+                discount_factor=None, first_discount_exp=1, detail=False, out=None, coop_factor=0.0):
         gamma = self.scenarios[0].params.DISCOUNT_FACTOR if discount_factor is None else discount_factor
-        rp = _abi.RolloutParams(seed, rollout_base, rollouts_per_leaf, max_steps, gamma, first_discount_exp, 0)
+        rp = _abi.RolloutParams(seed, rollout_base, rollouts_per_leaf, max_steps, gamma, first_discount_exp, 0,
+                                coop_factor)
         L = leaves.n
         N = L * rollouts_per_leaf
         A, M, V, R = self.A, self.M, self.V, self.R

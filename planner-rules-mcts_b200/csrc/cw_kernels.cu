@@ -462,11 +462,23 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
   cw_acc_flush(args, lacc, viol_tot, a);
 }
 
-// fixed point -> double
+// fixed point -> double, and the agents' sums mixed: value_i = own_i + coop * sum_{j != i} own_j
+// (mvmcts COOP_FACTOR, src/util.cpp:28-29; 0 in every test of the reference: unpinned)
 __global__ void cw_finalize_returns_kernel(const long long* __restrict__ fx, double* __restrict__ out,
-                                           int64_t count) {
+                                           int64_t count, int M, int V, double coop) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = static_cast<double>(fx[i]) * (1.0 / kFixScale);
+  if (i >= count) return;
+  const double own = static_cast<double>(fx[i]) * (1.0 / kFixScale);
+  double others = 0.0;
+  if (coop != 0.0) {
+    const int64_t leaf = i / (static_cast<int64_t>(M) * V);
+    const int v = static_cast<int>(i % V);
+    for (int j = 0; j < M; ++j) {
+      const int64_t o = (leaf * M + j) * V + v;
+      if (o != i) others += static_cast<double>(fx[o]) * (1.0 / kFixScale);
+    }
+  }
+  out[i] = coop != 0.0 ? own + coop * others : own;
 }
 
 // ------------------------------------------------------------------ K4 / K6 / queries
@@ -749,7 +761,7 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
     cw_rollout_kernel<false><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
   e->launches++;
   cw_finalize_returns_kernel<<<static_cast<int>((fx_count + 255) / 256), 256, 0, e->stream>>>(
-      a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count));
+      a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count), M, V, rp.coop_factor);
   e->launches++;
   e->time_end();
   BRM_CUDA_CHECK(cudaGetLastError());

@@ -177,12 +177,16 @@ gw_rollout_kernel(const GwRolloutArgs args) {
   }
 }
 
-// Deterministic second stage: per leaf, sum the warp partials in a fixed order.
+// Deterministic second stage: per leaf, sum the warp partials in a fixed order, then mix the
+// agents' sums: value_i = own_i + coop * sum_{j != i} own_j (mvmcts COOP_FACTOR, src/util.cpp:28-29;
+// 0 in every test of the reference, so the mixing rule itself is unpinned).
 __global__ void __launch_bounds__(128)
-leaf_reduce_kernel(const double* __restrict__ part, int32_t warps_per_leaf, int32_t nvals,
-                   double* __restrict__ out) {
+leaf_reduce_kernel(const double* __restrict__ part, int32_t warps_per_leaf, int32_t n_agents, int32_t V,
+                   double coop, double* __restrict__ out) {
   __shared__ double sm[128];
+  __shared__ double own[BRM_GW_MAX_AGENTS * BRM_MAX_REWARD];
   const int64_t leaf = blockIdx.x;
+  const int nvals = n_agents * V;
   for (int val = 0; val < nvals; ++val) {
     double x = 0.0;
     for (int w = threadIdx.x; w < warps_per_leaf; w += blockDim.x)
@@ -193,8 +197,15 @@ leaf_reduce_kernel(const double* __restrict__ part, int32_t warps_per_leaf, int3
       if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
       __syncthreads();
     }
-    if (threadIdx.x == 0) out[leaf * nvals + val] = sm[0];
+    if (threadIdx.x == 0) own[val] = sm[0];
     __syncthreads();
+  }
+  if (threadIdx.x < nvals) {
+    const int v = threadIdx.x % V;
+    double others = 0.0;
+    for (int j = 0; j < n_agents; ++j)
+      if (j * V + v != static_cast<int>(threadIdx.x)) others += own[j * V + v];
+    out[leaf * nvals + threadIdx.x] = coop != 0.0 ? own[threadIdx.x] + coop * others : own[threadIdx.x];
   }
 }
 
@@ -439,9 +450,9 @@ int grid_for(const brm_engine* e, int64_t threads_needed, int block, int ctas_pe
 }  // namespace
 
 // second-stage reduction shared with the continuous-world rollout kernel
-void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t nvals,
-                        double* out, int32_t n_leaves) {
-  leaf_reduce_kernel<<<n_leaves, 128, 0, e->stream>>>(part, per_leaf, nvals, out);
+void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t n_agents, int32_t V,
+                        double coop, double* out, int32_t n_leaves) {
+  leaf_reduce_kernel<<<n_leaves, 128, 0, e->stream>>>(part, per_leaf, n_agents, V, coop, out);
   e->launches++;
 }
 
@@ -479,7 +490,7 @@ int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_roll
   rc = dispatch_agents<RolloutLauncher>(A, e, a, grid);
   if (rc != BRM_OK) return rc;
   e->launches++;
-  launch_leaf_reduce(e, a.part_returns, a.warps_per_leaf, A * V, out.returns_sum, leaves.n);
+  launch_leaf_reduce(e, a.part_returns, a.warps_per_leaf, A, V, rp.coop_factor, out.returns_sum, leaves.n);
   e->time_end();
   BRM_CUDA_CHECK(cudaGetLastError());
   return BRM_OK;

@@ -215,12 +215,13 @@ class GridWorldEngine:
 
     # -- rollouts (mvmcts::RandomHeuristic) ----------------------------------------------
     def rollout(self, leaves, rollouts_per_leaf, seed=1000, rollout_base=0, max_steps=30,
-                discount_factor=0.95, first_discount_exp=1, detail=False, out=None):
+                discount_factor=0.95, first_discount_exp=1, detail=False, out=None, coop_factor=0.0):
         """Random rollouts from every leaf state.  Host batches return numpy arrays; for a
         device batch pass `out` = dict of preallocated CUDA tensors (returns_sum, viol_sum,
-        agent_steps) and nothing is copied."""
+        agent_steps) and nothing is copied.  coop_factor: mvmcts COOP_FACTOR, returns_sum of
+        agent i = own_i + coop_factor * sum of the others'."""
         rp = _abi.RolloutParams(seed, rollout_base, rollouts_per_leaf, max_steps, discount_factor,
-                                first_discount_exp, 0)
+                                first_discount_exp, 0, coop_factor)
         L = leaves.n
         N = L * rollouts_per_leaf
         A, V, R = self.A, self.V, self.R

@@ -34,8 +34,9 @@ class MctsParameters:
     """The mvmcts::MvmctsParameters fields the reference sets (src/util.cpp:23-89)."""
 
     def __init__(self, V, discount_factor=0.9, exploration_constant=1.42, lower_bound=None, upper_bound=None,
-                 threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000):
+                 threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000, coop_factor=0.0):
         self.DISCOUNT_FACTOR = discount_factor
+        self.COOP_FACTOR = coop_factor            # src/util.cpp:28-29
         self.EXPLORATION_CONSTANT = exploration_constant
         lb = [-1.0] * V
         lb[-1] = -1000.0                      # src/util.cpp:58-59
@@ -103,9 +104,16 @@ class Mcts:
         n = self.p.rollouts_per_expansion
         out = self.engine.rollout(node.state, n, seed=self.p.seed, rollout_base=self._next_rollout,
                                   max_steps=self.p.MAX_NUMBER_OF_ITERATIONS,
-                                  discount_factor=self.p.DISCOUNT_FACTOR, first_discount_exp=0)
+                                  discount_factor=self.p.DISCOUNT_FACTOR, first_discount_exp=0,
+                                  coop_factor=self.p.COOP_FACTOR)
         self._next_rollout += n
         return out["returns_sum"][0] / n  # [M][V]
+
+    def _coop(self, r):
+        """Cooperative reward [M][V]: own + COOP_FACTOR * the others' (applied to step and terminal
+        rewards here, to rollout returns on the device)."""
+        c = self.p.COOP_FACTOR
+        return r if c == 0.0 else r + c * (r.sum(axis=0, keepdims=True) - r)
 
     # -- search ----------------------------------------------------------------------------
     def Search(self, state, max_iterations):
@@ -118,7 +126,7 @@ class Mcts:
             node, path = self.root, []
             while True:
                 if node.terminal:
-                    value = self.engine.terminal_reward(node.state)[:, :, 0].astype(np.float64)
+                    value = self._coop(self.engine.terminal_reward(node.state)[:, :, 0].astype(np.float64))
                     break
                 ja = self._select(node)
                 if ja in node.children:
@@ -128,7 +136,7 @@ class Mcts:
                     continue
                 nxt, rew = self.engine.execute(node.state, np.array(ja, np.uint8).reshape(M, 1))
                 child = self._make_node(nxt)
-                r = rew[:, :, 0].astype(np.float64)
+                r = self._coop(rew[:, :, 0].astype(np.float64))
                 node.children[ja] = (child, r)
                 path.append((node, ja, r))
                 value = self._evaluate(child)

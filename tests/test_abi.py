@@ -25,13 +25,13 @@ def test_header_symbols_are_exported(built):
     for s in syms:
         assert hasattr(lib, s), "libbrm.so does not export %s" % s
     assert sorted(_abi.SYMBOLS) == syms, "planner_rules_mcts_b200._abi.SYMBOLS out of sync with brm.h"
-    assert lib.brm_abi_version() == 1
+    assert lib.brm_abi_version() == 2
 
 
 def test_struct_sizes_match_header(built):
     # sizes the C side was compiled with (computed from the header's layout rules)
     assert ctypes.sizeof(_abi.Rule) == 8 + 4 + 4 + 4 + 256 + 16
-    assert ctypes.sizeof(_abi.RolloutParams) == 40
+    assert ctypes.sizeof(_abi.RolloutParams) == 48
     assert ctypes.sizeof(_abi.GwParams) == 7 * 4 + 8 * 4 + 4 + 3 * 8
     assert ctypes.sizeof(_abi.GwStates) == 8 + 5 * 8
 

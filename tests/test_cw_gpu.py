@@ -332,3 +332,16 @@ def test_edge_shapes_rollouts_match_oracle(built, orc, n_agents, n_mcts, n):
     assert term.terminal[0] == 1
     z = eng.rollout(term, 8, seed=1)
     assert z["agent_steps"][0] == 0 and np.all(z["viol_sum"] == 0)
+
+
+def test_coop_factor_mixes_agent_returns(built):
+    """COOP_FACTOR (src/util.cpp:28-29): returns_sum_i = own_i + c * sum of the others' (unpinned:
+    0 in every test of the reference); per-rollout returns stay unmixed."""
+    scn = scenarios.merge_scenario()
+    eng = brm.RulesMctsEngine([scn])
+    leaves = eng.initial_batch([0]).select(np.zeros(5, np.int64))
+    own = eng.rollout(leaves, 96, seed=7, max_steps=12, detail=True)
+    mix = eng.rollout(leaves, 96, seed=7, max_steps=12, detail=True, coop_factor=0.25)
+    s = own["returns_sum"]
+    np.testing.assert_allclose(mix["returns_sum"], s + 0.25 * (s.sum(axis=1, keepdims=True) - s), rtol=1e-12, atol=1e-9)
+    assert (mix["ro_returns"] == own["ro_returns"]).all() and (mix["viol_sum"] == own["viol_sum"]).all()

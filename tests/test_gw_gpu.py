@@ -244,3 +244,13 @@ def test_errors(built):
         eng.rollout(leaves, 8, max_steps=1000)
     with pytest.raises(brm.BrmError):
         brm.GridWorldEngine(brm.GridWorldStateParameter(num_other_agents=20), device=0)
+
+
+def test_coop_factor_mixes_agent_returns(built):
+    eng = brm.GridWorldEngine()
+    leaves = eng.base_test_env_batch(7)
+    own = eng.rollout(leaves, 100, seed=3)
+    mix = eng.rollout(leaves, 100, seed=3, coop_factor=0.5)
+    s = own["returns_sum"]
+    np.testing.assert_allclose(mix["returns_sum"], s + 0.5 * (s.sum(axis=1, keepdims=True) - s), rtol=1e-12, atol=1e-9)
+    assert (mix["viol_sum"] == own["viol_sum"]).all()
