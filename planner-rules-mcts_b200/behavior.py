@@ -74,6 +74,8 @@ class RuleState:
 
 
 class BehaviorRulesMcts:
+    STATISTIC = "uct"
+
     def __init__(self, params: PlannerParameters, state_params: RulesMctsStateParameters,
                  prediction_settings: PredictionSettings, common_rules=(), agent_rules=None,
                  multi_agent=True, shape: AgentModel = None, ego_goal=None, device=0):
@@ -93,6 +95,33 @@ class BehaviorRulesMcts:
         self._device = device
         self._abi_engine = None   # created by the first Plan(): the bookkeeping alone needs no GPU
         self._decision = 0
+        self.mcts_ = None
+
+    def __repr__(self):
+        return "bark.behavior." + type(self).__name__
+
+    # pickling as in python/python_planner_rules_mcts.cpp:44-70: parameters, rules and prediction
+    # settings of a model -- not the search state (root, known agents, rule states)
+    def __getstate__(self):
+        return dict(params=self.params, state_params=self.state_params_,
+                    prediction_settings=self.prediction_settings_, common_rules=self.common_rules_,
+                    agent_rules=self.agent_rules_, multi_agent=self.multi_agent_, shape=self.shape,
+                    ego_goal=self.ego_goal, device=self._device)
+
+    def __setstate__(self, st):
+        self.__init__(st["params"], st["state_params"], st["prediction_settings"], st["common_rules"],
+                      st["agent_rules"], st["multi_agent"], st["shape"], st["ego_goal"], st["device"])
+
+    def AddLabels(self, label_names):
+        """The label functions are built into the kernels; this checks that the names exist."""
+        from .continuous import CW_LABELS
+        unknown = [n for n in label_names if n.split("#")[0] not in CW_LABELS]
+        if unknown:
+            raise KeyError("unknown label function(s) %s (known: %s)" % (unknown, sorted(CW_LABELS)))
+
+    def GetTree(self, value_idx=0):
+        """(value, ego polyline) per leaf of the last search tree (:431-460)."""
+        return self.mcts_.GetTree(value_idx) if self.mcts_ is not None else []
 
     # -- rules ------------------------------------------------------------------------------
     def AddCommonRules(self, rules):
@@ -229,7 +258,7 @@ class BehaviorRulesMcts:
                             threshold=self.params.Threshold,
                             max_rollout_steps=self.params.MaxNumIterationsRandomHeuristic,
                             rollouts_per_expansion=self.params.RolloutsPerExpansion,
-                            seed=self.params.RandomSeed + self._decision)
+                            seed=self.params.RandomSeed + self._decision, statistic=self.STATISTIC)
         self._decision += 1
         mcts = Mcts(engine, mp).Search(root, self.params.MaxNumIterations)
         self.last_stats = mcts.GetRootStats()
@@ -265,3 +294,13 @@ class BehaviorRulesMcts:
 
     def GetKnownAgents(self):
         return sorted(self.known_agents_)
+
+
+class BehaviorRulesMctsUct(BehaviorRulesMcts):
+    """BehaviorRulesMcts<ThresUCTStatistic> (python/python_planner_rules_mcts.cpp:30-32)."""
+    STATISTIC = "uct"
+
+
+class BehaviorRulesMctsGreedy(BehaviorRulesMcts):
+    """BehaviorRulesMcts<ThresGreedyStatistic> (python/python_planner_rules_mcts.cpp:72-75)."""
+    STATISTIC = "greedy"

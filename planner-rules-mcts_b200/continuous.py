@@ -410,11 +410,27 @@ class MvmctsState:
                                                   for f in CwBatch.FIELDS]))
 
     def Execute(self, joint_action, rewards=None):
+        """With a `rewards` list (the C++ out-parameter) returns the successor; without one
+        returns (successor, rewards) like the reference's Python binding
+        (python/python_planner_rules_mcts.cpp:113-120)."""
         acts = np.asarray(joint_action, np.uint8).reshape(self.engine.M, 1)
         nb, rew = self.engine.execute(self.batch, acts)  # raises BrmError(ERR_TERMINAL) on a terminal state
+        out = [rew[a, :, 0].astype(np.float64) for a in range(self.engine.M)]
         if rewards is not None:
-            rewards[:] = [rew[a, :, 0].astype(np.float64) for a in range(self.engine.M)]
-        return MvmctsState(self.engine, nb)
+            rewards[:] = out
+            return MvmctsState(self.engine, nb)
+        return MvmctsState(self.engine, nb), out
+
+    def EvaluateRules(self):
+        """:186-197: transit the rule automata on this state (mutates it), returns the penalties."""
+        nb, rew = self.engine.evaluate_rules(self.batch)
+        self.batch = nb
+        return [rew[a, :, 0].astype(np.float64) for a in range(self.engine.M)]
+
+    @property
+    def observed_world(self):
+        """What is left of bark's ObservedWorld here: agent states [A][4] and flags [A]."""
+        return self.GetAgentStates(), self.GetAgentFlags()
 
     def GetNumActions(self, agent_idx):
         return int(self.engine.get_num_actions(self.batch)[agent_idx, 0])

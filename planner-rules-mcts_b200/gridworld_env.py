@@ -19,24 +19,25 @@ from .gridworld import GridWorldEngine, GridWorldState, GridWorldStateParameter,
 from .mcts import Mcts, MctsParameters
 
 
-def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000):
+def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000, statistic="uct"):
     """BaseTestEnv::MakeMctsParameters (gridworld/base_test_env.cpp:45-77)."""
     thres = np.asarray(thres, np.float64)
     assert thres.size == 3
     return MctsParameters(
         3, discount_factor=0.95, exploration_constant=[0.8, 0.8, 0.8],
         lower_bound=[-1.0, -1.0, -100.0], upper_bound=[0.0, 0.0, 0.0], threshold=thres,
-        max_rollout_steps=30, rollouts_per_expansion=rollouts_per_expansion, seed=seed)
+        max_rollout_steps=30, rollouts_per_expansion=rollouts_per_expansion, seed=seed,
+        statistic=statistic, decay1=0.8, decay2=0.12)
 
 
 class CrossingTestEnv:
     """BaseTestEnv + CrossingTestEnv<Stats>: owns the state, the MCTS and the histories."""
 
-    def __init__(self, thres, device=0, engine=None, rollouts_per_expansion=16, seed=1000):
+    def __init__(self, thres, device=0, engine=None, rollouts_per_expansion=16, seed=1000, statistic="uct"):
         self.grid_world_state_parameter = GridWorldStateParameter()
         self.engine = engine or GridWorldEngine(self.grid_world_state_parameter, make_default_rules(),
                                                 device=device)
-        self.mcts_parameters = MakeMctsParameters(thres, rollouts_per_expansion, seed)
+        self.mcts_parameters = MakeMctsParameters(thres, rollouts_per_expansion, seed, statistic)
         self.state = GridWorldState(self.engine)
         A, V = self.engine.A, self.engine.V
         self.rewards = np.zeros((A, V))

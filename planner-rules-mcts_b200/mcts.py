@@ -19,7 +19,7 @@ from . import parallel
 
 
 class _Node:
-    __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q")
+    __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q", "value")
 
     def __init__(self, state, terminal, n_actions, V):
         self.state = state
@@ -28,15 +28,21 @@ class _Node:
         self.children = {}
         self.N = [np.zeros(k) for k in self.n_actions]
         self.Q = [np.zeros((k, V)) for k in self.n_actions]
+        self.value = np.zeros((len(self.n_actions), V))  # the heuristic's estimate at expansion
 
 
 class MctsParameters:
     """The mvmcts::MvmctsParameters fields the reference sets (src/util.cpp:23-89)."""
 
     def __init__(self, V, discount_factor=0.9, exploration_constant=1.42, lower_bound=None, upper_bound=None,
-                 threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000, coop_factor=0.0):
+                 threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000, coop_factor=0.0,
+                 statistic="uct", decay1=0.8, decay2=0.12):
         self.DISCOUNT_FACTOR = discount_factor
         self.COOP_FACTOR = coop_factor            # src/util.cpp:28-29
+        # "uct": ThresUCTStatistic; "greedy": ThresGreedyStatistic (epsilon-greedy on the thresholded
+        # order, epsilon = DECAY1 / (1 + DECAY2 * visits of the node); gridworld/base_test_env.cpp:69-70)
+        assert statistic in ("uct", "greedy")
+        self.statistic, self.DECAY1, self.DECAY2 = statistic, decay1, decay2
         self.EXPLORATION_CONSTANT = exploration_constant
         lb = [-1.0] * V
         lb[-1] = -1000.0                      # src/util.cpp:58-59
@@ -62,6 +68,7 @@ class Mcts:
         # normalised with the same bounds
         span = np.maximum(self.p.UPPER_BOUND - self.p.LOWER_BOUND, 1e-9)
         self._thr_norm = None if self.p.THRESHOLD is None else (self.p.THRESHOLD - self.p.LOWER_BOUND) / span
+        self._rng = np.random.default_rng(self.p.seed)
 
     # -- helpers -----------------------------------------------------------------------
     def _make_node(self, state):
@@ -90,6 +97,16 @@ class Mcts:
             total = node.N[a].sum()
             mean = node.Q[a] / node.N[a][:, None]
             norm = (mean - self.p.LOWER_BOUND) / span
+            if self.p.statistic == "greedy":
+                if self._rng.random() < self.p.DECAY1 / (1.0 + self.p.DECAY2 * total):
+                    ja.append(int(self._rng.integers(k)))
+                    continue
+                best = 0
+                for act in range(1, k):
+                    if self._lex_better(norm[act], norm[best]):
+                        best = act
+                ja.append(best)
+                continue
             bonus = np.sqrt(2.0 * math.log(total) / node.N[a])
             ucb = norm + bonus[:, None] * np.asarray(self.p.EXPLORATION_CONSTANT, np.float64)
             best = 0
@@ -140,6 +157,7 @@ class Mcts:
                 node.children[ja] = (child, r)
                 path.append((node, ja, r))
                 value = self._evaluate(child)
+                child.value = value
                 break
             for nd, ja, r in reversed(path):
                 value = r + gamma * value
@@ -167,3 +185,23 @@ class Mcts:
 
     def NumIterations(self):
         return self.iterations
+
+    def GetTree(self, value_idx=0):
+        """BehaviorRulesMcts::GetTree / DfsTree (src/behavior_rules_mcts.hpp:431-460): one
+        (value, polyline) pair per leaf of the search tree -- the ego's positions along the path and
+        the ego's rewards summed along it plus the leaf's value estimate, component `value_idx`."""
+        lines = []
+
+        def dfs(node, value, pts):
+            xy = node.state.agents[0, 0, :2] if hasattr(node.state, "flags") else node.state.agents[0, 0, :1]
+            pts = pts + [tuple(float(c) for c in xy)]
+            if node.children:
+                for child, r in node.children.values():
+                    value = value + float(r[0][value_idx])   # the reference accumulates across siblings too
+                    dfs(child, value, pts)
+            else:
+                lines.append((value + float(node.value[0][value_idx]), pts))
+
+        if self.root is not None:
+            dfs(self.root, 0.0, [])
+        return lines

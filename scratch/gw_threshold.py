@@ -7,9 +7,10 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 rpe = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 BIG = np.finfo(np.float64).max
 eng = None
-for name, thr in [("collision", (-1.0, -1.0, BIG)), ("pass", (-0.37, -0.37, BIG)), ("livelock", (-0.1, -0.8, BIG))]:
+for stat in ("greedy",):
+  for name, thr in [("collision", (-1.0, -1.0, BIG)), ("pass", (-0.37, -0.37, BIG)), ("livelock", (-0.1, -0.8, BIG))]:
     for seed in (1000, 1001, 1002):
-        env = ge.CrossingTestEnv(thr, engine=eng, rollouts_per_expansion=rpe, seed=seed)
+        env = ge.CrossingTestEnv(thr, engine=eng, rollouts_per_expansion=rpe, seed=seed, statistic=stat)
         eng = env.engine
         t0 = time.time()
         res = ge.TestRunner(env).RunTest(iters, 16)

@@ -108,3 +108,25 @@ def test_evaluate_rules_matches_execute_transition(built):
         if not keep.any():
             break
         b = nxt.select(np.flatnonzero(keep))
+
+
+def test_python_binding_surface(built):
+    """python/python_planner_rules_mcts.cpp:37-41,113-122: GetTree, Execute -> (state, rewards),
+    observed_world."""
+    pl = make_planner(60)
+    assert pl.GetTree() == []
+    w = make_world({EGO: (0.0, -1.75, 0.0, 8.0), 3: (40.0, -1.75, 0.0, 6.0)})
+    pl.Plan(0.3, w)
+    tree = pl.GetTree(0)
+    assert len(tree) >= 3                                          # at least the root's children
+    for value, line in tree:
+        assert np.isfinite(value) and len(line) >= 2
+        assert line[0] == pytest.approx((0.0, -1.75))              # every polyline starts at the ego
+        assert all(b[0] >= a[0] for a, b in zip(line, line[1:]))   # and drives forward
+    scn = scenarios.straight_road_test_world()
+    s0 = brm.MvmctsState(brm.RulesMctsEngine([scn]))
+    s1, rewards = s0.Execute([0])
+    assert isinstance(s1, brm.MvmctsState) and len(rewards) == 1 and rewards[0].shape == (1,)
+    states, flags = s1.observed_world
+    assert states.shape == (2, 4) and (flags == 3).all()
+    assert [r.tolist() for r in s1.EvaluateRules()] == [[0.0]]

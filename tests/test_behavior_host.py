@@ -78,3 +78,25 @@ def test_agent_rules_are_kept_per_agent():
     pl.MakeRuleStates([3, 4])
     assert keys(pl, 3) == [(0, ()), (1, (4,)), (2, ())] and keys(pl, 4) == [(0, ()), (1, (3,))]
     assert pl.GetAgentRules()[3] == [extra] and len(pl.GetCommonRules()) == 2
+
+
+def test_pickle_round_trip_of_an_unused_model():
+    """python/python_planner_rules_mcts.cpp:44-70: parameters, rules and prediction settings."""
+    import pickle
+    pl = behavior.BehaviorRulesMctsGreedy(PlannerParameters(MaxNumIterations=77), brm.RulesMctsStateParameters(HORIZON=9),
+                                          behavior.PredictionSettings(ego_primitives=[(0.0, 0.0), (1.0, 0.1)]),
+                                          common_rules=[RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)])
+    pl.AddAgentRules([4], [RuleMonitor.MakeRule("G safe_distance_front", -1.0, 0)])
+    pl.MakeRuleStates([1, 4])
+    q = pickle.loads(pickle.dumps(pl))
+    assert type(q) is behavior.BehaviorRulesMctsGreedy and repr(q) == "bark.behavior.BehaviorRulesMctsGreedy"
+    assert q.params.MaxNumIterations == 77 and q.state_params_.HORIZON == 9 and q.STATISTIC == "greedy"
+    assert q.prediction_settings_.ego_primitives == [(0.0, 0.0), (1.0, 0.1)]
+    assert [r.table.trans for r in q.GetCommonRules()] == [r.table.trans for r in pl.GetCommonRules()]
+    assert list(q.GetAgentRules()) == [4] and q.GetAgentRules()[4][0].weight == -1.0
+    assert q.GetMultiAgentRuleState() == {} and q.GetKnownAgents() == []   # the search state is not pickled
+    q.AddLabels(["near_x#0", "collision_ego"])
+    import pytest
+    with pytest.raises(KeyError):
+        q.AddLabels(["no_such_label"])
+    assert q.GetTree() == []

@@ -20,22 +20,25 @@ def engine(built):
     return ge.CrossingTestEnv((0.0, 0.0, BIG)).engine
 
 
-def run(engine, thres, tmp_path=None):
-    env = ge.CrossingTestEnv(thres, engine=engine, seed=1000)   # RandomGenerator seed of the suite's main()
+def run(engine, thres, tmp_path=None, statistic="uct"):
+    env = ge.CrossingTestEnv(thres, engine=engine, seed=1000, statistic=statistic)   # seed of the suite's main()
     runner = ge.TestRunner(env, q_val_fname=None if tmp_path is None else str(tmp_path / "q_val.dat"))
     res = runner.RunTest(3000, 16)                               # :28
     return np.array(env.state_history), res, env
 
 
-def test_collision(engine):
-    hist, res, _ = run(engine, (-1.0, -1.0, BIG))                # :41-42
+# the reference's suite is typed on both statistics (:36-37)
+@pytest.mark.parametrize("statistic", ["uct", "greedy"])
+def test_collision(engine, statistic):
+    hist, res, _ = run(engine, (-1.0, -1.0, BIG), statistic=statistic)   # :41-42
     assert hist[-1][0] == hist[-1][2]                            # collision of 0 and 2 (:45)
     assert hist[-1][1] > MERGING_POINT                           # 1 has passed the merging point (:47)
     assert res.collision
 
 
-def test_pass(engine, tmp_path):
-    hist, res, env = run(engine, (-0.37, -0.37, BIG), tmp_path)  # :51-52
+@pytest.mark.parametrize("statistic", ["uct", "greedy"])
+def test_pass(engine, tmp_path, statistic):
+    hist, res, env = run(engine, (-0.37, -0.37, BIG), tmp_path, statistic)  # :51-52
     last = hist[-1]
     assert last[0] > MERGING_POINT and last[1] > MERGING_POINT and last[2] > MERGING_POINT  # :55-57
     assert last[0] < last[2] < last[1]                           # order 1, 2, 0 (:59-60)
@@ -48,6 +51,8 @@ def test_pass(engine, tmp_path):
 
 
 def test_livelock(engine):
+    # (with the epsilon-greedy statistic two of three seeds end in the livelock; seed 1000 lets agent
+    # 2 through -- the reference's decay schedule is un-vendored, so only UCT is asserted here)
     hist, res, _ = run(engine, (-0.1, -0.8, BIG))                # :64-65
     last = hist[-1]
     assert last[0] < MERGING_POINT and last[1] > MERGING_POINT and last[2] < MERGING_POINT  # :68-70
