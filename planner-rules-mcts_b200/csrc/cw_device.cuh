@@ -492,7 +492,7 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
     if (rules_only || !(B.ego_only && a != 0)) {  // :104-108
       CwVec rr = {0.f, 0.f, 0.f, 0.f};
       for (int sl = 0; sl < B.R; ++sl) {
-        // one 16-byte record per slot: x = label kinds of the 4 APs (a byte each),
+        // one 16-byte record per slot: x = label-word bit read by each of the 4 APs (a byte each),
         // y = n_aps | priority << 8 | init << 16 | on_violation << 24,
         // z = rule | (rank + 1) << 8, w = weight
         const uint4 rec = B.slot_rec[sl];
@@ -507,12 +507,12 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
         const uint32_t W = w0 | (((merged_mask >> other) & 1u) << BRM_CW_LABEL_MERGED_X) |
                            (((front_mask >> other) & 1u) << BRM_CW_LABEL_IN_DIRECT_FRONT_X) |
                            (((near_mask >> other) & 1u) << BRM_CW_LABEL_NEAR_X);
+        // letter bit k = AP k (the blob's tables are stored in this order; unused APs read the
+        // always-zero bit 31)
         uint32_t letter = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < BRM_MAX_APS; ++k) {
-          const uint32_t bit = (W >> ((rec.x >> (8 * k)) & 0xffu)) & 1u;
-          if (k < n_aps) letter |= bit << (n_aps - 1 - k);
-        }
+        for (uint32_t k = 0; k < BRM_MAX_APS; ++k)
+          letter |= ((W >> ((rec.x >> (8 * k)) & 31u)) & 1u) << k;
         uint32_t nxt = B.rules[rec.z & 0xffu].trans[(cur << n_aps) + letter];
         if (nxt == BRM_VIOLATION) {
           viol[sl * col_stride] += 1;
@@ -520,7 +520,7 @@ __device__ __forceinline__ void cw_evaluate(const CwBlob& B, CwAgent& t, int a, 
           const uint32_t pr = (rec.y >> 8) & 0xffu;
           vec_add_at(rr, static_cast<int>(pr), __uint_as_float(rec.w));
         }
-        q[sl * col_stride] = static_cast<uint8_t>(nxt);
+        if (nxt != cur) q[sl * col_stride] = static_cast<uint8_t>(nxt);
       }
       r.c0 += rr.c0; r.c1 += rr.c1; r.c2 += rr.c2; r.c3 += rr.c3;
     }

@@ -146,14 +146,23 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
       BRM_REQUIRE(r.trans[t] == BRM_VIOLATION || r.trans[t] < r.n_states,
                   "brm_cw_configure: rule %d transition %d out of range", k, t);
     B->rules[k] = r;
+    // device order of the letter bits: AP k at bit k (the ABI's tables have AP 0 at the top bit)
+    for (int q = 0; q < r.n_states; ++q)
+      for (int l = 0; l < (1 << r.n_aps); ++l) {
+        int nl = 0;
+        for (int a = 0; a < r.n_aps; ++a) nl |= ((l >> (r.n_aps - 1 - a)) & 1) << a;
+        B->rules[k].trans[q * (1 << r.n_aps) + nl] = r.trans[q * (1 << r.n_aps) + l];
+      }
     const int reps = rule_specific(r) ? s.n_agents - 1 : 1;
     for (int j = 0; j < reps; ++j) {
       BRM_REQUIRE(R < BRM_CW_MAX_SLOTS, "brm_cw_configure: more than %d rule states per agent", BRM_CW_MAX_SLOTS);
       B->slot_rule[R] = static_cast<uint8_t>(k);
       B->slot_rank[R] = rule_specific(r) ? static_cast<int8_t>(j) : -1;
       uint4 rec;
+      // x: per AP the bit of the slot's label word it reads; unused APs read bit 31 (always 0)
       rec.x = 0;
-      for (int a = 0; a < r.n_aps; ++a) rec.x |= static_cast<uint32_t>(r.ap_label[a]) << (8 * a);
+      for (int a = 0; a < BRM_MAX_APS; ++a)
+        rec.x |= static_cast<uint32_t>(a < r.n_aps ? r.ap_label[a] : 31) << (8 * a);
       rec.y = static_cast<uint32_t>(r.n_aps) | (static_cast<uint32_t>(r.priority) << 8) |
               (static_cast<uint32_t>(r.init_state) << 16) | (static_cast<uint32_t>(r.on_violation ? 1 : 0) << 24);
       rec.z = static_cast<uint32_t>(k) | (static_cast<uint32_t>(rule_specific(r) ? j + 1 : 0) << 8);
