@@ -726,7 +726,6 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
     BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<true>, kThreads, smem));
   else
     BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<false>, kThreads, smem));
-  if (getenv("BRM_DEBUG")) fprintf(stderr, "[brm] cw_rollout: smem %zu B/CTA, %d CTAs/SM\n", smem, per_sm);
   int64_t grid = static_cast<int64_t>(e->sm_count) * (per_sm > 0 ? per_sm : 1);
   const int64_t total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
   BRM_REQUIRE(total + 4 * 32 < (1ll << 31), "brm_cw_rollout: %lld rollouts in one call (limit 2^31)",
@@ -752,8 +751,6 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
     if (grid > units) grid = units;
   }
   if (grid < 1) grid = 1;
-  if (const char* v = getenv("BRM_CW_CHUNK")) a.chunk = ctx.c.G * atoi(v);   // tuning experiments
-  if (const char* v = getenv("BRM_CW_PARTS")) a.parts = atoi(v);
   e->time_begin();
   if (passive)
     cw_rollout_kernel<true><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
