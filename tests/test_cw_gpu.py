@@ -271,6 +271,15 @@ def test_errors(built):
     other = scenarios.highway_scenario()
     with pytest.raises(brm.BrmError):
         brm.RulesMctsEngine([scn, other], device=0)  # shapes differ
+    # an empty batch is refused with an error, not a crash
+    empty = brm.CwBatch.zeros(eng.A, eng.M, eng.R, 0)
+    with pytest.raises(brm.BrmError, match="empty batch"):
+        eng.get_num_actions(empty)
+    with pytest.raises(brm.BrmError, match="empty batch"):
+        eng.rollout(empty, 4)
+    # more rollouts in one call than the 31-bit rollout index holds
+    with pytest.raises(brm.BrmError, match="rollouts in one call"):
+        eng.rollout(eng.initial_batch(), 2**31 - 1)
 
 
 def test_replay_matches_committed_golden_traces(built):

@@ -244,6 +244,18 @@ def test_errors(built):
         eng.rollout(leaves, 8, max_steps=1000)
     with pytest.raises(brm.BrmError):
         brm.GridWorldEngine(brm.GridWorldStateParameter(num_other_agents=20), device=0)
+    # an empty batch is refused with an error, not a crash
+    with pytest.raises(brm.BrmError, match="empty batch"):
+        eng.is_terminal(brm.GwBatch.zeros(eng.A, eng.R, 0))
+    # Execute must not be given the same arrays for input and output
+    import ctypes as C
+    from planner_rules_mcts_b200 import _abi
+    b = eng.base_test_env_batch(4)
+    s = b.to_abi()
+    rew = np.zeros((eng.A, eng.V, 4))
+    acts = np.zeros((eng.A, 4), np.uint8)
+    rc = eng.lib.brm_gw_execute(eng.engine.handle, C.byref(s), acts.ctypes.data, C.byref(s), rew.ctypes.data)
+    assert rc == _abi.ERR_INVALID and b"must not share" in eng.lib.brm_last_error()
 
 
 def test_coop_factor_mixes_agent_returns(built):
