@@ -38,6 +38,9 @@ L2_FLUSH_BYTES = 256 << 20
 WORKLOADS = {
     "M": dict(name="multi_agent_merge", leaves=256, rollouts_per_leaf=1024, max_steps=20, agents=4,
               desc="multi-agent merge: 4 agents, zipper + safe-distance rules, 262144 rollouts/decision, horizon 20"),
+    "R": dict(name="root_parallel_merge", leaves=128, rollouts_per_leaf=1024, max_steps=20, agents=4,
+              desc="root-parallel MCTS: the merge scenario with 131072 rollouts/decision per GPU (1M on 8 GPUs), "
+                   "per-GPU root statistics merged by one NCCL allreduce"),
     "S": dict(name="single_agent_highway", leaves=64, rollouts_per_leaf=1024, max_steps=20, agents=4,
               desc="single-agent highway lane change, safe-distance rule, 65536 rollouts/decision, horizon 20"),
     "G": dict(name="gridworld_threshold_test", leaves=256, rollouts_per_leaf=1024, max_steps=30, agents=3,
@@ -125,7 +128,7 @@ def build_workload(kind, device, rank, cuda_stream=None):
         w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
                  gamma=0.9, dtype="f32", state_bytes=16, scn=scns)
         return w
-    scn = scenarios.merge_scenario(seed=1000) if kind == "M" else scenarios.highway_scenario(seed=1000)
+    scn = scenarios.merge_scenario(seed=1000) if kind in ("M", "R") else scenarios.highway_scenario(seed=1000)
     eng = brm.RulesMctsEngine([scn], device=device, cuda_stream=cuda_stream)
     n_act = len(scn.agents[0].primitives)
     # leaves = children of the root under random first joint actions (tree kept on the host)
@@ -242,7 +245,7 @@ def reference_workload(kind):
         w.update(engine=_E, leaves=lv, A=3, gamma=0.95, ref_rollouts_per_step=200000)
         return w
     from planner_rules_mcts_b200 import scenarios
-    scn = {"M": scenarios.merge_scenario, "S": scenarios.highway_scenario,
+    scn = {"M": scenarios.merge_scenario, "R": scenarios.merge_scenario, "S": scenarios.highway_scenario,
            "W": scenarios.intersection_scenario}[kind](seed=1000)
     A = len(scn.agents)
     lv = _HostLeaves()
@@ -260,7 +263,7 @@ def reference_workload(kind):
         s += reps
     lv.q = q
     w.update(leaves=lv, scn=[scn], A=A, gamma=scn.params.DISCOUNT_FACTOR,
-             ref_rollouts_per_step={"M": 60000, "S": 100000, "W": 20000}[kind])
+             ref_rollouts_per_step={"M": 60000, "R": 60000, "S": 100000, "W": 20000}[kind])
     return w
 
 
@@ -269,7 +272,15 @@ def load_inst_counts(kind):
     path = os.path.join(ROOT, "profiles", "inst_counts.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get(kind)
+            d = json.load(open(path))
+            if kind != "R":
+                return d.get(kind)
+            # R runs M's kernel on M's scenario: per-agent-step counts carry over, per-launch traffic does not
+            m = dict(d.get("M") or {})
+            if m:
+                m["dram_bytes_per_launch"] = None
+                m["source"] = "workload M's capture (same kernel and scenario): " + m.get("source", "")
+            return m or None
         except (ValueError, OSError):
             return None
     return None
