@@ -41,6 +41,13 @@ struct alignas(16) GwBlob {
   double w_speed, w_acc;
   uint8_t slot_rule[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
   int8_t slot_other[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
+  // per rule slot, for the automaton step: the bit of the agent's label word each of the 4 APs
+  // reads (a byte each; 31 = always zero), and rule | n_aps << 8 | priority << 16 |
+  // init_state << 24 | on_violation << 31.  Label word: bit 0 collision, 1 merged_e,
+  // 2 + j merged_x#j, 10 + j in_direct_front_x#j.  `rules[k].trans` is stored with AP k of the
+  // letter at bit k (the ABI has AP 0 at the top bit).
+  uint32_t slot_bits[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
+  uint32_t slot_meta[BRM_GW_MAX_AGENTS][BRM_GW_MAX_SLOTS];
   brm_rule rules[BRM_MAX_RULES];
   uint8_t _tail[16 - (sizeof(brm_rule) * BRM_MAX_RULES) % 16];
 };

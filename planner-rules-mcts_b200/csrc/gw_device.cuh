@@ -126,32 +126,26 @@ __device__ __forceinline__ void gw_step(const GwBlob& B, GwRegs<A>& s, const uin
       continue;
     }
     // automata transit (:76-79)
+    // label word of this agent: the slot records say which bit each AP reads (common.cuh)
+    const uint32_t word = lab.ego | (lab.merged << 2) | (lab.front << 10);
     for (int sl = 0; sl < B.R; ++sl) {
-      const brm_rule& rule = B.rules[B.slot_rule[i][sl]];
-      const int other = B.slot_other[i][sl];
-      const int n_aps = rule.n_aps;
+      const uint32_t bits = B.slot_bits[i][sl], meta = B.slot_meta[i][sl];
+      const uint32_t n_aps = (meta >> 8) & 0xffu;
       uint32_t letter = 0;
-      for (int k = 0; k < n_aps; ++k) {
-        const uint32_t kind = rule.ap_label[k];
-        uint32_t val;
-        if (kind == BRM_GW_LABEL_COLLISION) val = lab.ego & 1u;
-        else if (kind == BRM_GW_LABEL_MERGED_E) val = (lab.ego >> 1) & 1u;
-        else if (kind == BRM_GW_LABEL_MERGED_X) val = (lab.merged >> other) & 1u;
-        else val = (lab.front >> other) & 1u;
-        letter |= val << (n_aps - 1 - k);
-      }
+#pragma unroll
+      for (uint32_t k = 0; k < BRM_MAX_APS; ++k) letter |= ((word >> ((bits >> (8 * k)) & 31u)) & 1u) << k;
       const uint32_t cur = static_cast<uint32_t>(s.q[i] >> (4 * sl)) & 15u;
-      uint32_t nxt = rule.trans[(cur << n_aps) + letter];
+      uint32_t nxt = B.rules[meta & 0xffu].trans[(cur << n_aps) + letter];
       if (nxt == BRM_VIOLATION) {
         on_violation(i, sl);
-        nxt = rule.on_violation ? cur : rule.init_state;
-        const int pr = rule.priority;
-        const double w = static_cast<double>(rule.weight);
+        nxt = (meta >> 31) ? cur : ((meta >> 24) & 0x7fu);
+        const int pr = static_cast<int>((meta >> 16) & 0xffu);
+        const double w = static_cast<double>(B.rules[meta & 0xffu].weight);
 #pragma unroll
         for (int v = 0; v < BRM_MAX_REWARD; ++v)
           if (v == pr) r[v] = __dadd_rn(r[v], w);
       }
-      s.q[i] = (s.q[i] & ~(15ull << (4 * sl))) | (static_cast<uint64_t>(nxt) << (4 * sl));
+      if (nxt != cur) s.q[i] = (s.q[i] & ~(15ull << (4 * sl))) | (static_cast<uint64_t>(nxt) << (4 * sl));
     }
     // GetActionCost (:120-132); explicit _rn ops: no FMA contraction, so the double
     // result is bit-identical to the reference's separate multiply and add.

@@ -118,6 +118,13 @@ int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rule
       BRM_REQUIRE(r.trans[s] == BRM_VIOLATION || r.trans[s] < r.n_states,
                   "brm_gw_configure: rule %d transition %d out of range", k, s);
     B.rules[k] = r;
+    // device order of the letter bits: AP a at bit a
+    for (int q = 0; q < r.n_states; ++q)
+      for (int l = 0; l < (1 << r.n_aps); ++l) {
+        int nl = 0;
+        for (int a = 0; a < r.n_aps; ++a) nl |= ((l >> (r.n_aps - 1 - a)) & 1) << a;
+        B.rules[k].trans[q * (1 << r.n_aps) + nl] = r.trans[q * (1 << r.n_aps) + l];
+      }
   }
   // rule-slot layout per agent (BaseTestEnv::GetAutomataVec, gridworld/base_test_env.cpp:122-140)
   int R = 0;
@@ -144,6 +151,24 @@ int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rule
       }
     }
     R = n;
+    for (int sl = 0; sl < n; ++sl) {
+      const brm_rule& r = rules[B.slot_rule[i][sl]];
+      const int other = B.slot_other[i][sl];
+      uint32_t bits = 0;
+      for (int a = 0; a < BRM_MAX_APS; ++a) {
+        uint32_t pos = 31;
+        if (a < r.n_aps) {
+          const int kind = r.ap_label[a];
+          pos = kind == BRM_GW_LABEL_COLLISION ? 0 : kind == BRM_GW_LABEL_MERGED_E ? 1
+              : kind == BRM_GW_LABEL_MERGED_X ? 2 + other : 10 + other;
+        }
+        bits |= pos << (8 * a);
+      }
+      B.slot_bits[i][sl] = bits;
+      B.slot_meta[i][sl] = static_cast<uint32_t>(B.slot_rule[i][sl]) | (static_cast<uint32_t>(r.n_aps) << 8) |
+                           (static_cast<uint32_t>(r.priority) << 16) |
+                           (static_cast<uint32_t>(r.init_state) << 24) | (r.on_violation ? 1u << 31 : 0u);
+    }
   }
   B.R = R;
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
