@@ -285,13 +285,8 @@ __device__ __forceinline__ bool cw_out_of_map(const CwBlob& B, const CwAgent& t,
   uint32_t inside = 0;
   bool vertex_in = false;
   const float f = B.front[a], r = B.rear[a], h = B.hw[a];
-  const float ylo = fminf(fminf(cy[0], cy[1]), fminf(cy[2], cy[3]));
-  const float yhi = fmaxf(fmaxf(cy[0], cy[1]), fmaxf(cy[2], cy[3]));
   for (int e = 0; e < B.n_road; ++e) {
     const float4 g = B.road_edge[e];
-    // an edge whose y range misses the rectangle's: no corner ray crosses it (both
-    // comparisons below agree for every corner) and its start vertex is outside
-    if (fminf(g.x, g.y) > yhi || fmaxf(g.x, g.y) < ylo) continue;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool cross = ((g.x > cy[k]) != (g.y > cy[k])) && (cx[k] < g.w * (cy[k] - g.x) + g.z);
