@@ -61,6 +61,14 @@ struct alignas(16) CwBlob {
   // blocks of all lanes in lane order (n_blk <= 64, one bit each in the candidate mask):
   // blk_gbox = bounding box grown by the lane's half width, blk_box = tight box,
   // blk_info = lane | first segment (within the lane) << 8 | segment count << 16
+  // an 8 x 8 grid over the union of the grown boxes: per cell the blocks whose grown box reaches
+  // into it (a superset; the blocks named there are then tested exactly)
+  // (`use_grid`, decided at upload: used when the longest list of a cell is at most a quarter of
+  // the blocks; where many lanes cross, testing all boxes in a uniform loop is cheaper than a
+  // divergent walk over the cell's list -- the rollout kernel has an instance for either)
+  float grid_x0, grid_y0, grid_ix, grid_iy;  // origin and 1 / cell size
+  int32_t use_grid, _p6, _p7, _p8;
+  unsigned long long cell_mask[64];
   float4 blk_gbox[kCwMaxBlkTotal];
   float4 blk_box[kCwMaxBlkTotal];
   uint32_t blk_info[kCwMaxBlkTotal];
@@ -78,6 +86,7 @@ struct CwCommon {
   int32_t blob_cap;           // bytes reserved for the blob in shared memory
   int32_t A, M, V, R, G;      // G = rollouts (states) per warp = 32 / M
   int32_t Ps;                 // passive-agent slots per lane
+  int32_t use_grid;           // every scenario's lane projection takes its candidates from the grid
 };
 struct CwLaunchCtx {
   CwCommon c;
@@ -176,15 +185,29 @@ __device__ __forceinline__ void cw_integrate(const CwBlob& B, CwAgent& t, int a,
 //   * a candidate block whose tight box is farther than the best distance found so far on
 //     its lane cannot hold the nearest segment.
 // A lane none of whose blocks survives is a lane the point is not on.
+template <bool GRID = false>
 __device__ __forceinline__ void cw_frenet(const CwBlob& B, CwAgent& t) {
   t.lane = -1;
   t.s = 0.f;
   t.lat = 0.f;
-  // candidate mask, built in two 32-bit halves (scenarios rarely have more than 32 blocks)
-  const int nb = B.n_blk;
-  uint32_t lo = 0u, hi = 0u;
-  {
-    uint32_t bit = 1u;
+  // candidate mask: the grid cell of the point names the blocks that can contain it, those are
+  // tested exactly (a point outside the grid is outside every grown box)
+  unsigned long long mask = 0ull;
+  if (GRID) {
+    const float fx = (t.x - B.grid_x0) * B.grid_ix, fy = (t.y - B.grid_y0) * B.grid_iy;
+    unsigned long long cand = 0ull;
+    if (fx >= 0.f && fx < 8.f && fy >= 0.f && fy < 8.f)
+      cand = B.cell_mask[static_cast<int>(fy) * 8 + static_cast<int>(fx)];
+    while (cand) {
+      const int i = __ffsll(static_cast<long long>(cand)) - 1;
+      cand &= cand - 1ull;
+      const float4 g = B.blk_gbox[i];
+      if (t.x >= g.x && t.x <= g.z && t.y >= g.y && t.y <= g.w) mask |= 1ull << i;
+    }
+  } else {
+    // all boxes, in two 32-bit halves (scenarios rarely have more than 32 blocks)
+    const int nb = B.n_blk;
+    uint32_t lo = 0u, hi = 0u, bit = 1u;
     const int n0 = nb < 32 ? nb : 32;
     for (int i = 0; i < n0; ++i, bit <<= 1) {
       const float4 g = B.blk_gbox[i];
@@ -195,8 +218,8 @@ __device__ __forceinline__ void cw_frenet(const CwBlob& B, CwAgent& t) {
       const float4 g = B.blk_gbox[i];
       if (t.x >= g.x && t.x <= g.z && t.y >= g.y && t.y <= g.w) hi |= bit;
     }
+    mask = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
   }
-  unsigned long long mask = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
   const float kInf = __int_as_float(0x7f800000);
   int l = -1, n_seg = 0, seg_off = 0, bk = 0;
   float best = kInf, btu = 0.f, hw2 = 0.f;

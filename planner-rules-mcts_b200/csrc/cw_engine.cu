@@ -242,6 +242,42 @@ int build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out) {
     }
   }
   B->n_blk = n_blk;
+  // grid over the union of the grown boxes (a little larger, so that a point on or beyond its
+  // border is outside every box); a cell lists the blocks whose grown box overlaps the cell
+  // widened by a margin that covers the fp32 evaluation of the cell index on the device
+  {
+    double gx0 = 1e300, gy0 = 1e300, gx1 = -1e300, gy1 = -1e300;
+    for (int i = 0; i < n_blk; ++i) {
+      gx0 = std::min(gx0, static_cast<double>(B->blk_gbox[i].x));
+      gy0 = std::min(gy0, static_cast<double>(B->blk_gbox[i].y));
+      gx1 = std::max(gx1, static_cast<double>(B->blk_gbox[i].z));
+      gy1 = std::max(gy1, static_cast<double>(B->blk_gbox[i].w));
+    }
+    if (n_blk == 0) gx0 = gy0 = 0.0, gx1 = gy1 = 1.0;
+    gx0 -= 0.01; gy0 -= 0.01; gx1 += 0.01; gy1 += 0.01;
+    const double cw = (gx1 - gx0) / 8.0, ch = (gy1 - gy0) / 8.0;
+    B->grid_x0 = static_cast<float>(gx0);
+    B->grid_y0 = static_cast<float>(gy0);
+    B->grid_ix = static_cast<float>(1.0 / cw);
+    B->grid_iy = static_cast<float>(1.0 / ch);
+    // the device's cell of a coordinate: floor((x - fl(gx0)) * fl(1/cw)) in fp32; its error is far
+    // below one percent of a cell
+    const double ox = B->grid_x0, oy = B->grid_y0, sx = 1.0 / B->grid_ix, sy = 1.0 / B->grid_iy;
+    int most = 0;
+    for (int cy = 0; cy < 8; ++cy)
+      for (int cx = 0; cx < 8; ++cx) {
+        const double x0 = ox + (cx - 0.01) * sx, x1 = ox + (cx + 1.01) * sx;
+        const double y0 = oy + (cy - 0.01) * sy, y1 = oy + (cy + 1.01) * sy;
+        unsigned long long m = 0ull;
+        for (int i = 0; i < n_blk; ++i) {
+          const float4 g = B->blk_gbox[i];
+          if (g.x <= x1 && g.z >= x0 && g.y <= y1 && g.w >= y0) m |= 1ull << i;
+        }
+        B->cell_mask[cy * 8 + cx] = m;
+        most = std::max(most, __builtin_popcountll(m));
+      }
+    B->use_grid = (n_blk > 0 && 4 * most <= n_blk) ? 1 : 0;
+  }
   B->total_bytes = static_cast<int32_t>(offsetof(CwBlob, segs) + static_cast<size_t>(off) * sizeof(CwSeg));
   return BRM_OK;
 }
@@ -340,7 +376,7 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   std::vector<CwBlob>* blobs = new std::vector<CwBlob>(n_scenarios);
   std::vector<int32_t> bytes(n_scenarios);
-  int A = 0, M = 0, V = 0, R = 0, cap = 0;
+  int A = 0, M = 0, V = 0, R = 0, cap = 0, use_grid = 1;
   for (int i = 0; i < n_scenarios; ++i) {
     int Ri = 0;
     int rc = build_blob(scenarios[i], &(*blobs)[i], &Ri);
@@ -359,6 +395,7 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
     }
     bytes[i] = (B.total_bytes + 15) & ~15;
     if (bytes[i] > cap) cap = bytes[i];
+    use_grid &= B.use_grid;
   }
   brm_cw_release(e);
   CwEngine* c = new CwEngine();
@@ -390,6 +427,7 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
   c->ctx.c.R = R;
   c->ctx.c.G = 32 / M;  // one lane per MCTS agent
   c->ctx.c.Ps = (A - M + M - 1) / M;
+  c->ctx.c.use_grid = use_grid;
   c->ctx.smem_bytes = static_cast<size_t>(cap) + 2u * static_cast<size_t>(R) * kThreads +
                       static_cast<size_t>(c->ctx.c.Ps) * kCwPasWords * sizeof(float) * kThreads;
   e->cw = c;

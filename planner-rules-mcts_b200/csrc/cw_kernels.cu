@@ -137,6 +137,7 @@ __device__ __forceinline__ void cw_load_rules(const brm_cw_states& S, const CwCo
 
 // Predict for my passive agents: they follow primitive 0 of their own table
 // (BehaviorConstantAcceleration in the reference's prediction settings)
+template <bool GRID = false>
 __device__ __forceinline__ uint32_t cw_move_passive(const CwBlob& B, const CwCommon& c, const CwMap& m,
                                                     const CwSmem& sm, bool live) {
   uint32_t moved = 0;
@@ -147,7 +148,7 @@ __device__ __forceinline__ uint32_t cw_move_passive(const CwBlob& B, const CwCom
     cw_pas_load(sm.pas, slot, p);
     if ((p.flags & BRM_CW_PRESENT) && (p.flags & BRM_CW_VALID)) {
       cw_integrate(B, p, j, 0u);
-      cw_frenet(B, p);
+      cw_frenet<GRID>(B, p);
       cw_pas_store(sm.pas, slot, p);
       ++moved;
     }
@@ -224,7 +225,7 @@ __device__ __forceinline__ void cw_acc_flush(const CwRolloutArgs& args, CwLaneAc
 // next rollout id of the warp's current range at once, and an empty range is replaced by
 // `fetch(lo, hi)` (warp-uniform; a range [lo, hi) of flat rollout ids inside ONE leaf, or
 // lo >= hi when the work is exhausted).  Lanes therefore only idle at the very end.
-template <bool PASSIVE, class Fetch>
+template <bool PASSIVE, bool GRID, class Fetch>
 __device__ __forceinline__ void cw_run_warp(const CwRolloutArgs& args, const CwBlob& B, const CwSmem& sm,
                                             uint32_t* viol_tot, CwPose* pose_w, CwLaneAcc& lacc, Fetch fetch) {
   const CwCommon& c = args.c;
@@ -267,7 +268,7 @@ __device__ __forceinline__ void cw_run_warp(const CwRolloutArgs& args, const CwB
           leaf = lf;
           CwAgent t0;
           cw_load_agent(args.leaves, leaf, lane < A ? lane : 0, lane < A, t0);
-          if (t0.flags & BRM_CW_PRESENT) cw_frenet(B, t0);
+          if (t0.flags & BRM_CW_PRESENT) cw_frenet<GRID>(B, t0);
           __syncwarp();
           if (lane < A) {
             CwPose p;
@@ -324,10 +325,10 @@ __device__ __forceinline__ void cw_run_warp(const CwRolloutArgs& args, const CwB
     const uint32_t in_flags = t.flags;
     if (live && movable) {
       cw_integrate(B, t, a, act);
-      cw_frenet(B, t);
+      cw_frenet<GRID>(B, t);
       ++steps;
     }
-    if (PASSIVE) steps += cw_move_passive(B, c, m, sm, live);
+    if (PASSIVE) steps += cw_move_passive<GRID>(B, c, m, sm, live);
     CwStepOut o;
     cw_evaluate<false, PASSIVE>(B, t, a, base, real, live, in_v, in_th, in_flags, horizon - 1, sm.q, sm.viol,
                                 kThreads, sm.pas, o);
@@ -386,7 +387,7 @@ __device__ __forceinline__ void cw_run_warp(const CwRolloutArgs& args, const CwB
   __syncwarp();
 }
 
-template <bool PASSIVE>
+template <bool PASSIVE, bool GRID>
 __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kernel(const CwRolloutArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
       hi = min(c_hi, (c_lo / n + 1) * n);
       c_lo = hi;
     };
-    cw_run_warp<PASSIVE>(args, B, sm, viol_tot, pose_w, lacc, fetch);
+    cw_run_warp<PASSIVE, GRID>(args, B, sm, viol_tot, pose_w, lacc, fetch);
   } else {
     // several scenarios: the blob is CTA-wide, so a CTA works on one leaf at a time.  Units
     // (a leaf's rollouts, or one of `parts` slices of them) are claimed from a global counter;
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, kCwRolloutCtasPerSm) cw_rollout_kern
         lo = leaf * n + b;
         hi = leaf * n + e;
       };
-      cw_run_warp<PASSIVE>(args, B, sm, viol_tot, pose_w, lacc, fetch);
+      cw_run_warp<PASSIVE, GRID>(args, B, sm, viol_tot, pose_w, lacc, fetch);
     }
   }
   cw_acc_flush(args, lacc, viol_tot, a);
@@ -688,8 +689,10 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
                       const brm_rollout_params& rp, const brm_cw_rollout_out& out) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(cw_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(cw_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(cw_rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   const int M = ctx.c.M, V = ctx.c.V, R = ctx.c.R;
@@ -720,12 +723,12 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   // the CTAs claim their work from a counter
   const size_t smem = cw_rollout_smem_bytes(ctx);
   int per_sm = 0;
-  // agents outside the MCTS list (kept in shared-memory slots) or not: two instances of the kernel
+  // instances of the kernel: agents outside the MCTS list (kept in shared-memory slots) or not,
+  // candidate blocks of the lane projection from the grid or from a pass over all boxes
   const bool passive = ctx.c.Ps > 0;
-  if (passive)
-    BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<true>, kThreads, smem));
-  else
-    BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_rollout_kernel<false>, kThreads, smem));
+  auto kernel = passive ? (ctx.c.use_grid ? cw_rollout_kernel<true, true> : cw_rollout_kernel<true, false>)
+                        : (ctx.c.use_grid ? cw_rollout_kernel<false, true> : cw_rollout_kernel<false, false>);
+  BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
   int64_t grid = static_cast<int64_t>(e->sm_count) * (per_sm > 0 ? per_sm : 1);
   const int64_t total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
   BRM_REQUIRE(total + 4 * 32 < (1ll << 31), "brm_cw_rollout: %lld rollouts in one call (limit 2^31)",
@@ -752,10 +755,7 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   }
   if (grid < 1) grid = 1;
   e->time_begin();
-  if (passive)
-    cw_rollout_kernel<true><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
-  else
-    cw_rollout_kernel<false><<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
+  kernel<<<static_cast<int>(grid), kThreads, smem, e->stream>>>(a);
   e->launches++;
   cw_finalize_returns_kernel<<<static_cast<int>((fx_count + 255) / 256), 256, 0, e->stream>>>(
       a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count), M, V, rp.coop_factor);
