@@ -1,9 +1,11 @@
 // Continuous-world kernels (sm_100a):
 //   K3 cw_rollout_kernel   fused random rollouts (mvmcts::RandomHeuristic over
 //                          MvmctsState::Execute): lane = MCTS agent, floor(32/M) rollouts in
-//                          flight per warp, finished rollouts are replaced at once; agents
-//                          that are only simulated live in shared-memory slots of the lanes
+//                          flight per warp, finished rollouts are replaced at once from
+//                          work the warps / CTAs claim at run time; agents that are only
+//                          simulated live in shared-memory slots of the lanes
 //   K4 cw_batch_kernel<EXECUTE>  one Execute for n states
+//      cw_batch_kernel<RULES>    MvmctsState::EvaluateRules() for n states
 //   K6 cw_batch_kernel<REPLAY>   replay of given action sequences with a full trace
 //      cw_batch_kernel<QUERY>    CheckTerminal / GetNumActions / GetTerminalReward
 // Every CTA stages the scenario blob it works on into shared memory with a TMA bulk copy
