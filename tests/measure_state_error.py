@@ -1,6 +1,8 @@
+"""Measurement behind DESIGN.md's error figures: largest position / reward difference between
+the CUDA replay and the FP64 oracle on random action sequences (run on a GPU box)."""
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import planner_rules_mcts_b200 as brm
 from planner_rules_mcts_b200 import scenarios
 from oracle import cw as ocw

@@ -1,6 +1,8 @@
+"""Measurement behind DESIGN.md's lane statistics: rollout lengths and the share of lane-steps that
+belong to agents that still move, per workload (run on a GPU box)."""
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 for kind in ("M", "W"):
     w = bench.build_workload(kind, 0, 0, None)
