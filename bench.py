@@ -389,13 +389,13 @@ def run_gpu(args):
                  agent_steps=pin(np.zeros(n_leaves, np.uint64)))
     h_stats = pin(np.zeros((M, w["n_actions"], 1 + V), np.float64))
     h2d = sum(getattr(host_leaves, f).nbytes for f in fields if getattr(host_leaves, f) is not None)
-    h2d += h_first.nbytes + h_out["returns_sum"].nbytes + h_stats.nbytes  # root_stats_reduce inputs
+    h2d += h_first.nbytes + h_stats.nbytes  # first actions and the statistics accumulated into
     d2h = sum(v.nbytes for v in h_out.values()) + h_stats.nbytes
 
     def e2e_step(step_idx):
         h_stats[:] = 0
-        eng.rollout(host_leaves, n, out=h_out, **rollout_kwargs(step_idx))
-        eng.root_stats_reduce(h_first, h_out["returns_sum"], n, h_stats, n_actions=w["n_actions"])
+        # one C-ABI call per decision: rollouts + root statistics, one upload / download / synchronisation
+        eng.rollout(host_leaves, n, out=h_out, first_action=h_first, stats=h_stats, **rollout_kwargs(step_idx))
         if world > 1:
             t = torch.from_numpy(h_stats).to(dev)
             dist.all_reduce(t)
@@ -482,8 +482,9 @@ def run_gpu(args):
                     clocks=clocks,
                     e2e=dict(value=e2e_steps_all / e2e_sec_max, unit=UNIT, h2d_bytes_per_step=int(h2d),
                              d2h_bytes_per_step=int(d2h), steps=e2e_steps_n,
-                             note="planner_rules_mcts_b200 engine.rollout + root_stats_reduce on pinned host "
-                                  "buffers; H2D, kernels, D2H and the host wall clock all inside"),
+                             note="planner_rules_mcts_b200 engine.rollout with root statistics (one "
+                                  "brm_*_rollout_root_stats call per decision) on pinned host buffers; H2D, "
+                                  "kernels, D2H and the host wall clock all inside"),
                     gpu_launches=int(launches_all), roofline=roof, wall_s=t_wall)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(kind, w)

@@ -424,6 +424,19 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
                           const uint8_t* leaf_first_action, const double* returns_sum,
                           int32_t rollouts_per_leaf, double* stats);
 
+/* One decision of a root-parallel search in ONE call: brm_*_rollout followed by
+ * brm_root_stats_reduce on the device, before anything is copied back (host batches: one upload,
+ * three launches, one download, one synchronisation).  out->returns_sum may be NULL for host
+ * batches when only the statistics are wanted.  stats is ACCUMULATED into, like
+ * brm_root_stats_reduce; leaf_first_action [n][A] uint8 (A = MCTS agents). */
+int brm_gw_rollout_root_stats(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                              const brm_gw_rollout_out* out, const uint8_t* leaf_first_action,
+                              int32_t n_actions, double* stats);
+int brm_cw_rollout_root_stats(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
+                              const brm_cw_rollout_out* out, const uint8_t* leaf_first_action,
+                              int32_t n_actions, double* stats);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,7 +135,7 @@ class CwTrace(C.Structure):
 # every symbol include/brm.h declares (tests/test_abi.py checks the library exports them)
 SYMBOLS = [
     "brm_cw_configure", "brm_cw_rules_per_agent", "brm_cw_check_terminal", "brm_cw_execute",
-    "brm_cw_evaluate_rules",
+    "brm_cw_evaluate_rules", "brm_cw_rollout_root_stats", "brm_gw_rollout_root_stats",
     "brm_cw_get_num_actions", "brm_cw_terminal_reward", "brm_cw_rollout", "brm_cw_replay",
     "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_synchronize",
     "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
@@ -186,6 +186,8 @@ def load():
     lib.brm_cw_get_num_actions.argtypes = [vp, P(CwStates), vp]
     lib.brm_cw_terminal_reward.argtypes = [vp, P(CwStates), vp]
     lib.brm_cw_rollout.argtypes = [vp, P(CwStates), P(RolloutParams), P(CwRolloutOut)]
+    lib.brm_cw_rollout_root_stats.argtypes = [vp, P(CwStates), P(RolloutParams), P(CwRolloutOut), vp, i32, vp]
+    lib.brm_gw_rollout_root_stats.argtypes = [vp, P(GwStates), P(RolloutParams), P(GwRolloutOut), vp, i32, vp]
     lib.brm_cw_replay.argtypes = [vp, P(CwStates), vp, i32, P(CwTrace)]
     _lib = lib
     return lib

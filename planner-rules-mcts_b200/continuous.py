@@ -345,7 +345,11 @@ class RulesMctsEngine:
 
     # -- rollouts -----------------------------------------------------------------------
     def rollout(self, leaves, rollouts_per_leaf, seed=1000, rollout_base=0, max_steps=30,
-                discount_factor=None, first_discount_exp=1, detail=False, out=None, coop_factor=0.0):
+                discount_factor=None, first_discount_exp=1, detail=False, out=None, coop_factor=0.0,
+                first_action=None, stats=None):
+        """Random rollouts from every leaf.  With `first_action` [L][M] and `stats`
+        [M][n_actions][1+V] the per-leaf sums are also folded into the root statistics in the same
+        call (brm_cw_rollout_root_stats)."""
         gamma = self.scenarios[0].params.DISCOUNT_FACTOR if discount_factor is None else discount_factor
         rp = _abi.RolloutParams(seed, rollout_base, rollouts_per_leaf, max_steps, gamma, first_discount_exp, 0,
                                 coop_factor)
@@ -364,7 +368,11 @@ class RulesMctsEngine:
         for k, _ in _abi.CwRolloutOut._fields_:
             setattr(o, k, _ptr(out.get(k)))
         s = leaves.to_abi()
-        _abi.check(self.lib.brm_cw_rollout(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o)))
+        if stats is not None:
+            _abi.check(self.lib.brm_cw_rollout_root_stats(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o),
+                                                          _ptr(first_action), int(stats.shape[1]), _ptr(stats)))
+        else:
+            _abi.check(self.lib.brm_cw_rollout(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o)))
         return out
 
     # -- replay ---------------------------------------------------------------------------

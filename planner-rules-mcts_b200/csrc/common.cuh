@@ -60,6 +60,12 @@ struct EventPair {
 }  // namespace brm
 
 struct CwScenario;  // cw_kernels.cu
+struct brm_engine;
+namespace brm {
+int launch_root_stats(brm_engine* e, int32_t n_leaves, int32_t n_agents, int32_t n_actions, int32_t V,
+                      const uint8_t* d_first_action, const double* d_returns_sum, int32_t rollouts_per_leaf,
+                      double* d_stats);
+}
 
 struct brm_engine {
   int device = 0;

@@ -550,18 +550,27 @@ int brm_cw_terminal_reward(brm_engine* e, const brm_cw_states* s, float* out) {
   return cw_query(e, s, nullptr, out, "brm_cw_terminal_reward");
 }
 
-int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
-                   const brm_cw_rollout_out* out) {
+// rollouts, optionally followed by the root statistics (first_action != NULL) in the same call
+static int cw_rollout_impl(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
+                           const brm_cw_rollout_out* out, const uint8_t* first_action, int32_t n_actions,
+                           double* stats) {
   BRM_TRY(check_ready(e, "brm_cw_rollout"));
   BRM_TRY(check_states(e, leaves, "brm_cw_rollout", false));
-  BRM_REQUIRE(rp && out && out->returns_sum, "brm_cw_rollout: rp/out/returns_sum is required");
+  BRM_REQUIRE(rp && out && (out->returns_sum || first_action), "brm_cw_rollout: rp/out/returns_sum is required");
   BRM_REQUIRE(rp->rollouts_per_leaf >= 1, "brm_cw_rollout: rollouts_per_leaf must be >= 1");
   BRM_REQUIRE(rp->max_steps >= 0 && rp->max_steps <= 255, "brm_cw_rollout: max_steps %d not in [0,255]",
               rp->max_steps);
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   CwEngine* c = cw_of(e);
   const int A = c->ctx.c.A, M = c->ctx.c.M, R = c->ctx.c.R, V = c->ctx.c.V;
-  if (leaves->mem == BRM_MEM_DEVICE) return cw_launch_rollout(e, c->ctx, c->n_scenarios, *leaves, *rp, *out);
+  if (leaves->mem == BRM_MEM_DEVICE) {
+    BRM_REQUIRE(out->returns_sum, "brm_cw_rollout: device batches need a returns_sum buffer");
+    BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, *leaves, *rp, *out));
+    if (first_action)
+      BRM_TRY(brm::launch_root_stats(e, leaves->n, M, n_actions, V, first_action, out->returns_sum,
+                                     rp->rollouts_per_leaf, stats));
+    return BRM_OK;
+  }
   const size_t L = leaves->n, N = L * static_cast<size_t>(rp->rollouts_per_leaf);
   Stager st(e);
   brm_cw_states d;
@@ -577,7 +586,16 @@ int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout
   if (out->ro_flags) BRM_TRY(st.alloc(N * A, &o.ro_flags));
   if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
   BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, d, *rp, o));
-  BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * M * V));
+  if (first_action) {
+    uint8_t* d_fa;
+    double* d_st;
+    const size_t st_count = static_cast<size_t>(M) * n_actions * (1 + V);
+    BRM_TRY(st.in(first_action, L * M, &d_fa));
+    BRM_TRY(st.in(stats, st_count, &d_st));
+    BRM_TRY(brm::launch_root_stats(e, leaves->n, M, n_actions, V, d_fa, o.returns_sum, rp->rollouts_per_leaf, d_st));
+    BRM_TRY(st.out(stats, d_st, st_count));
+  }
+  if (out->returns_sum) BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * M * V));
   if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * M * R));
   if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));
   if (out->ro_returns) BRM_TRY(st.out(out->ro_returns, o.ro_returns, N * M * V));
@@ -588,6 +606,18 @@ int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout
   if (out->ro_steps) BRM_TRY(st.out(out->ro_steps, o.ro_steps, N));
   BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRM_OK;
+}
+
+int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
+                   const brm_cw_rollout_out* out) {
+  return cw_rollout_impl(e, leaves, rp, out, nullptr, 0, nullptr);
+}
+
+int brm_cw_rollout_root_stats(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,
+                              const brm_cw_rollout_out* out, const uint8_t* leaf_first_action, int32_t n_actions,
+                              double* stats) {
+  BRM_REQUIRE(leaf_first_action && stats && n_actions >= 1, "brm_cw_rollout_root_stats: bad arguments");
+  return cw_rollout_impl(e, leaves, rp, out, leaf_first_action, n_actions, stats);
 }
 
 int brm_cw_replay(brm_engine* e, const brm_cw_states* s0, const uint8_t* actions, int32_t T,

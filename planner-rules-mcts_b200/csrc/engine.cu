@@ -196,6 +196,24 @@ int brm_device_info(brm_engine* e, int* sm_count, int* sm_clock_khz, int* cc_maj
   return BRM_OK;
 }
 
+}  // extern "C"
+
+namespace brm {
+// K5 on device pointers (also used by brm_*_rollout_root_stats)
+int launch_root_stats(brm_engine* e, int32_t n_leaves, int32_t n_agents, int32_t n_actions, int32_t V,
+                      const uint8_t* d_first_action, const double* d_returns_sum, int32_t rollouts_per_leaf,
+                      double* d_stats) {
+  const int total = n_agents * n_actions * (1 + V);
+  root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(n_leaves, n_agents, n_actions, V, d_first_action,
+                                                             d_returns_sum, rollouts_per_leaf, d_stats);
+  e->launches++;
+  BRM_CUDA_CHECK(cudaGetLastError());
+  return BRM_OK;
+}
+}  // namespace brm
+
+extern "C" {
+
 int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t n_agents,
                           int32_t n_actions, int32_t reward_vec_size,
                           const uint8_t* leaf_first_action, const double* returns_sum,

@@ -248,18 +248,27 @@ int brm_gw_terminal_reward(brm_engine* e, const brm_gw_states* s, double* out) {
   return gw_query(e, s, nullptr, nullptr, out, "brm_gw_terminal_reward");
 }
 
-int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
-                   const brm_gw_rollout_out* out) {
+// rollouts, optionally followed by the root statistics (first_action != NULL) in the same call
+static int gw_rollout_impl(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                           const brm_gw_rollout_out* out, const uint8_t* first_action, int32_t n_actions,
+                           double* stats) {
   BRM_TRY(check_ready(e, "brm_gw_rollout"));
   BRM_TRY(check_states(leaves, "brm_gw_rollout"));
   BRM_REQUIRE(rp && out, "brm_gw_rollout: NULL argument");
-  BRM_REQUIRE(out->returns_sum, "brm_gw_rollout: returns_sum is required");
+  BRM_REQUIRE(out->returns_sum || first_action, "brm_gw_rollout: returns_sum is required");
   BRM_REQUIRE(rp->rollouts_per_leaf >= 1, "brm_gw_rollout: rollouts_per_leaf must be >= 1");
   BRM_REQUIRE(rp->max_steps >= 0 && rp->max_steps <= 255, "brm_gw_rollout: max_steps %d not in [0,255]",
               rp->max_steps);
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   const int A = e->gw_blob.A, R = e->gw_blob.R, V = e->gw_blob.V;
-  if (leaves->mem == BRM_MEM_DEVICE) return gw_launch_rollout(e, *leaves, *rp, *out);
+  if (leaves->mem == BRM_MEM_DEVICE) {
+    BRM_REQUIRE(out->returns_sum, "brm_gw_rollout: device batches need a returns_sum buffer");
+    BRM_TRY(gw_launch_rollout(e, *leaves, *rp, *out));
+    if (first_action)
+      BRM_TRY(brm::launch_root_stats(e, leaves->n, A, n_actions, V, first_action, out->returns_sum,
+                                     rp->rollouts_per_leaf, stats));
+    return BRM_OK;
+  }
   const size_t L = leaves->n;
   const size_t N = L * static_cast<size_t>(rp->rollouts_per_leaf);
   Stager st(e);
@@ -275,7 +284,16 @@ int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout
   if (out->ro_agents) BRM_TRY(st.alloc(N * A * 4, &o.ro_agents));
   if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
   BRM_TRY(gw_launch_rollout(e, d, *rp, o));
-  BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * A * V));
+  if (first_action) {
+    uint8_t* d_fa;
+    double* d_st;
+    const size_t st_count = static_cast<size_t>(A) * n_actions * (1 + V);
+    BRM_TRY(st.in(first_action, L * A, &d_fa));
+    BRM_TRY(st.in(stats, st_count, &d_st));
+    BRM_TRY(brm::launch_root_stats(e, leaves->n, A, n_actions, V, d_fa, o.returns_sum, rp->rollouts_per_leaf, d_st));
+    BRM_TRY(st.out(stats, d_st, st_count));
+  }
+  if (out->returns_sum) BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * A * V));
   if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * A * R));
   if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));
   if (out->ro_returns) BRM_TRY(st.out(out->ro_returns, o.ro_returns, N * A * V));
@@ -285,6 +303,18 @@ int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout
   if (out->ro_steps) BRM_TRY(st.out(out->ro_steps, o.ro_steps, N));
   BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRM_OK;
+}
+
+int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                   const brm_gw_rollout_out* out) {
+  return gw_rollout_impl(e, leaves, rp, out, nullptr, 0, nullptr);
+}
+
+int brm_gw_rollout_root_stats(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
+                              const brm_gw_rollout_out* out, const uint8_t* leaf_first_action, int32_t n_actions,
+                              double* stats) {
+  BRM_REQUIRE(leaf_first_action && stats && n_actions >= 1, "brm_gw_rollout_root_stats: bad arguments");
+  return gw_rollout_impl(e, leaves, rp, out, leaf_first_action, n_actions, stats);
 }
 
 int brm_gw_replay(brm_engine* e, const brm_gw_states* s0, const uint8_t* actions, int32_t T,

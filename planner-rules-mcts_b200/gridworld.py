@@ -215,11 +215,14 @@ class GridWorldEngine:
 
     # -- rollouts (mvmcts::RandomHeuristic) ----------------------------------------------
     def rollout(self, leaves, rollouts_per_leaf, seed=1000, rollout_base=0, max_steps=30,
-                discount_factor=0.95, first_discount_exp=1, detail=False, out=None, coop_factor=0.0):
+                discount_factor=0.95, first_discount_exp=1, detail=False, out=None, coop_factor=0.0,
+                first_action=None, stats=None):
         """Random rollouts from every leaf state.  Host batches return numpy arrays; for a
         device batch pass `out` = dict of preallocated CUDA tensors (returns_sum, viol_sum,
         agent_steps) and nothing is copied.  coop_factor: mvmcts COOP_FACTOR, returns_sum of
-        agent i = own_i + coop_factor * sum of the others'."""
+        agent i = own_i + coop_factor * sum of the others'.  With `first_action` [L][A] and
+        `stats` [A][n_actions][1+V] the per-leaf sums are also folded into the root statistics in
+        the same call (brm_gw_rollout_root_stats)."""
         rp = _abi.RolloutParams(seed, rollout_base, rollouts_per_leaf, max_steps, discount_factor,
                                 first_discount_exp, 0, coop_factor)
         L = leaves.n
@@ -238,7 +241,11 @@ class GridWorldEngine:
         for k, _ in _abi.GwRolloutOut._fields_:
             setattr(o, k, _ptr(out.get(k)))
         s = leaves.to_abi()
-        _abi.check(self.lib.brm_gw_rollout(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o)))
+        if stats is not None:
+            _abi.check(self.lib.brm_gw_rollout_root_stats(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o),
+                                                          _ptr(first_action), int(stats.shape[1]), _ptr(stats)))
+        else:
+            _abi.check(self.lib.brm_gw_rollout(self.engine.handle, C.byref(s), C.byref(rp), C.byref(o)))
         return out
 
     # -- replay (parity instrument) ---------------------------------------------------------

@@ -354,3 +354,29 @@ def test_coop_factor_mixes_agent_returns(built):
     s = own["returns_sum"]
     np.testing.assert_allclose(mix["returns_sum"], s + 0.25 * (s.sum(axis=1, keepdims=True) - s), rtol=1e-12, atol=1e-9)
     assert (mix["ro_returns"] == own["ro_returns"]).all() and (mix["viol_sum"] == own["viol_sum"]).all()
+
+
+def test_rollout_with_root_stats_in_one_call(built):
+    """brm_cw_rollout_root_stats == brm_cw_rollout followed by brm_root_stats_reduce, host and device."""
+    import torch
+    scn = scenarios.merge_scenario()
+    eng = brm.RulesMctsEngine([scn])
+    rng = np.random.default_rng(3)
+    L, n, n_act = 23, 40, 3
+    leaves = eng.initial_batch([0]).select(np.zeros(L, np.int64))
+    first = rng.integers(0, n_act, size=(L, eng.M)).astype(np.uint8)
+    ref = eng.rollout(leaves, n, seed=11, max_steps=12)
+    want = np.ones((eng.M, n_act, 1 + eng.V))          # accumulated INTO: start from non-zero statistics
+    eng.root_stats_reduce(first, ref["returns_sum"], n, want, n_act)
+    got = np.ones((eng.M, n_act, 1 + eng.V))
+    out = eng.rollout(leaves, n, seed=11, max_steps=12, first_action=first, stats=got)
+    assert np.array_equal(got, want) and np.array_equal(out["returns_sum"], ref["returns_sum"])
+    assert got[:, :, 0].sum() == eng.M * (n_act + L * n)
+    # device batches
+    d_out = dict(returns_sum=torch.zeros((L, eng.M, eng.V), dtype=torch.float64, device="cuda"))
+    d_stats = torch.ones((eng.M, n_act, 1 + eng.V), dtype=torch.float64, device="cuda")
+    d_leaves, d_first = leaves.cuda(0), torch.from_numpy(first).cuda()
+    torch.cuda.synchronize()
+    eng.rollout(d_leaves, n, seed=11, max_steps=12, out=d_out, first_action=d_first, stats=d_stats)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_stats.cpu().numpy(), want)

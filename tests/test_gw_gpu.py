@@ -266,3 +266,17 @@ def test_coop_factor_mixes_agent_returns(built):
     s = own["returns_sum"]
     np.testing.assert_allclose(mix["returns_sum"], s + 0.5 * (s.sum(axis=1, keepdims=True) - s), rtol=1e-12, atol=1e-9)
     assert (mix["viol_sum"] == own["viol_sum"]).all()
+
+
+def test_rollout_with_root_stats_in_one_call(built):
+    eng = brm.GridWorldEngine()
+    rng = np.random.default_rng(4)
+    L, n = 17, 64
+    leaves = eng.base_test_env_batch(L)
+    first = rng.integers(0, 3, size=(L, eng.A)).astype(np.uint8)
+    ref = eng.rollout(leaves, n, seed=2)
+    want = np.zeros((eng.A, 3, 1 + eng.V))
+    eng.root_stats_reduce(first, ref["returns_sum"], n, want)
+    got = np.zeros((eng.A, 3, 1 + eng.V))
+    out = eng.rollout(leaves, n, seed=2, first_action=first, stats=got)
+    assert np.array_equal(got, want) and np.array_equal(out["returns_sum"], ref["returns_sum"])
