@@ -1,7 +1,7 @@
 """Planner shell (planner.py) on the GPU: the behavioural pins of the reference's
-SingleAgentSuite (test/single_agent_test.cpp:229-306) on a world shaped like bark's
+SingleAgentSuite (test/single_agent_test.cpp:229-344) on a world shaped like bark's
 make_test_world: accelerate on a free road (best action == 1), brake behind a slower agent
-(best action == 4), reach the goal in closed loop without a collision."""
+(best action == 4), reach the goal in closed loop without a collision, change_lane."""
 import numpy as np
 import pytest
 
@@ -46,26 +46,33 @@ def test_agent_in_front_must_brake(built):
 
 
 def test_agent_in_front_reach_goal_closed_loop(built, tmp_path):
-    """Closed loop in the manner of :272-306 (plan, step the world, repeat): behind a slower
-    agent the ego must reach its goal region without ever touching the other vehicle.  The
-    longitudinal primitives of the suite are used; with the +-1 rad steering primitives this
-    flat-normalised UCT parks at low speed instead of re-aligning (the reference's thresholded
-    statistics are un-vendored), which is why the steering pair is left out here."""
-    scn = suite_world(1, 2.0, 2.0, goal=(30.0, 60.0, -4.25, 0.75))
-    for ag in scn.agents[:1]:
-        ag.primitives = [(0.0, 0.0), (5.0, 0.0), (-3.0, 0.0)]
-    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=400))
-    hist, final = planner.run_closed_loop(pl, max_steps=100)
+    """:271-305: behind a slower agent (bumper gap 2 m, 2 m/s slower) the planner must bring the ego
+    into the goal box ahead (the suite's 5 x 5 polygon moved to (10, -1.75)) without ever touching
+    the other vehicle -- with all five motion primitives of the suite, steering included."""
+    scn = suite_world(1, 2.0, 2.0, goal=(7.5, 12.5, -4.25, 0.75))
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))   # :187
+    hist, final = planner.run_closed_loop(pl, max_steps=100)                               # :292
     assert final.terminal[0] == 1
-    x, flags = final.agents[0, 0, 0], final.flags[0, 0]
-    assert flags & 2, "the ego must not have collided"             # EXPECT_FALSE(collision_ego), :293
-    assert 30.0 <= x - 1.0 and x + 3.0 <= 60.0, "the ego must end inside the goal region"  # :294-299
-    gap = hist[:, 1, 0] - hist[:, 0, 0]
-    assert (gap > 4.0).all()  # never closer than bumper contact on the way
+    x, y, flags = final.agents[0, 0, 0], final.agents[0, 0, 1], final.flags[0, 0]
+    assert flags & 2, "the ego must not have collided"             # EXPECT_FALSE(collision_ego), :295
+    assert 7.5 <= x - 1.0 and x + 3.0 <= 12.5 and -4.25 < y < 0.75, "the ego must end inside the goal"  # :296-299
+    gap = np.hypot(hist[:, 1, 0] - hist[:, 0, 0], hist[:, 1, 1] - hist[:, 0, 1])
+    assert (gap > 2.0).all()  # never closer than two half widths
     path = tmp_path / "states.tsv"
     planner.write_state_history_tsv(str(path), hist)
     lines = path.read_text().splitlines()
     assert lines[0] == "Timestep\tAgent 0\tAgent 1" and len(lines) == hist.shape[0] + 1
+
+
+def test_change_lane(built):
+    """:307-344: no other agent, goal box moved to (10, -2) with heading limits +-0.2 rad; the goal
+    must be reached within 20 steps."""
+    scn = suite_world(0, 2.0, 2.0, goal=(7.5, 12.5, -4.5, 0.5, -0.2, 0.2))
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))
+    hist, final = planner.run_closed_loop(pl, max_steps=20)                                # :330
+    x, y, th = final.agents[0, 0, :3]
+    assert final.terminal[0] == 1 and final.flags[0, 0] & 2
+    assert 7.5 <= x - 1.0 and x + 3.0 <= 12.5 and -4.5 < y < 0.5 and abs(th) < 0.2        # AtGoal, :337-341
 
 
 def test_terminal_root_is_refused(built):
