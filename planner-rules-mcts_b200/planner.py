@@ -34,6 +34,7 @@ class PlannerParameters:
     Search: str = "mcts"                  # "mcts": host tree (mcts.py); "flat": depth-1 root-parallel search
     RolloutsPerExpansion: int = 16        # mcts: device rollouts per expanded node
     UCTExplorationConstant: float = 1.42  # src/util.cpp:51-56
+    Statistic: str = "uct"                # "uct" (BehaviorRulesMctsUct) | "greedy" (BehaviorRulesMctsGreedy)
 
 
 class BehaviorRulesMcts:
@@ -68,7 +69,7 @@ class BehaviorRulesMcts:
                                 threshold=self.params.Threshold,
                                 max_rollout_steps=self.params.MaxNumIterationsRandomHeuristic,
                                 rollouts_per_expansion=self.params.RolloutsPerExpansion,
-                                seed=self.params.RandomSeed + self.decision)
+                                seed=self.params.RandomSeed + self.decision, statistic=self.params.Statistic)
             m = Mcts(eng, mp).Search(state_batch, self.params.MaxNumIterations)
             self.last_stats = m.GetRootStats()
             self.last_action = m.ReturnBestAction()[0]

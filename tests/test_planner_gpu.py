@@ -22,9 +22,14 @@ def suite_world(n_others, rel_distance, velocity_difference, goal):
         primitives=PRIMITIVES, goal=goal, params=p, rules=[RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)])
 
 
-def test_no_agent_in_front_accelerate(built):
+# the reference's suite is typed on BehaviorRulesMctsUct and BehaviorRulesMctsGreedy (:225-227)
+STATISTICS = ["uct", "greedy"]
+
+
+@pytest.mark.parametrize("statistic", STATISTICS)
+def test_no_agent_in_front_accelerate(built, statistic):
     scn = suite_world(0, 7.0, 0.0, goal=(7.5, 12.5, -4.25, 0.75))
-    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))  # :187
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000, Statistic=statistic))  # :187
     a = pl.Plan(pl.engine.initial_batch([0]))
     q = pl.GetExpectedRewards()
     assert a == 1 and pl.GetLastAction() == 1, q   # :248
@@ -32,9 +37,10 @@ def test_no_agent_in_front_accelerate(built):
     assert pl.last_stats[0, 1, 0] == pl.last_stats[0, :, 0].max()  # UCT concentrates on the best action
 
 
-def test_agent_in_front_must_brake(built):
+@pytest.mark.parametrize("statistic", STATISTICS)
+def test_agent_in_front_must_brake(built, statistic):
     scn = suite_world(1, 2.0, 2.0, goal=(7.5, 12.5, -4.25, 0.75))
-    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000, Statistic=statistic))
     a = pl.Plan(pl.engine.initial_batch([0]))
     assert a == 4, pl.GetExpectedRewards()         # :268
     # the flat root-parallel search must at least rank braking above accelerating here
@@ -45,12 +51,13 @@ def test_agent_in_front_must_brake(built):
     assert qf[4][0] > qf[1][0]
 
 
-def test_agent_in_front_reach_goal_closed_loop(built, tmp_path):
+@pytest.mark.parametrize("statistic", STATISTICS)
+def test_agent_in_front_reach_goal_closed_loop(built, tmp_path, statistic):
     """:271-305: behind a slower agent (bumper gap 2 m, 2 m/s slower) the planner must bring the ego
     into the goal box ahead (the suite's 5 x 5 polygon moved to (10, -1.75)) without ever touching
     the other vehicle -- with all five motion primitives of the suite, steering included."""
     scn = suite_world(1, 2.0, 2.0, goal=(7.5, 12.5, -4.25, 0.75))
-    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))   # :187
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000, Statistic=statistic))   # :187
     hist, final = planner.run_closed_loop(pl, max_steps=100)                               # :292
     assert final.terminal[0] == 1
     x, y, flags = final.agents[0, 0, 0], final.agents[0, 0, 1], final.flags[0, 0]
@@ -64,11 +71,12 @@ def test_agent_in_front_reach_goal_closed_loop(built, tmp_path):
     assert lines[0] == "Timestep\tAgent 0\tAgent 1" and len(lines) == hist.shape[0] + 1
 
 
-def test_change_lane(built):
+@pytest.mark.parametrize("statistic", STATISTICS)
+def test_change_lane(built, statistic):
     """:307-344: no other agent, goal box moved to (10, -2) with heading limits +-0.2 rad; the goal
     must be reached within 20 steps."""
     scn = suite_world(0, 2.0, 2.0, goal=(7.5, 12.5, -4.5, 0.5, -0.2, 0.2))
-    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000))
+    pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000, Statistic=statistic))
     hist, final = planner.run_closed_loop(pl, max_steps=20)                                # :330
     x, y, th = final.agents[0, 0, :3]
     assert final.terminal[0] == 1 and final.flags[0, 0] & 2
