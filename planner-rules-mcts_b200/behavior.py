@@ -258,7 +258,8 @@ class BehaviorRulesMcts:
                             threshold=self.params.Threshold,
                             max_rollout_steps=self.params.MaxNumIterationsRandomHeuristic,
                             rollouts_per_expansion=self.params.RolloutsPerExpansion,
-                            seed=self.params.RandomSeed + self._decision, statistic=self.STATISTIC)
+                            seed=self.params.RandomSeed + self._decision, statistic=self.STATISTIC,
+                            batch_size=self.params.BatchSize)
         self._decision += 1
         mcts = Mcts(engine, mp).Search(root, self.params.MaxNumIterations)
         self.last_stats = mcts.GetRootStats()

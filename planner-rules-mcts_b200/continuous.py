@@ -217,6 +217,14 @@ class CwBatch:
         return CwBatch(t(self.scenario), t(self.agents), t(self.flags), t(self.horizon), t(self.terminal),
                        t(self.q), viol)
 
+    @staticmethod
+    def concat(batches):
+        """Host batches only: one batch holding the states of all `batches`, in order."""
+        cat = lambda f, ax: np.ascontiguousarray(np.concatenate([getattr(b, f) for b in batches], axis=ax))
+        viol = None if any(b.viol is None for b in batches) else cat("viol", 2)
+        return CwBatch(cat("scenario", 0), cat("agents", 1), cat("flags", 1), cat("horizon", 0), cat("terminal", 0),
+                       cat("q", 2), viol)
+
     def select(self, idx):
         idx = np.asarray(idx)
         v = None if self.viol is None else np.ascontiguousarray(self.viol[:, :, idx])

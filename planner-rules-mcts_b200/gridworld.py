@@ -113,6 +113,13 @@ class GwBatch:
         viol = None if self.viol is None else torch.from_numpy(self.viol.view(np.int32)).to(dev)
         return GwBatch(t(self.agents), t(self.term), t(self.depth), t(self.q), viol)
 
+    @staticmethod
+    def concat(batches):
+        """Host batches only: one batch holding the states of all `batches`, in order."""
+        cat = lambda f, ax: np.ascontiguousarray(np.concatenate([getattr(b, f) for b in batches], axis=ax))
+        viol = None if any(b.viol is None for b in batches) else cat("viol", 2)
+        return GwBatch(cat("agents", 1), cat("term", 0), cat("depth", 0), cat("q", 2), viol)
+
     def select(self, idx):
         """Host batches only: states idx (array of indices)."""
         v = None if self.viol is None else np.ascontiguousarray(self.viol[:, :, idx])

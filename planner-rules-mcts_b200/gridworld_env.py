@@ -19,7 +19,7 @@ from .gridworld import GridWorldEngine, GridWorldState, GridWorldStateParameter,
 from .mcts import Mcts, MctsParameters
 
 
-def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000, statistic="uct"):
+def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000, statistic="uct", batch_size=1):
     """BaseTestEnv::MakeMctsParameters (gridworld/base_test_env.cpp:45-77)."""
     thres = np.asarray(thres, np.float64)
     assert thres.size == 3
@@ -27,17 +27,18 @@ def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000, statistic="u
         3, discount_factor=0.95, exploration_constant=[0.8, 0.8, 0.8],
         lower_bound=[-1.0, -1.0, -100.0], upper_bound=[0.0, 0.0, 0.0], threshold=thres,
         max_rollout_steps=30, rollouts_per_expansion=rollouts_per_expansion, seed=seed,
-        statistic=statistic, decay1=0.8, decay2=0.12)
+        statistic=statistic, decay1=0.8, decay2=0.12, batch_size=batch_size)
 
 
 class CrossingTestEnv:
     """BaseTestEnv + CrossingTestEnv<Stats>: owns the state, the MCTS and the histories."""
 
-    def __init__(self, thres, device=0, engine=None, rollouts_per_expansion=16, seed=1000, statistic="uct"):
+    def __init__(self, thres, device=0, engine=None, rollouts_per_expansion=16, seed=1000, statistic="uct",
+                 batch_size=1):
         self.grid_world_state_parameter = GridWorldStateParameter()
         self.engine = engine or GridWorldEngine(self.grid_world_state_parameter, make_default_rules(),
                                                 device=device)
-        self.mcts_parameters = MakeMctsParameters(thres, rollouts_per_expansion, seed, statistic)
+        self.mcts_parameters = MakeMctsParameters(thres, rollouts_per_expansion, seed, statistic, batch_size)
         self.state = GridWorldState(self.engine)
         A, V = self.engine.A, self.engine.V
         self.rewards = np.zeros((A, V))

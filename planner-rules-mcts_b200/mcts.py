@@ -19,7 +19,7 @@ from . import parallel
 
 
 class _Node:
-    __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q", "value")
+    __slots__ = ("state", "terminal", "n_actions", "children", "N", "Q", "value", "term_value")
 
     def __init__(self, state, terminal, n_actions, V):
         self.state = state
@@ -29,6 +29,7 @@ class _Node:
         self.N = [np.zeros(k) for k in self.n_actions]
         self.Q = [np.zeros((k, V)) for k in self.n_actions]
         self.value = np.zeros((len(self.n_actions), V))  # the heuristic's estimate at expansion
+        self.term_value = None                             # terminal nodes: GetTerminalReward, cached
 
 
 class MctsParameters:
@@ -36,13 +37,17 @@ class MctsParameters:
 
     def __init__(self, V, discount_factor=0.9, exploration_constant=1.42, lower_bound=None, upper_bound=None,
                  threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000, coop_factor=0.0,
-                 statistic="uct", decay1=0.8, decay2=0.12):
+                 statistic="uct", decay1=0.8, decay2=0.12, batch_size=1):
         self.DISCOUNT_FACTOR = discount_factor
         self.COOP_FACTOR = coop_factor            # src/util.cpp:28-29
         # "uct": ThresUCTStatistic; "greedy": ThresGreedyStatistic (epsilon-greedy on the thresholded
         # order, epsilon = DECAY1 / (1 + DECAY2 * visits of the node); gridworld/base_test_env.cpp:69-70)
         assert statistic in ("uct", "greedy")
         self.statistic, self.DECAY1, self.DECAY2 = statistic, decay1, decay2
+        # iterations that descend the tree before the device is called: 1 = the reference's loop;
+        # > 1: leaf-parallel rounds with a virtual loss (one batched Execute + one rollout launch
+        # for all of them, INTEGRATION.md level 2)
+        self.batch_size = max(1, int(batch_size))
         self.EXPLORATION_CONSTANT = exploration_constant
         lb = [-1.0] * V
         lb[-1] = -1000.0                      # src/util.cpp:58-59
@@ -137,6 +142,8 @@ class Mcts:
         self.root = self._make_node(state)
         if self.root.terminal:
             raise RuntimeError("Current state is terminal! Aborting!")  # src/behavior_rules_mcts.hpp:208-209
+        if self.p.batch_size > 1:
+            return self._search_batched(max_iterations)
         gamma = self.p.DISCOUNT_FACTOR
         M, V = self.engine.M, self.engine.V
         for _ in range(max_iterations):
@@ -165,6 +172,79 @@ class Mcts:
                     nd.N[a][ja[a]] += 1
                     nd.Q[a][ja[a]] += value[a]
             self.iterations += 1
+        return self
+
+    def _search_batched(self, max_iterations):
+        """Leaf-parallel rounds: `batch_size` descents per round, kept apart by a virtual loss (each
+        descent counts its visits at once, with the lower bound as value, until its real return is
+        known); the new nodes of a round are created by ONE batched Execute and evaluated by ONE
+        rollout launch.  Descents that ask for the same expansion share it."""
+        eng, p = self.engine, self.p
+        gamma, M = p.DISCOUNT_FACTOR, eng.M
+        vloss = p.LOWER_BOUND.astype(np.float64)
+        batch_type = type(self.root.state)
+        done = 0
+        while done < max_iterations:
+            k = min(p.batch_size, max_iterations - done)
+            descents = []          # (path, ("term", node) | ("exp", index into expansions))
+            expansions, index = [], {}
+            for _ in range(k):
+                node, path = self.root, []
+                while True:
+                    if node.terminal:
+                        descents.append((path, ("term", node)))
+                        break
+                    ja = self._select(node)
+                    for a in range(M):                      # virtual loss
+                        node.N[a][ja[a]] += 1
+                        node.Q[a][ja[a]] += vloss
+                    if ja in node.children:
+                        child, r = node.children[ja]
+                        path.append((node, ja, r))
+                        node = child
+                        continue
+                    key = (id(node), ja)
+                    if key not in index:
+                        index[key] = len(expansions)
+                        expansions.append((node, ja))
+                    path.append((node, ja, None))
+                    descents.append((path, ("exp", index[key])))
+                    break
+            new_nodes = []
+            if expansions:
+                parents = batch_type.concat([nd.state for nd, _ in expansions])
+                acts = np.array([ja for _, ja in expansions], np.uint8).T.copy()       # [M][n]
+                nxt, rew = eng.execute(parents, acts)
+                term = eng.is_terminal(nxt)
+                nact = eng.get_num_actions(nxt)
+                tval = eng.terminal_reward(nxt).astype(np.float64)
+                n = p.rollouts_per_expansion
+                out = eng.rollout(nxt, n, seed=p.seed, rollout_base=self._next_rollout,
+                                  max_steps=p.MAX_NUMBER_OF_ITERATIONS, discount_factor=p.DISCOUNT_FACTOR,
+                                  first_discount_exp=0, coop_factor=p.COOP_FACTOR)
+                self._next_rollout += n * len(expansions)
+                for i, (nd, ja) in enumerate(expansions):
+                    child = _Node(nxt.select(np.array([i])), term[i], nact[:, i], eng.V)
+                    child.value = out["returns_sum"][i] / n
+                    child.term_value = self._coop(tval[:, :, i])
+                    r = self._coop(rew[:, :, i].astype(np.float64))
+                    nd.children[ja] = (child, r)
+                    new_nodes.append((child, r))
+            for path, (kind, what) in descents:
+                if kind == "term":
+                    if what.term_value is None:
+                        what.term_value = self._coop(eng.terminal_reward(what.state)[:, :, 0].astype(np.float64))
+                    value = what.term_value
+                else:
+                    child, r_new = new_nodes[what]
+                    value = child.value
+                for nd, ja, r in reversed(path):
+                    r = r_new if r is None else r
+                    value = r + gamma * value
+                    for a in range(M):                      # replace the virtual loss by the return
+                        nd.Q[a][ja[a]] += value[a] - vloss
+                self.iterations += 1
+            done += k
         return self
 
     def GetRootStats(self):

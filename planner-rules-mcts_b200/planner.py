@@ -35,6 +35,7 @@ class PlannerParameters:
     RolloutsPerExpansion: int = 16        # mcts: device rollouts per expanded node
     UCTExplorationConstant: float = 1.42  # src/util.cpp:51-56
     Statistic: str = "uct"                # "uct" (BehaviorRulesMctsUct) | "greedy" (BehaviorRulesMctsGreedy)
+    BatchSize: int = 1                    # mcts: descents per device round (1 = the reference's serial loop)
 
 
 class BehaviorRulesMcts:
@@ -69,7 +70,8 @@ class BehaviorRulesMcts:
                                 threshold=self.params.Threshold,
                                 max_rollout_steps=self.params.MaxNumIterationsRandomHeuristic,
                                 rollouts_per_expansion=self.params.RolloutsPerExpansion,
-                                seed=self.params.RandomSeed + self.decision, statistic=self.params.Statistic)
+                                seed=self.params.RandomSeed + self.decision, statistic=self.params.Statistic,
+                                batch_size=self.params.BatchSize)
             m = Mcts(eng, mp).Search(state_batch, self.params.MaxNumIterations)
             self.last_stats = m.GetRootStats()
             self.last_action = m.ReturnBestAction()[0]

@@ -20,8 +20,9 @@ def engine(built):
     return ge.CrossingTestEnv((0.0, 0.0, BIG)).engine
 
 
-def run(engine, thres, tmp_path=None, statistic="uct"):
-    env = ge.CrossingTestEnv(thres, engine=engine, seed=1000, statistic=statistic)   # seed of the suite's main()
+def run(engine, thres, tmp_path=None, statistic="uct", batch_size=1):
+    env = ge.CrossingTestEnv(thres, engine=engine, seed=1000, statistic=statistic,   # seed of the suite's main()
+                             batch_size=batch_size)
     runner = ge.TestRunner(env, q_val_fname=None if tmp_path is None else str(tmp_path / "q_val.dat"))
     res = runner.RunTest(3000, 16)                               # :28
     return np.array(env.state_history), res, env
@@ -57,3 +58,11 @@ def test_livelock(engine):
     last = hist[-1]
     assert last[0] < MERGING_POINT and last[1] > MERGING_POINT and last[2] < MERGING_POINT  # :68-70
     assert not res.collision
+
+
+def test_pass_with_leaf_parallel_rounds(engine):
+    """The same suite with 8 descents per device round (virtual loss): same behaviour, half the time."""
+    hist, res, _ = run(engine, (-0.37, -0.37, BIG), batch_size=8)
+    last = hist[-1]
+    assert (last > MERGING_POINT).all() and last[0] < last[2] < last[1]
+    assert not res.collision and not res.violation

@@ -88,3 +88,14 @@ def test_terminal_root_is_refused(built):
     pl = planner.BehaviorRulesMcts(scn)
     with pytest.raises(RuntimeError):
         pl.Plan(pl.engine.initial_batch([0]))
+
+
+@pytest.mark.parametrize("batch", [8, 32])
+def test_leaf_parallel_rounds_keep_the_pins(built, batch):
+    """mcts.py with batch_size > 1: several descents per round (virtual loss), one batched Execute
+    and one rollout launch for all of them -- same decisions, a fraction of the round trips."""
+    for n_others, rel, dv, want in ((0, 7.0, 0.0, 1), (1, 2.0, 2.0, 4)):
+        scn = suite_world(n_others, rel, dv, goal=(7.5, 12.5, -4.25, 0.75))
+        pl = planner.BehaviorRulesMcts(scn, planner.PlannerParameters(MaxNumIterations=1000, BatchSize=batch))
+        assert pl.Plan(pl.engine.initial_batch([0])) == want, pl.GetExpectedRewards()
+        assert pl.last_stats[0, :, 0].sum() == 1000            # every descent is counted exactly once
