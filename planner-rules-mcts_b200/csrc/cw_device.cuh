@@ -26,7 +26,7 @@ struct alignas(16) CwLaneHdr {
 constexpr int kCwMaxSegs = BRM_CW_MAX_LANES * (BRM_CW_MAX_PTS - 1);
 constexpr int kCwThreads = 128;          // CTA size of every continuous-world kernel
 // resident CTAs per SM the rollout kernel is compiled for.  Measured on B200 (M / W / S
-// workloads): 5 CTAs (<= 102 registers, 92 used) beats 6 (80 regs) and 8 (64 regs) by 2-12 %,
+// workloads): 5 CTAs (<= 102 registers, 96 used) beats 6 (80 regs) and 8 (64 regs) by 2-12 %,
 // and 4 or 3 CTAs are no better -- registers matter more than occupancy here.
 #ifndef BRM_CW_CTAS_PER_SM
 #define BRM_CW_CTAS_PER_SM 5
