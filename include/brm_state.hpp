@@ -155,9 +155,14 @@ class GridWorldRolloutEvaluator {
   GridWorldRolloutEvaluator(std::shared_ptr<GridWorldContext> ctx, const brm_rollout_params& rp)
       : ctx_(std::move(ctx)), rp_(rp) {}
 
-  // returns [leaf][agent] -> Reward (mean over rollouts_per_leaf rollouts)
+  // returns [leaf][agent] -> Reward (mean over rollouts_per_leaf rollouts).  With `first_action`
+  // ([leaf][agent] root action each leaf descends from) and `stats` ([agent][n_actions][1+V], visits
+  // and value sums, accumulated into) the root statistics are folded in the same call
+  // (brm_gw_rollout_root_stats).
   std::vector<std::vector<Reward>> Evaluate(const std::vector<std::shared_ptr<GridWorldState>>& leaves,
-                                            uint64_t rollout_base) {
+                                            uint64_t rollout_base,
+                                            const std::vector<uint8_t>* first_action = nullptr, int n_actions = 0,
+                                            std::vector<double>* stats = nullptr) {
     const int A = ctx_->A, V = ctx_->V, R = ctx_->R;
     const size_t L = leaves.size();
     std::vector<int32_t> agents(static_cast<size_t>(A) * L * 4), depth(L);
@@ -185,7 +190,11 @@ class GridWorldRolloutEvaluator {
     out.returns_sum = sums.data();
     brm_rollout_params rp = rp_;
     rp.rollout_base = rollout_base;
-    check(brm_gw_rollout(ctx_->engine->get(), &b, &rp, &out));
+    if (stats)
+      check(brm_gw_rollout_root_stats(ctx_->engine->get(), &b, &rp, &out, first_action->data(), n_actions,
+                                      stats->data()));
+    else
+      check(brm_gw_rollout(ctx_->engine->get(), &b, &rp, &out));
     std::vector<std::vector<Reward>> res(L, std::vector<Reward>(A, Reward(V, 0.0)));
     for (size_t l = 0; l < L; ++l)
       for (int a = 0; a < A; ++a)
@@ -324,7 +333,9 @@ class RulesMctsRolloutEvaluator {
 
   // returns [leaf][agent] -> Reward (mean over rollouts_per_leaf rollouts)
   std::vector<std::vector<Reward>> Evaluate(const std::vector<std::shared_ptr<MvmctsState>>& leaves,
-                                            uint64_t rollout_base) {
+                                            uint64_t rollout_base,
+                                            const std::vector<uint8_t>* first_action = nullptr, int n_actions = 0,
+                                            std::vector<double>* stats = nullptr) {
     const int A = ctx_->A, M = ctx_->M, V = ctx_->V, R = ctx_->R;
     const size_t L = leaves.size();
     std::vector<int32_t> scenario(L), horizon(L);
@@ -358,7 +369,11 @@ class RulesMctsRolloutEvaluator {
     out.returns_sum = sums.data();
     brm_rollout_params rp = rp_;
     rp.rollout_base = rollout_base;
-    check(brm_cw_rollout(ctx_->engine->get(), &b, &rp, &out));
+    if (stats)
+      check(brm_cw_rollout_root_stats(ctx_->engine->get(), &b, &rp, &out, first_action->data(), n_actions,
+                                      stats->data()));
+    else
+      check(brm_cw_rollout(ctx_->engine->get(), &b, &rp, &out));
     std::vector<std::vector<Reward>> res(L, std::vector<Reward>(M, Reward(V, 0.0)));
     for (size_t l = 0; l < L; ++l)
       for (int a = 0; a < M; ++a)

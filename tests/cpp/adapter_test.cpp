@@ -80,6 +80,15 @@ int main(int argc, char** argv) {
     for (size_t l = 0; l < means.size(); ++l)
       for (int a = 0; a < ctx->A; ++a)
         std::printf("leaf %zu agent %d mean %.17g %.17g %.17g\n", l, a, means[l][a][0], means[l][a][1], means[l][a][2]);
+    // the same rollouts with the root statistics folded in the same call
+    std::vector<uint8_t> first = {0, 1, 2, 2, 1, 0};  // [leaf][agent]
+    std::vector<double> stats(static_cast<size_t>(ctx->A) * 3 * (1 + ctx->V), 0.0);
+    ev.Evaluate({root, root}, 0, &first, 3, &stats);
+    for (int a = 0; a < ctx->A; ++a)
+      for (int k = 0; k < 3; ++k) {
+        const double* st = &stats[(static_cast<size_t>(a) * 3 + k) * (1 + ctx->V)];
+        std::printf("stats agent %d action %d visits %.17g sums %.17g %.17g %.17g\n", a, k, st[0], st[1], st[2], st[3]);
+      }
     return 0;
   }
   if (mode == "cw") {

@@ -68,6 +68,15 @@ def test_adapter_gridworld_matches_python_mirror(exe, tmp_path):
     for l in range(2):
         for a in range(3):
             assert got[l * 3 + a] == "leaf %d agent %d mean %.17g %.17g %.17g" % (l, a, *means[l, a])
+    stats = np.zeros((3, 3, 1 + eng.V))
+    first = np.array([[0, 1, 2], [2, 1, 0]], np.uint8)
+    eng.rollout(eng.base_test_env_batch(2), n, seed=1000, max_steps=30, discount_factor=0.95, first_action=first,
+                stats=stats)
+    got = [l for l in lines if l.startswith("stats")]
+    assert len(got) == 9
+    for a in range(3):
+        for k in range(3):
+            assert got[a * 3 + k] == "stats agent %d action %d visits %.17g sums %.17g %.17g %.17g" % (a, k, *stats[a, k])
 
 
 @pytest.mark.gpu
