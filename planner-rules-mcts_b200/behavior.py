@@ -202,15 +202,29 @@ class BehaviorRulesMcts:
             m.goal = self.ego_goal if k == 0 else None
             models.append(m)
         state = np.array([observed_world.agents[i] for i in order], np.float32)
+        # the uploaded rule list: the common rules, then the rules given to single agents; every
+        # MCTS agent gets the list of rule indices that apply to it (its own rule list, in order)
+        rules, per_agent = list(self.common_rules_), []
+        for i in agent_ids:
+            idx = list(range(len(self.common_rules_)))
+            for r in self.agent_rules_.get(i, []):
+                k = next((k for k, u in enumerate(rules) if u is r), None)
+                if k is None:
+                    rules.append(r)
+                    k = len(rules) - 1
+                idx.append(k)
+            per_agent.append(idx)
+        only_common = len(rules) == len(self.common_rules_)
         scn = Scenario(self.state_params_, models, len(agent_ids), observed_world.lanes,
-                       np.asarray(observed_world.road), self.common_rules_, state)
-        return RulesMctsEngine([scn], engine=self._abi_engine), order
+                       np.asarray(observed_world.road), rules, state, None if only_common else per_agent)
+        return RulesMctsEngine([scn], engine=self._abi_engine), order, rules, per_agent
 
-    def _slots(self, order, a):
-        """(rule index, bound world agent id or None) of every rule slot of MCTS agent a, in the
-        engine's order: rules in order, agent-specific ones once per other agent ascending."""
+    @staticmethod
+    def _slots(order, a, rules):
+        """(uploaded rule index, bound world agent id or None) of every rule slot of MCTS agent a, in
+        the engine's order: rules in order, agent-specific ones once per other agent ascending."""
         out = []
-        for k, rule in enumerate(self.common_rules_):
+        for k, rule in enumerate(rules):
             if rule.IsAgentSpecific():
                 out += [(k, o) for j, o in enumerate(order) if j != a]
             else:
@@ -226,20 +240,19 @@ class BehaviorRulesMcts:
         self.AddKnownAgents(new_agents)
         agent_ids = self.GetAgentIdMap(observed_world)
         self.RemoveRuleStates(list(observed_world.GetValidAgents()))
-        if any(self.agent_rules_.get(i) for i in agent_ids):
-            raise NotImplementedError("per-agent rule sets are not uploaded to the device engine yet")
-
         if self._abi_engine is None:
             self._abi_engine = _abi.Engine(self._device)
-        engine, order = self._configure(observed_world, agent_ids)
+        engine, order, rules, per_agent = self._configure(observed_world, agent_ids)
         M, R = engine.M, engine.R
         q0 = np.zeros((M, R), np.uint8)
         index = []
         for a in range(M):
-            states = {(rs.rule, rs.agent_ids): rs for rs in self.multi_agent_rule_state_[order[a]]}
-            row = [states[(k, () if o is None else (o,))] for k, o in self._slots(order, a)]
+            # the agent's own rule numbering (common rules, then its own) -> uploaded rule index
+            states = {(per_agent[a][rs.rule], rs.agent_ids): rs for rs in self.multi_agent_rule_state_[order[a]]}
+            slots = self._slots(order, a, rules)
+            row = [states.get((k, () if o is None else (o,))) for k, o in slots]   # None: rule of another agent
             assert len(row) == R
-            q0[a] = [rs.q for rs in row]
+            q0[a] = [rules[k].disabled_state if rs is None else rs.q for rs, (k, _) in zip(row, slots)]
             index.append(row)
         root = engine.make_batch(engine.scenarios[0].initial_state[None], q=q0)
         if root.terminal[0]:
@@ -248,8 +261,9 @@ class BehaviorRulesMcts:
         root, _ = engine.evaluate_rules(root)
         for a in range(M):
             for s, rs in enumerate(index[a]):
-                rs.q = int(root.q[a, s, 0])
-                rs.violations += int(root.viol[a, s, 0])
+                if rs is not None:
+                    rs.q = int(root.q[a, s, 0])
+                    rs.violations += int(root.viol[a, s, 0])
         root.viol[:] = 0
 
         sp = self.state_params_

@@ -147,6 +147,10 @@ class Scenario:
     rules: List[RuleMonitor]
     # initial world state: [A][4] (x, y, theta, v)
     initial_state: Optional[np.ndarray] = None
+    # per MCTS agent the indices of the rules that apply to it (None: every rule, AddCommonRules);
+    # AddAgentRules of the reference: rules listed for some agents only.  The slots of the other
+    # rules start (and stay) in the rule's `disabled_state` -- see initial_q().
+    agent_rules: Optional[List[Optional[List[int]]]] = None
 
     def to_abi(self):
         s = _abi.CwScenario()
@@ -249,12 +253,17 @@ class RulesMctsEngine:
         self.R = int(self.lib.brm_cw_rules_per_agent(self.engine.handle))
 
     def initial_q(self, scenario=0):
-        rules = self.scenarios[scenario].rules
+        """[M][R] initial automaton states; rules that do not apply to an agent (Scenario.agent_rules)
+        sit in their absorbing `disabled_state`."""
+        scn = self.scenarios[scenario]
         q = np.zeros((self.M, self.R), np.uint8)
         s = 0
-        for r in rules:
+        for k, r in enumerate(scn.rules):
             reps = self.A - 1 if r.IsAgentSpecific() else 1
             q[:, s:s + reps] = r.table.init
+            for a, lst in enumerate(scn.agent_rules or []):
+                if lst is not None and k not in lst:
+                    q[a, s:s + reps] = r.disabled_state
             s += reps
         return q
 

@@ -504,13 +504,31 @@ class RuleMonitor:
     def IsAgentSpecific(self):
         return self.table.is_agent_specific()
 
+    @property
+    def disabled_state(self):
+        """State index of "this rule does not apply to this agent" in the packed table: one extra
+        absorbing, accepting state behind the automaton's own.  An agent that was not given the rule
+        (BehaviorRulesMcts::AddAgentRules, src/behavior_rules_mcts.hpp:278-293) carries it in the
+        rule's slots: no letter moves it, it never violates and its final penalty is 0 -- the
+        kernels skip absorbing states, so such slots cost nothing."""
+        return self.table.n_states
+
+    def packed_table(self):
+        """(n_states, rows, accepting) as uploaded: the automaton plus the `disabled_state`."""
+        t = self.table
+        rows = [list(row) for row in t.trans] + [[t.n_states] * (1 << t.n_aps)]
+        return t.n_states + 1, rows, list(t.accepting) + [1]
+
     def to_abi(self, label_ids):
         """Pack into the C-ABI brm_rule; `label_ids` maps AP base names to label kinds."""
         from . import _abi
         t = self.table
         r = _abi.Rule()
         r.n_aps = t.n_aps
-        r.n_states = t.n_states
+        n_states, rows, accepting = self.packed_table()
+        if n_states > _abi.MAX_DFA_STATES:
+            raise ValueError("rule automaton has %d states (limit %d)" % (t.n_states, _abi.MAX_DFA_STATES - 1))
+        r.n_states = n_states
         r.init_state = t.init
         r.priority = self.priority
         r.on_violation = 0 if self.on_violation == "reset" else 1
@@ -522,9 +540,9 @@ class RuleMonitor:
             r.ap_label[k] = label_ids[base]
             r.ap_agent_specific[k] = 1 if "#" in name else 0
         stride = 1 << t.n_aps
-        for q, row in enumerate(t.trans):
+        for q, row in enumerate(rows):
             for l, nxt in enumerate(row):
                 r.trans[q * stride + l] = nxt
-        for q, a in enumerate(t.accepting):
+        for q, a in enumerate(accepting):
             r.accepting[q] = a
         return r

@@ -75,17 +75,18 @@ def oracle_config(scn, precision=0):
     for k, r in enumerate(scn.rules):
         t = r.table
         o = c.rules[k]
-        o.n_aps, o.n_states, o.init_state = t.n_aps, t.n_states, t.init
+        n_states, rows, accepting = r.packed_table()   # with the "does not apply" state, as uploaded
+        o.n_aps, o.n_states, o.init_state = t.n_aps, n_states, t.init
         o.priority = r.priority
         o.reset_on_violation = 1 if r.on_violation == "reset" else 0
         o.weight = r.weight
         for j, name in enumerate(t.aps):
             o.ap_label[j] = CW_LABELS[name.split("#")[0]]
         stride = 1 << t.n_aps
-        for q, row in enumerate(t.trans):
+        for q, row in enumerate(rows):
             for l, nxt in enumerate(row):
                 o.trans[q * stride + l] = nxt
-        for q, acc in enumerate(t.accepting):
+        for q, acc in enumerate(accepting):
             o.accepting[q] = acc
     return c
 

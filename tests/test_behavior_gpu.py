@@ -130,3 +130,23 @@ def test_python_binding_surface(built):
     states, flags = s1.observed_world
     assert states.shape == (2, 4) and (flags == 3).all()
     assert [r.tolist() for r in s1.EvaluateRules()] == [[0.0]]
+
+
+def test_rules_given_to_single_agents(built):
+    """AddAgentRules (:278-293): the ego alone carries the "has been near" rule; the other interacting
+    agents are searched with the common rule only, and the ego's state still advances."""
+    rules = [RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)]
+    near = RuleMonitor.MakeRule("F near_x#0", -1.0, 0)
+    sp = brm.RulesMctsStateParameters(HORIZON=10, NEAR_DISTANCE=12.0)
+    pl = behavior.BehaviorRulesMctsUct(PlannerParameters(MaxNumIterations=100, RolloutsPerExpansion=8), sp,
+                                       behavior.PredictionSettings(ego_primitives=PRIMS), common_rules=rules,
+                                       shape=brm.AgentModel(**scenarios.CAR))
+    pl.AddAgentRules([EGO], [near])
+    agents = {EGO: (0.0, -1.75, 0.0, 8.0), 3: (8.0, -5.25, 0.0, 8.0), 12: (60.0, -5.25, 0.0, 8.0)}
+    pl.Plan(0.3, make_world(agents))
+    st = pl.GetMultiAgentRuleState()
+    assert sorted((r.rule, r.agent_ids) for r in st[EGO]) == [(0, ()), (1, (3,)), (1, (12,))]
+    assert sorted((r.rule, r.agent_ids) for r in st[3]) == [(0, ())]
+    ego = {r.agent_ids: r for r in st[EGO] if r.rule == 1}
+    done = [q for q in range(near.table.n_states) if near.table.accepting[q]]
+    assert ego[(3,)].q in done and ego[(12,)].q == near.table.init       # 3 is near, 12 is not

@@ -31,7 +31,8 @@ def replay_both(eng, orc, scn, acts, states=None, flags=None, horizon=None):
     batch = eng.make_batch(states, flags=flags, horizon=horizon)
     tr = eng.replay(batch, acts)
     cfg = oracle_config(scn)
-    outs = [orc.replay(cfg, states[b], flags[b], horizon, acts[b]) for b in range(B)]
+    q0 = eng.initial_q() if scn.agent_rules else None   # rules that do not apply sit in their disabled state
+    outs = [orc.replay(cfg, states[b], flags[b], horizon, acts[b], q0=q0) for b in range(B)]
     return tr, outs, batch
 
 
@@ -380,3 +381,38 @@ def test_rollout_with_root_stats_in_one_call(built):
     eng.rollout(d_leaves, n, seed=11, max_steps=12, out=d_out, first_action=d_first, stats=d_stats)
     torch.cuda.synchronize()
     assert np.array_equal(d_stats.cpu().numpy(), want)
+
+
+def test_agent_rule_masks_match_oracle(built, orc):
+    """Rules given to some agents only (BehaviorRulesMcts::AddAgentRules): the slots of rules that do
+    not apply to an agent start in the rule's absorbing `disabled_state`, stay there and earn
+    nothing -- replay and rollouts against the oracle from the same initial automaton states."""
+    scn = scenarios.merge_scenario()
+    scn.agent_rules = [[0, 1], [0], [1], []]          # ego: both rules, agent 3: none
+    eng = brm.RulesMctsEngine([scn], device=0)
+    rng = np.random.default_rng(21)
+    B, T = 64, 20
+    acts = rng.integers(0, 3, size=(B, T, scn.n_mcts_agents)).astype(np.uint8)
+    tr, outs, _ = replay_both(eng, orc, scn, acts)
+    compared = sum(compare_trace(tr, b, o, scn) for b, o in enumerate(outs))
+    assert compared >= 0.9 * sum(o["steps"] for o in outs)
+    q0 = eng.initial_q()
+    R0 = 1                                             # slot 0: safe distance, slots 1..3: zipper per other agent
+    ran = np.arange(T)[None, :] < tr["steps_out"][:, None]        # steps a replay executed before it ended
+    assert (tr["q_out"][:, :, 1, R0:][ran] == q0[1, R0:]).all()   # agent 1 has no zipper rule
+    assert (tr["q_out"][:, :, 2, :R0][ran] == q0[2, :R0]).all()   # agent 2 has no safe-distance rule
+    assert (tr["q_out"][:, :, 3][ran] == q0[3]).all() and (tr["viol_out"][:, :, 3] == 0).all()
+    assert (q0[3] == [r.disabled_state for r in (scn.rules[0], scn.rules[1], scn.rules[1], scn.rules[1])]).all()
+    # against the same world with every rule for everybody, the masks do change the outcome
+    eng_all = brm.RulesMctsEngine([scenarios.merge_scenario()], device=0)
+    tr_all = eng_all.replay(eng_all.make_batch(np.broadcast_to(scn.initial_state, (B, 4, 4))), acts)
+    assert (tr_all["viol_out"][:, :, 3].sum() > 0) or (tr_all["q_out"][:, :, 3] != q0[3]).any()
+    # rollouts: per-rollout outputs against the oracle
+    leaves = eng.initial_batch([0])
+    out = eng.rollout(leaves, 48, seed=4, max_steps=12, detail=True)
+    ref = orc.rollout_detail(oracle_config(scn), scn.initial_state, FL(4), scn.params.HORIZON, 4, 0, 48, 12,
+                             scn.params.DISCOUNT_FACTOR, q0=q0)
+    safe = ref["margin"] >= GUARD
+    assert safe.sum() >= 24
+    assert np.array_equal(out["ro_q"][safe], ref["q"][safe]) and np.array_equal(out["ro_viol"][safe], ref["viol"][safe])
+    np.testing.assert_allclose(out["ro_returns"][safe], ref["returns"][safe], rtol=1e-5, atol=2e-4)

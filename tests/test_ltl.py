@@ -80,7 +80,10 @@ def test_rule_packs_into_abi():
     r = brm.RuleMonitor.MakeRule(brm.ZIP_FORMULA, -1.0, 1)
     from planner_rules_mcts_b200.gridworld import GW_LABELS
     abi = r.to_abi(GW_LABELS)
-    assert abi.n_aps == 3 and abi.n_states == 4 and abi.priority == 1 and abi.weight == -1.0
+    # 4 automaton states + the absorbing, accepting "rule does not apply" state behind them
+    assert abi.n_aps == 3 and abi.n_states == 5 and abi.priority == 1 and abi.weight == -1.0
+    assert r.disabled_state == 4 and abi.accepting[4] == 1
+    assert all(abi.trans[4 * 8 + l] == 4 for l in range(8))
     assert list(abi.ap_label[:3]) == [3, 1, 2] and list(abi.ap_agent_specific[:3]) == [1, 0, 1]
     with pytest.raises(KeyError):
         brm.RuleMonitor.MakeRule("G !nonsense", -1, 0).to_abi(GW_LABELS)
