@@ -10,7 +10,6 @@ the single-state view with the StateInterface member names.  All arithmetic runs
 libbrm.so on the GPU.
 """
 import ctypes as C
-import math
 from dataclasses import dataclass, field
 from typing import List, Optional
 

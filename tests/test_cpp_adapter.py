@@ -1,6 +1,5 @@
 """include/brm_state.hpp: the C++ StateInterface adapter compiles against the C ABI, refuses
 to run without a GPU, and on a GPU reproduces what the Python mirror computes."""
-import ctypes
 import os
 import subprocess
 
@@ -9,7 +8,6 @@ import pytest
 
 import planner_rules_mcts_b200 as brm
 from planner_rules_mcts_b200 import _abi, scenarios
-from planner_rules_mcts_b200.continuous import CW_LABELS
 from planner_rules_mcts_b200.gridworld import GW_LABELS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -8,7 +8,6 @@ import pytest
 
 from oracle import cw as ocw
 from planner_rules_mcts_b200 import scenarios
-from planner_rules_mcts_b200.ltl import RuleMonitor
 from tests.cw_common import oracle_config
 
 FL = lambda n: np.full(n, ocw.PRESENT | ocw.VALID, np.uint8)
