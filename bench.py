@@ -126,7 +126,7 @@ def build_workload(kind, device, rank, cuda_stream=None):
         leaves = eng.initial_batch()
         first = np.zeros((L, eng.M), np.uint8)
         w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
-                 gamma=0.9, dtype="f32", state_bytes=16, scn=scns)
+                 gamma=0.9, dtype="f64", state_bytes=32, scn=scns)
         return w
     scn = scenarios.merge_scenario(seed=1000) if kind in ("M", "R") else scenarios.highway_scenario(seed=1000)
     eng = brm.RulesMctsEngine([scn], device=device, cuda_stream=cuda_stream)
@@ -141,7 +141,7 @@ def build_workload(kind, device, rank, cuda_stream=None):
     if len(bad):
         leaves, _ = eng.execute(root, first.T.copy())
     w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=n_act,
-             gamma=scn.params.DISCOUNT_FACTOR, dtype="f32", state_bytes=16, scn=[scn])
+             gamma=scn.params.DISCOUNT_FACTOR, dtype="f64", state_bytes=32, scn=[scn])
     return w
 
 
@@ -250,7 +250,7 @@ def reference_workload(kind):
     A = len(scn.agents)
     lv = _HostLeaves()
     lv.scenario = np.zeros(1, np.int32)
-    lv.agents = scn.initial_state[:, None, :].astype(np.float32).copy()
+    lv.agents = scn.initial_state[:, None, :].astype(np.float64).copy()
     lv.flags = np.full((A, 1), 3, np.uint8)
     lv.horizon = np.array([scn.params.HORIZON], np.int32)
     M = scn.n_mcts_agents
@@ -443,7 +443,8 @@ def run_gpu(args):
         # algorithmic bytes of one rollout launch (rollout mode): every rollout
         # reads its leaf state + rule states + Philox key/counter and writes returns and
         # violation counters; lane polylines / automaton tables are staged once per CTA
-        bytes_per_rollout = A * (17 + R) + 16 + M * (4 * V + 4 * R)
+        sb = w["state_bytes"]
+        bytes_per_rollout = A * (sb + 1 + R) + 16 + M * ((sb // 4) * V + 4 * R)
         algo_bytes = rollouts_per_step * bytes_per_rollout * args.steps
         hbm_achieved = algo_bytes / kern_s / 1e9
         sm_mhz = clocks.get("sm_mhz") or info["sm_clock_khz"] / 1e3

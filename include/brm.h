@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BRM_ABI_VERSION 2
+#define BRM_ABI_VERSION 3
 
 #define BRM_OK 0
 #define BRM_ERR_INVALID (-1)
@@ -63,6 +63,11 @@ int brm_create(int device, void* cuda_stream, brm_engine** out);
 void brm_destroy(brm_engine* e);
 const char* brm_last_error(void);
 int brm_abi_version(void);
+/* sizeof of the ABI's structs as this library was compiled, in the order: brm_rule,
+ * brm_rollout_params, brm_gw_params, brm_gw_states, brm_cw_params, brm_cw_agent, brm_cw_lane,
+ * brm_cw_scenario, brm_cw_states, brm_cw_rollout_out, brm_cw_trace.  Fills up to n entries and
+ * returns the number there are -- lets a foreign-language binding check its own layouts. */
+int brm_abi_struct_sizes(int32_t* out, int32_t n);
 /* Block until everything enqueued on the engine's stream has finished. */
 int brm_synchronize(brm_engine* e);
 /* Number of kernels this engine has launched since creation (bench `gpu_launches`). */
@@ -267,56 +272,65 @@ int brm_gw_replay(brm_engine* e, const brm_gw_states* s0, const uint8_t* actions
 
 /* mirrors RulesMctsStateParameters (src/rules_mcts_state_parameters.hpp:33-46, defaults
  * src/rules_mcts_state_parameters.cpp:36-78) plus the dynamics / label constants that
- * live in bark's parameter server. */
+ * live in bark's parameter server.  Doubles, like the reference's members: the device
+ * computes the continuous world in FP64 (labels / automaton states / violation counts must
+ * equal the reference's double arithmetic bit for bit). */
 typedef struct {
-  float collision_weight;            /* 0     */
-  float out_of_map_weight;           /* -800  */
-  float potential_weight;            /* 32    */
-  float acceleration_weight;         /* 0     */
-  float radial_acceleration_weight;  /* 0     */
-  float desired_velocity_weight;     /* -5    */
-  float lane_center_weight;          /* 0     */
-  float prediction_time_span;        /* 0.3   */
-  float desired_velocity;            /* 10    */
-  float discount_factor;             /* 0.9 (used by PotentialReward, :250-257) */
-  float goal_reward;                 /* 0     */
-  int32_t reward_vector_size;        /* 1     */
-  int32_t horizon;                   /* 30    */
+  double collision_weight;            /* 0     */
+  double out_of_map_weight;           /* -800  */
+  double potential_weight;            /* 32    */
+  double acceleration_weight;         /* 0     */
+  double radial_acceleration_weight;  /* 0     */
+  double desired_velocity_weight;     /* -5    */
+  double lane_center_weight;          /* 0     */
+  double prediction_time_span;        /* 0.3   */
+  double desired_velocity;            /* 10    */
+  double discount_factor;             /* 0.9 (used by PotentialReward, :250-257) */
+  double goal_reward;                 /* 0     */
+  int32_t reward_vector_size;         /* 1     */
+  int32_t horizon;                    /* 30    */
   int32_t use_rule_reward_for_ego_only; /* false */
-  float wheel_base;                  /* 2.7   SingleTrackModel */
-  float integration_time_delta;      /* 0.02  BehaviorMotionPrimitives::IntegrationTimeDelta */
-  float sd_reaction_time;            /* safe-distance label: reaction time delta        */
-  float sd_max_decel_rear;           /* |a_r|                                           */
-  float sd_max_decel_front;          /* |a_f|                                           */
-  float near_distance;               /* near_x#j: centre distance below this            */
+  int32_t remove_agents_out_of_map;   /* bark "World::remove_agents_out_of_map" (false): agents whose
+                                         shape leaves the road polygon are removed by Predict; an MCTS
+                                         agent that vanished earns OUT_OF_MAP_WEIGHT (:121-125) */
+  double wheel_base;                  /* 2.7   SingleTrackModel */
+  double integration_time_delta;      /* 0.02  BehaviorMotionPrimitives::IntegrationTimeDelta */
+  double sd_reaction_time;            /* safe-distance label: reaction time delta        */
+  double sd_max_decel_rear;           /* |a_r|                                           */
+  double sd_max_decel_front;          /* |a_f|                                           */
+  double near_distance;               /* near_x#j: centre distance below this            */
 } brm_cw_params;
 
 typedef struct {
-  float front, rear, half_width; /* rectangle [-rear, front] x [-half_width, half_width] around the pose */
+  double front, rear, half_width; /* rectangle [-rear, front] x [-half_width, half_width] around the pose */
+  double goal[6];                 /* xmin, xmax, ymin, ymax, theta_lo, theta_hi */
   int32_t has_goal;
-  float goal[6];                 /* xmin, xmax, ymin, ymax, theta_lo, theta_hi */
-  int32_t n_prims;               /* motion primitives; agents outside the MCTS agent list use primitive 0 */
-  float prim_acc[BRM_CW_MAX_PRIMS];
-  float prim_delta[BRM_CW_MAX_PRIMS];
+  int32_t n_prims;                /* motion primitives; agents outside the MCTS agent list use primitive 0 */
+  double prim_acc[BRM_CW_MAX_PRIMS];
+  double prim_delta[BRM_CW_MAX_PRIMS];
 } brm_cw_agent;
 
 typedef struct {
   int32_t n_pts;
   int32_t successor; /* lane that continues this one (-1: none) */
   int32_t flags;     /* bit0: rightmost lane */
-  float half_width;
-  float s_point;     /* arc length of the merge point on this lane (beyond-point labels) */
-  float pts[BRM_CW_MAX_PTS][2];
+  int32_t _pad;
+  double half_width;
+  double s_point;    /* arc length of the merge point on this lane (beyond-point labels) */
+  double pts[BRM_CW_MAX_PTS][2];
 } brm_cw_lane;
 
 /* One scenario.  Agents 0..n_mcts_agents-1 are the MCTS agents (ego = 0; the reference's
- * agent_idx list, src/behavior_rules_mcts.hpp:392-414); the rest are simulated only. */
+ * agent_idx list, src/behavior_rules_mcts.hpp:392-414); the rest are simulated only.
+ * Coordinates must lie within +-BRM_CW_MAX_COORD metres (the fp32 culling boxes of the lane
+ * projection are grown for the rounding of such coordinates). */
+#define BRM_CW_MAX_COORD 4096.0
 typedef struct {
   brm_cw_params params;
-  int32_t n_agents, n_mcts_agents, n_lanes, n_road, n_rules;
+  int32_t n_agents, n_mcts_agents, n_lanes, n_road, n_rules, _pad;
   brm_cw_agent agents[BRM_CW_MAX_AGENTS];
   brm_cw_lane lanes[BRM_CW_MAX_LANES];
-  float road[BRM_CW_MAX_ROAD][2];
+  double road[BRM_CW_MAX_ROAD][2];
   brm_rule rules[BRM_MAX_RULES]; /* common rules of every MCTS agent */
 } brm_cw_scenario;
 
@@ -326,7 +340,8 @@ typedef struct {
 
 /* A batch of n states of scenarios (MvmctsState members, src/rules_mcts_state.hpp:80-87).
  *   scenario [n]        index of the uploaded scenario each state lives in
- *   agents   [A][n][4]  float (x, y, theta, v): one 16-byte vector per agent
+ *   agents   [A][n][4]  double (x, y, theta, v): two 16-byte vectors per agent, consecutive
+ *                       states consecutive in memory (bark State [t, x, y, theta, v] without t)
  *   flags    [A][n]     BRM_CW_PRESENT | BRM_CW_VALID
  *   horizon  [n]        remaining horizon_
  *   terminal [n]        is_terminal_state_ (CheckTerminal, :266-285; fill with brm_cw_check_terminal)
@@ -335,7 +350,7 @@ typedef struct {
   int32_t n;
   int32_t mem;
   int32_t* scenario;
-  float* agents;
+  double* agents;
   uint8_t* flags;
   int32_t* horizon;
   uint8_t* terminal;
@@ -350,35 +365,36 @@ int32_t brm_cw_rules_per_agent(const brm_engine* e);
 
 /* MvmctsState ctor's CheckTerminal (:52, :266-285): fills s->terminal. */
 int brm_cw_check_terminal(brm_engine* e, brm_cw_states* s);
-/* MvmctsState::Execute (:57-128): actions [M][n] uint8, rewards [M][V][n] float.
+/* MvmctsState::Execute (:57-128): actions [M][n] uint8, rewards [M][V][n] double (the
+ * reference's Reward is an Eigen::VectorXd).
  * BRM_MEM_HOST batches are checked first: BRM_ERR_TERMINAL if any state is terminal (:59). */
 int brm_cw_execute(brm_engine* e, const brm_cw_states* in, const uint8_t* actions,
-                   brm_cw_states* out, float* rewards);
+                   brm_cw_states* out, double* rewards);
 /* MvmctsState::EvaluateRules() (:186-197), the call BehaviorRulesMcts::Plan makes on the root
  * state to carry the automata from the last planning step to the current world
  * (src/behavior_rules_mcts.hpp:211-214): labels of the states as they are, one transition per
  * rule state of every MCTS agent that is present and VALID.  `out` = `in` with the new automaton
- * states (and violation counters); rewards [M][V][n] float = the rule penalties only. */
-int brm_cw_evaluate_rules(brm_engine* e, const brm_cw_states* in, brm_cw_states* out, float* rewards);
+ * states (and violation counters); rewards [M][V][n] double = the rule penalties only. */
+int brm_cw_evaluate_rules(brm_engine* e, const brm_cw_states* in, brm_cw_states* out, double* rewards);
 /* MvmctsState::GetNumActions (:129-141): out [M][n] */
 int brm_cw_get_num_actions(brm_engine* e, const brm_cw_states* s, uint8_t* out);
-/* MvmctsState::GetTerminalReward (:148-164): out [M][V][n] float */
-int brm_cw_terminal_reward(brm_engine* e, const brm_cw_states* s, float* out);
+/* MvmctsState::GetTerminalReward (:148-164): out [M][V][n] double */
+int brm_cw_terminal_reward(brm_engine* e, const brm_cw_states* s, double* out);
 
 /* mvmcts::RandomHeuristic over MvmctsState (instantiated at
  * src/behavior_rules_mcts.hpp:188-189), fused on the device (K3 rules_rollout):
  *   returns_sum [n][M][V] double, viol_sum [n][M][R] uint64, agent_steps [n] uint64
  *   (agents integrated: present and VALID, MCTS or not).
- * Optional per-rollout outputs: ro_returns [N][M][V] float, ro_viol [N][M][R] uint8,
- * ro_q [N][M][R] uint8, ro_agents [N][A][4] float, ro_flags [N][A] uint8, ro_steps [N] int32. */
+ * Optional per-rollout outputs: ro_returns [N][M][V] double, ro_viol [N][M][R] uint8,
+ * ro_q [N][M][R] uint8, ro_agents [N][A][4] double, ro_flags [N][A] uint8, ro_steps [N] int32. */
 typedef struct {
   double* returns_sum;
   uint64_t* viol_sum;
   uint64_t* agent_steps;
-  float* ro_returns;
+  double* ro_returns;
   uint8_t* ro_viol;
   uint8_t* ro_q;
-  float* ro_agents;
+  double* ro_agents;
   uint8_t* ro_flags;
   int32_t* ro_steps;
 } brm_cw_rollout_out;
@@ -387,21 +403,21 @@ int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout
                    const brm_cw_rollout_out* out);
 
 /* Replay of given action sequences with a full trace (K6): actions [B][T][M];
- *   agents_out [B][T][A][4] float, flags_out [B][T][A], terminal_out [B][T],
- *   q_out [B][T][M][R], viol_out [B][T][M][R] uint32, rewards_out [B][T][M][V] float,
+ *   agents_out [B][T][A][4] double, flags_out [B][T][A], terminal_out [B][T],
+ *   q_out [B][T][M][R], viol_out [B][T][M][R] uint32, rewards_out [B][T][M][V] double,
  *   labels_out [B][T][M][4] uint32 (word 0: ego bits by label kind; words 1..3: masks over j
- *   for kinds 8, 9, 10), frenet_out [B][T][A][3] float (lane, s, lat),
- *   term_reward_out [B][M][V] float, steps_out [B]. */
+ *   for kinds 8, 9, 10), frenet_out [B][T][A][3] double (lane, s, lat),
+ *   term_reward_out [B][M][V] double, steps_out [B]. */
 typedef struct {
-  float* agents_out;
+  double* agents_out;
   uint8_t* flags_out;
   uint8_t* terminal_out;
   uint8_t* q_out;
   uint32_t* viol_out;
-  float* rewards_out;
+  double* rewards_out;
   uint32_t* labels_out;
-  float* frenet_out;
-  float* term_reward_out;
+  double* frenet_out;
+  double* term_reward_out;
   int32_t* steps_out;
 } brm_cw_trace;
 

@@ -231,7 +231,7 @@ class MvmctsState {
 
   // agents: A x (x, y, theta, v); flags: A; q: M x R.  The constructor runs CheckTerminal
   // like the reference's (src/rules_mcts_state.cpp:52).
-  MvmctsState(std::shared_ptr<RulesMctsContext> ctx, int32_t scenario, std::vector<float> agents,
+  MvmctsState(std::shared_ptr<RulesMctsContext> ctx, int32_t scenario, std::vector<double> agents,
               std::vector<uint8_t> flags, int32_t horizon, std::vector<uint8_t> q)
       : ctx_(std::move(ctx)), scenario_(scenario), agents_(std::move(agents)), flags_(std::move(flags)),
         horizon_(horizon), terminal_(0), q_(std::move(q)) {
@@ -247,7 +247,7 @@ class MvmctsState {
     std::vector<uint8_t> act(M);
     for (int a = 0; a < M; ++a) act[a] = static_cast<uint8_t>(joint_action.at(a));
     auto next = std::make_shared<MvmctsState>(*this);  // copy: Execute fills it, incl. the terminal flag
-    std::vector<float> rew(static_cast<size_t>(M) * V);
+    std::vector<double> rew(static_cast<size_t>(M) * V);
     std::vector<uint32_t> viol_out(static_cast<size_t>(M) * R, 0);
     brm_cw_states in = view(const_cast<MvmctsState*>(this), nullptr);
     brm_cw_states out = view(next.get(), viol_out.data());
@@ -263,7 +263,7 @@ class MvmctsState {
   std::vector<Reward> EvaluateRules() {
     const int M = ctx_->M, V = ctx_->V, R = ctx_->R;
     MvmctsState next(*this);
-    std::vector<float> rew(static_cast<size_t>(M) * V);
+    std::vector<double> rew(static_cast<size_t>(M) * V);
     std::vector<uint32_t> viol_out(static_cast<size_t>(M) * R, 0);
     brm_cw_states in = view(this, nullptr);
     brm_cw_states out = view(&next, viol_out.data());
@@ -288,7 +288,7 @@ class MvmctsState {
   std::string PrintState() const { return std::string(); }  // :146
   std::vector<Reward> GetTerminalReward() const {
     const int M = ctx_->M, V = ctx_->V;
-    std::vector<float> out(static_cast<size_t>(M) * V);
+    std::vector<double> out(static_cast<size_t>(M) * V);
     brm_cw_states s = view(const_cast<MvmctsState*>(this), nullptr);
     check(brm_cw_terminal_reward(ctx_->engine->get(), &s, out.data()));
     std::vector<Reward> r(M, Reward(V, 0.0));
@@ -296,7 +296,7 @@ class MvmctsState {
       for (int v = 0; v < V; ++v) r[a][v] = out[static_cast<size_t>(a) * V + v];
     return r;
   }
-  const std::vector<float>& GetAgentStates() const { return agents_; }
+  const std::vector<double>& GetAgentStates() const { return agents_; }
   const std::vector<uint8_t>& GetMultiAgentRuleState() const { return q_; }
   const std::shared_ptr<RulesMctsContext>& Context() const { return ctx_; }
 
@@ -317,7 +317,7 @@ class MvmctsState {
   }
   std::shared_ptr<RulesMctsContext> ctx_;
   int32_t scenario_;
-  std::vector<float> agents_;
+  std::vector<double> agents_;
   std::vector<uint8_t> flags_;
   int32_t horizon_;
   uint8_t terminal_;
@@ -339,7 +339,7 @@ class RulesMctsRolloutEvaluator {
     const int A = ctx_->A, M = ctx_->M, V = ctx_->V, R = ctx_->R;
     const size_t L = leaves.size();
     std::vector<int32_t> scenario(L), horizon(L);
-    std::vector<float> agents(static_cast<size_t>(A) * L * 4);
+    std::vector<double> agents(static_cast<size_t>(A) * L * 4);
     std::vector<uint8_t> flags(static_cast<size_t>(A) * L), terminal(L), q(static_cast<size_t>(M) * R * L);
     for (size_t l = 0; l < L; ++l) {
       const MvmctsState& s = *leaves[l];
@@ -347,7 +347,7 @@ class RulesMctsRolloutEvaluator {
       horizon[l] = s.horizon_;
       terminal[l] = s.terminal_;
       for (int a = 0; a < A; ++a) {
-        std::memcpy(&agents[(static_cast<size_t>(a) * L + l) * 4], &s.agents_[4 * a], 4 * sizeof(float));
+        std::memcpy(&agents[(static_cast<size_t>(a) * L + l) * 4], &s.agents_[4 * a], 4 * sizeof(double));
         flags[static_cast<size_t>(a) * L + l] = s.flags_[a];
       }
       for (int a = 0; a < M; ++a)

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE -- CPU restatement of the continuous-world hot path (see the
 // header of oracle/cw_oracle.h for scope, citations and the "parity unpinned" note).
-// Not part of the product.  Compiled with -ffp-contract=off so that the float
-// instantiation rounds every operation separately.
+// Not part of the product.  All arithmetic in double, the reference's type; compiled with
+// -ffp-contract=off so that every operation rounds separately.
 #include "oracle/cw_oracle.h"
 
 #include <algorithm>
@@ -84,25 +84,25 @@ struct World {
     V = c->reward_vector_size;
     Slot s[CWO_MAX_SLOTS];
     R = M > 0 ? build_slots(*c, 0, s) : 0;
-    // every parameter is first rounded to float: the engine's ABI carries float32
-    // parameters, so both sides compute with the same constants
-    dt = static_cast<T>(static_cast<float>(c->prediction_time_span));
+    // parameters are used as the doubles they are (the reference computes in double
+    // throughout, src/rules_mcts_state.cpp:204-264)
+    dt = static_cast<T>(c->prediction_time_span);
     // BehaviorMPContinuousActions::Plan (bark, un-vendored): ceil(dt / integration_dt)
     // explicit-Euler sub-steps, the last one takes the remainder.
     n_sub = static_cast<int>(std::ceil(c->prediction_time_span / c->integration_time_delta - 1e-9));
     if (n_sub < 1) n_sub = 1;
-    h_sub = static_cast<T>(static_cast<float>(c->integration_time_delta));
-    h_last = static_cast<T>(static_cast<float>(c->prediction_time_span -
-                                               (n_sub - 1) * c->integration_time_delta));
+    h_sub = static_cast<T>(c->integration_time_delta);
+    h_last = static_cast<T>(c->prediction_time_span -
+                                               (n_sub - 1) * c->integration_time_delta);
     for (int l = 0; l < c->n_lanes; ++l) {
       const cwo_lane& L = c->lanes[l];
       T s0 = 0;
       for (int k = 0; k + 1 < L.n_pts; ++k) {
         Seg g;
-        g.x0 = static_cast<T>(static_cast<float>(L.pts[k][0]));
-        g.y0 = static_cast<T>(static_cast<float>(L.pts[k][1]));
-        const T x1 = static_cast<T>(static_cast<float>(L.pts[k + 1][0]));
-        const T y1 = static_cast<T>(static_cast<float>(L.pts[k + 1][1]));
+        g.x0 = static_cast<T>(L.pts[k][0]);
+        g.y0 = static_cast<T>(L.pts[k][1]);
+        const T x1 = static_cast<T>(L.pts[k + 1][0]);
+        const T y1 = static_cast<T>(L.pts[k + 1][1]);
         g.dx = x1 - g.x0;
         g.dy = y1 - g.y0;
         const T l2 = g.dx * g.dx + g.dy * g.dy;
@@ -117,10 +117,10 @@ struct World {
     for (int e = 0; e < c->n_road; ++e) {
       const int f = (e + 1) % c->n_road;
       Edge g;
-      g.xa = static_cast<T>(static_cast<float>(c->road[e][0]));
-      g.ya = static_cast<T>(static_cast<float>(c->road[e][1]));
-      const T xb = static_cast<T>(static_cast<float>(c->road[f][0]));
-      g.yb = static_cast<T>(static_cast<float>(c->road[f][1]));
+      g.xa = static_cast<T>(c->road[e][0]);
+      g.ya = static_cast<T>(c->road[e][1]);
+      const T xb = static_cast<T>(c->road[f][0]);
+      g.yb = static_cast<T>(c->road[f][1]);
       g.m = (g.yb != g.ya) ? (xb - g.xa) / (g.yb - g.ya) : T(0);
       edges.push_back(g);
     }
@@ -140,15 +140,15 @@ struct World {
     if (m < margin) margin = m;
   }
 
-  T front(int i) const { return static_cast<T>(static_cast<float>(c->agents[i].front)); }
-  T rear(int i) const { return static_cast<T>(static_cast<float>(c->agents[i].rear)); }
-  T hw(int i) const { return static_cast<T>(static_cast<float>(c->agents[i].half_width)); }
+  T front(int i) const { return static_cast<T>(c->agents[i].front); }
+  T rear(int i) const { return static_cast<T>(c->agents[i].rear); }
+  T hw(int i) const { return static_cast<T>(c->agents[i].half_width); }
 
   // ---- single-track kinematics, explicit Euler sub-steps (bark SingleTrackModel:
   //      x' = v cos(theta), y' = v sin(theta), theta' = v tan(delta) / wheel_base, v' = a)
   void integrate(State<T>& s, int i, int prim) const {
-    const T a = static_cast<T>(static_cast<float>(c->agents[i].prim_acc[prim]));
-    const T k = static_cast<T>(static_cast<float>(kappa[i][prim]));
+    const T a = static_cast<T>(c->agents[i].prim_acc[prim]);
+    const T k = static_cast<T>(kappa[i][prim]);
     T x = s.x[i], y = s.y[i], th = s.th[i], v = s.v[i];
     for (int n = 0; n < n_sub; ++n) {
       const T h = (n == n_sub - 1) ? h_last : h_sub;
@@ -185,7 +185,7 @@ struct World {
           bcross = g.dx * wy - g.dy * wx;
         }
       }
-      const T hwl = static_cast<T>(static_cast<float>(c->lanes[l].half_width));
+      const T hwl = static_cast<T>(c->lanes[l].half_width);
       const bool interior = !(bk == 0 && lt(btu, T(0))) && !(bk == ns - 1 && gt(btu, T(1)));
       if (interior && le(best, hwl * hwl)) {
         out.lane = l;
@@ -272,12 +272,12 @@ struct World {
     T cx[4], cy[4];
     corners(s, i, cx, cy);
     bool in = true;
-    const T g0 = static_cast<T>(static_cast<float>(ag.goal[0])), g1 = static_cast<T>(static_cast<float>(ag.goal[1]));
-    const T g2 = static_cast<T>(static_cast<float>(ag.goal[2])), g3 = static_cast<T>(static_cast<float>(ag.goal[3]));
+    const T g0 = static_cast<T>(ag.goal[0]), g1 = static_cast<T>(ag.goal[1]);
+    const T g2 = static_cast<T>(ag.goal[2]), g3 = static_cast<T>(ag.goal[3]);
     for (int k = 0; k < 4; ++k)
       in = ge(cx[k], g0) && le(cx[k], g1) && ge(cy[k], g2) && le(cy[k], g3) && in;
-    in = ge(s.th[i], static_cast<T>(static_cast<float>(ag.goal[4]))) &&
-         le(s.th[i], static_cast<T>(static_cast<float>(ag.goal[5]))) && in;
+    in = ge(s.th[i], static_cast<T>(ag.goal[4])) &&
+         le(s.th[i], static_cast<T>(ag.goal[5])) && in;
     return in;
   }
 
@@ -322,21 +322,21 @@ struct World {
     if (jf >= 0) {
       const T dist = gf - (front(i) + rear(jf));
       const T vr = s.v[i], vf = s.v[jf];
-      const T delta = static_cast<T>(static_cast<float>(c->sd_reaction_time));
-      const T ar = static_cast<T>(static_cast<float>(1.0 / (2.0 * std::fabs(c->sd_max_decel_rear))));
-      const T af = static_cast<T>(static_cast<float>(1.0 / (2.0 * std::fabs(c->sd_max_decel_front))));
+      const T delta = static_cast<T>(c->sd_reaction_time);
+      const T ar = static_cast<T>(1.0 / (2.0 * std::fabs(c->sd_max_decel_rear)));
+      const T af = static_cast<T>(1.0 / (2.0 * std::fabs(c->sd_max_decel_front)));
       const T dsafe = vr * delta + (vr * vr) * ar - (vf * vf) * af;
       safe = ge(dist, dsafe);
     }
     if (safe) w[0] |= 1u << CWO_LABEL_SAFE_DISTANCE_FRONT;
     auto beyond = [&](int k) {
       if (f[k].lane < 0) return false;
-      return ge(f[k].s, static_cast<T>(static_cast<float>(c->lanes[f[k].lane].s_point)));
+      return ge(f[k].s, static_cast<T>(c->lanes[f[k].lane].s_point));
     };
     if (beyond(i)) w[0] |= 1u << CWO_LABEL_MERGED_E;
     if (f[i].lane >= 0 && (c->lanes[f[i].lane].flags & 1)) w[0] |= 1u << CWO_LABEL_RIGHTMOST_LANE;
     if (f[i].lane >= 0) w[0] |= 1u << CWO_LABEL_ON_ROAD;
-    const T nd = static_cast<T>(static_cast<float>(c->near_distance));
+    const T nd = static_cast<T>(c->near_distance);
     for (int j = 0; j < A; ++j) {
       if (j == i || !(s.flags[j] & CWO_PRESENT)) continue;
       if (beyond(j)) w[1] |= 1u << j;
@@ -389,14 +389,20 @@ struct World {
       if (agent_steps) ++*agent_steps;
     }
     out.horizon = in.horizon - 1;
+    // World::Step -> RemoveInvalidAgents (bark, un-vendored; parameter
+    // "World::remove_agents_out_of_map", default false): agents whose shape is no longer
+    // within the road polygon leave the world
+    if (c->remove_agents_out_of_map)
+      for (int i = 0; i < A; ++i)
+        if ((out.flags[i] & CWO_PRESENT) && out_of_map(out, i)) out.flags[i] = 0;
     Frenet<T> f[CWO_MAX_AGENTS];
     for (int i = 0; i < A; ++i) {
       f[i].lane = -1; f[i].s = 0; f[i].lat = 0;
       if (out.flags[i] & CWO_PRESENT) f[i] = frenet(out, i);
       if (frenet_out) frenet_out[i] = f[i];
     }
-    const T gamma = static_cast<T>(static_cast<float>(c->discount_factor));
-    const T vdes = static_cast<T>(static_cast<float>(c->desired_velocity));
+    const T gamma = static_cast<T>(c->discount_factor);
+    const T vdes = static_cast<T>(c->desired_velocity);
     bool ego_coll = false, ego_oom = false, ego_goal = false;
     for (int ai = 0; ai < M; ++ai) {
       T* r = rewards + ai * V;
@@ -407,25 +413,25 @@ struct World {
         const bool oom = out_of_map(out, ai);
         const bool goal = at_goal(out, ai);
         if (ai == 0) { ego_coll = coll; ego_oom = oom; ego_goal = goal; }
-        r[0] += (coll ? T(1) : T(0)) * static_cast<T>(static_cast<float>(c->collision_weight));   // :91-92
-        r[0] += (oom ? T(1) : T(0)) * static_cast<T>(static_cast<float>(c->out_of_map_weight));   // :94-96
+        r[0] += (coll ? T(1) : T(0)) * static_cast<T>(c->collision_weight);   // :91-92
+        r[0] += (oom ? T(1) : T(0)) * static_cast<T>(c->out_of_map_weight);   // :94-96
         // GetActionCost (:202-248)
         {
           const T a = (out.v[ai] - in.v[ai]) / dt;
-          T cost = static_cast<T>(static_cast<float>(c->acceleration_weight)) * a * a * dt;
+          T cost = static_cast<T>(c->acceleration_weight) * a * a * dt;
           const T theta_dot = (out.th[ai] - in.th[ai]) / dt;
           const T avg_vel = T(0.5) * a * dt + in.v[ai];
           const T a_lat = theta_dot * avg_vel;
-          cost += static_cast<T>(static_cast<float>(c->radial_acceleration_weight)) * a_lat * a_lat * dt;
-          cost += static_cast<T>(static_cast<float>(c->desired_velocity_weight)) *
+          cost += static_cast<T>(c->radial_acceleration_weight) * a_lat * a_lat * dt;
+          cost += static_cast<T>(c->desired_velocity_weight) *
                   std::fabs(in.v[ai] - vdes) * dt;
           if (f[ai].lane >= 0)
-            cost += static_cast<T>(static_cast<float>(c->lane_center_weight)) * std::fabs(f[ai].lat) * dt;
+            cost += static_cast<T>(c->lane_center_weight) * std::fabs(f[ai].lat) * dt;
           r[V - 1] += cost;
         }
         // PotentialReward (:250-264)
         {
-          const T pw = static_cast<T>(static_cast<float>(c->potential_weight));
+          const T pw = static_cast<T>(c->potential_weight);
           const T pot_new = -pw * dt * std::fabs(out.v[ai] - vdes);
           const T pot_cur = -pw * dt * std::fabs(in.v[ai] - vdes);
           r[V - 1] += gamma * pot_new - pot_cur;
@@ -439,8 +445,10 @@ struct World {
             rr[c->rules[slots[k].rule].priority] += rule_step(slots[k], w, &out.q[ai][k], &out.viol[ai][k]);
           for (int v = 0; v < V; ++v) r[v] += rr[v];
         }
-        if (goal) r[V - 1] += static_cast<T>(static_cast<float>(c->goal_reward));  // :110-113
+        if (goal) r[V - 1] += static_cast<T>(c->goal_reward);  // :110-113
         if (coll) out.flags[ai] &= static_cast<uint8_t>(~CWO_VALID);               // :116-120
+      } else if ((in.flags[ai] & CWO_PRESENT) && !(out.flags[ai] & CWO_PRESENT)) {
+        r[0] += static_cast<T>(c->out_of_map_weight);  // left the map during this step, :121-125
       }
       if (labels_out) std::memcpy(labels_out + ai * 4, w, sizeof(w));
     }
@@ -452,6 +460,32 @@ struct World {
       out.terminal = (out.horizon == 0) || ego_oom || ego_coll || ego_goal;
     } else {
       out.terminal = check_terminal(out);
+    }
+  }
+
+  // MvmctsState::EvaluateRules() (:186-197): labels of the state as it is, one transition per
+  // rule state of every MCTS agent that is present and VALID; no other reward term
+  void evaluate_rules(State<T>& s, T* rewards, uint32_t* labels_out) {
+    Frenet<T> f[CWO_MAX_AGENTS];
+    for (int i = 0; i < A; ++i) {
+      f[i].lane = -1; f[i].s = 0; f[i].lat = 0;
+      if (s.flags[i] & CWO_PRESENT) f[i] = frenet(s, i);
+    }
+    for (int ai = 0; ai < M; ++ai) {
+      T* r = rewards + ai * V;
+      for (int v = 0; v < V; ++v) r[v] = 0;
+      uint32_t w[4] = {0, 0, 0, 0};
+      if ((s.flags[ai] & CWO_PRESENT) && (s.flags[ai] & CWO_VALID)) {
+        const bool coll = collision_ego(s, ai);
+        const bool oom = out_of_map(s, ai);
+        const bool goal = at_goal(s, ai);
+        labels(s, f, ai, coll, oom, goal, w);
+        Slot slots[CWO_MAX_SLOTS];
+        const int nr = build_slots(*c, ai, slots);
+        for (int k = 0; k < nr; ++k)
+          r[c->rules[slots[k].rule].priority] += rule_step(slots[k], w, &s.q[ai][k], &s.viol[ai][k]);
+      }
+      if (labels_out) std::memcpy(labels_out + ai * 4, w, sizeof(w));
     }
   }
 
@@ -470,7 +504,7 @@ struct World {
     }
   }
 
-  void init_state(const float* states0, const uint8_t* flags0, int horizon0, const uint8_t* q0,
+  void init_state(const double* states0, const uint8_t* flags0, int horizon0, const uint8_t* q0,
                   State<T>& s) {
     std::memset(&s, 0, sizeof(s));
     for (int i = 0; i < A; ++i) {
@@ -521,7 +555,7 @@ struct World {
 };
 
 template <class T>
-int replay_t(const cwo_config* cfg, const float* states0, const uint8_t* flags0, int32_t horizon0,
+int replay_t(const cwo_config* cfg, const double* states0, const uint8_t* flags0, int32_t horizon0,
              const uint8_t* q0, const uint8_t* actions, int32_t Tn, double* states_out,
              uint8_t* flags_out, uint8_t* terminal_out, uint8_t* q_out, uint32_t* viol_out,
              double* rewards_out, uint32_t* labels_out, double* frenet_out, double* margin_out,
@@ -562,7 +596,7 @@ int replay_t(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
 }
 
 template <class T>
-void rollout_range(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+void rollout_range(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                    int32_t horizon0, const uint8_t* q0, uint64_t seed, uint64_t begin, uint64_t end,
                    int max_steps, double gamma, int first_exp, double* ret_sum, uint64_t* viol_sum,
                    uint64_t* agent_steps, double* returns, uint32_t* viol, uint8_t* q_final,
@@ -575,8 +609,8 @@ void rollout_range(const cwo_config* cfg, const float* states0, const uint8_t* f
   for (uint64_t r = begin; r < end; ++r) {
     const uint64_t i = r - begin;
     w.margin = std::numeric_limits<double>::infinity();
-    const int k = w.rollout_one(root, seed, r, max_steps, static_cast<T>(static_cast<float>(gamma)),
-                                first_exp, ret, fin, agent_steps);
+    const int k = w.rollout_one(root, seed, r, max_steps, static_cast<T>(gamma), first_exp, ret, fin,
+                                agent_steps);
     if (ret_sum)
       for (int j = 0; j < M * V; ++j) ret_sum[j] += ret[j];
     if (viol_sum)
@@ -609,39 +643,63 @@ int32_t cwo_rules_per_agent(const cwo_config* cfg) {
   return cfg->n_mcts_agents > 0 ? build_slots(*cfg, 0, s) : 0;
 }
 
-int32_t cwo_check_terminal(const cwo_config* cfg, const float* states, const uint8_t* flags,
+int32_t cwo_check_terminal(const cwo_config* cfg, const double* states, const uint8_t* flags,
                            int32_t horizon) {
-  if (cfg->precision) {
-    World<float> w(cfg);
-    State<float> s;
-    w.init_state(states, flags, horizon, nullptr, s);
-    return s.terminal;
-  }
   World<double> w(cfg);
   State<double> s;
   w.init_state(states, flags, horizon, nullptr, s);
   return s.terminal;
 }
 
-int32_t cwo_replay(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_replay(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                    int32_t horizon0, const uint8_t* q0, const uint8_t* actions, int32_t T,
                    double* states_out, uint8_t* flags_out, uint8_t* terminal_out, uint8_t* q_out,
                    uint32_t* viol_out, double* rewards_out, uint32_t* labels_out,
                    double* frenet_out, double* margin_out, double* term_reward_out) {
-  if (cfg->precision)
-    return replay_t<float>(cfg, states0, flags0, horizon0, q0, actions, T, states_out, flags_out,
-                           terminal_out, q_out, viol_out, rewards_out, labels_out, frenet_out,
-                           margin_out, term_reward_out);
   return replay_t<double>(cfg, states0, flags0, horizon0, q0, actions, T, states_out, flags_out,
                           terminal_out, q_out, viol_out, rewards_out, labels_out, frenet_out,
                           margin_out, term_reward_out);
 }
 
-int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_evaluate_rules(const cwo_config* cfg, const double* states, const uint8_t* flags,
+                           int32_t horizon, const uint8_t* q_in, uint8_t* q_out, uint32_t* viol_out,
+                           double* rewards_out, uint32_t* labels_out) {
+  World<double> w(cfg);
+  State<double> s;
+  w.init_state(states, flags, horizon, q_in, s);
+  double rew[CWO_MAX_AGENTS * 8];
+  w.evaluate_rules(s, rew, labels_out);
+  for (int a = 0; a < w.M; ++a) {
+    for (int k = 0; k < w.R; ++k) {
+      q_out[a * w.R + k] = s.q[a][k];
+      viol_out[a * w.R + k] = s.viol[a][k];
+    }
+    for (int v = 0; v < w.V; ++v) rewards_out[a * w.V + v] = rew[a * w.V + v];
+  }
+  return 0;
+}
+
+void cwo_coop_mix(double* returns_sum, int32_t M, int32_t V, double coop_factor) {
+  // mvmcts COOP_FACTOR (src/util.cpp:28-29, 0 in every test of the reference; the mixing rule
+  // lives in the un-vendored mvmcts and is restated from the survey's recollection):
+  // value_i = own_i + coop * sum_{j != i} own_j, per reward component
+  if (coop_factor == 0.0) return;
+  double own[CWO_MAX_AGENTS * 8];
+  for (int i = 0; i < M * V; ++i) own[i] = returns_sum[i];
+  for (int a = 0; a < M; ++a)
+    for (int v = 0; v < V; ++v) {
+      double others = 0.0;
+      for (int j = 0; j < M; ++j)
+        if (j != a) others += own[j * V + v];
+      returns_sum[a * V + v] = own[a * V + v] + coop_factor * others;
+    }
+}
+
+int32_t cwo_rollout(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                     int32_t horizon0, const uint8_t* q0, uint64_t seed, uint64_t rollout_begin,
                     uint64_t n_rollouts, int32_t max_steps, double gamma,
-                    int32_t first_discount_exp, int32_t n_threads, double* returns_sum,
-                    uint64_t* viol_sum, uint64_t* agent_steps) {
+                    int32_t first_discount_exp, double coop_factor, int32_t n_threads,
+                    double* returns_sum, uint64_t* viol_sum, uint64_t* agent_steps) {
   const int M = cfg->n_mcts_agents, V = cfg->reward_vector_size, R = cwo_rules_per_agent(cfg);
   const int P = n_threads < 1 ? 1 : n_threads;
   std::vector<std::vector<double>> rs(P, std::vector<double>(M * V, 0.0));
@@ -655,14 +713,9 @@ int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* 
       std::vector<double> lr(M * V, 0.0);
       std::vector<uint64_t> lv(M * R + 1, 0);
       uint64_t ls = 0;
-      if (cfg->precision)
-        rollout_range<float>(cfg, states0, flags0, horizon0, q0, seed, b, e, max_steps, gamma,
-                             first_discount_exp, lr.data(), lv.data(), &ls, nullptr, nullptr,
-                             nullptr, nullptr, nullptr, nullptr, nullptr);
-      else
-        rollout_range<double>(cfg, states0, flags0, horizon0, q0, seed, b, e, max_steps, gamma,
-                              first_discount_exp, lr.data(), lv.data(), &ls, nullptr, nullptr,
-                              nullptr, nullptr, nullptr, nullptr, nullptr);
+      rollout_range<double>(cfg, states0, flags0, horizon0, q0, seed, b, e, max_steps, gamma,
+                            first_discount_exp, lr.data(), lv.data(), &ls, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, nullptr);
       rs[p] = lr;
       vs[p] = lv;
       st[p] = ls;
@@ -674,6 +727,7 @@ int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* 
     returns_sum[i] = 0;
     for (int p = 0; p < P; ++p) returns_sum[i] += rs[p][i];
   }
+  cwo_coop_mix(returns_sum, M, V, coop_factor);
   for (int i = 0; i < M * R; ++i) {
     viol_sum[i] = 0;
     for (int p = 0; p < P; ++p) viol_sum[i] += vs[p][i];
@@ -683,21 +737,16 @@ int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* 
   return 0;
 }
 
-int32_t cwo_rollout_detail(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_rollout_detail(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                            int32_t horizon0, const uint8_t* q0, uint64_t seed,
                            uint64_t rollout_begin, uint64_t n_rollouts, int32_t max_steps,
                            double gamma, int32_t first_discount_exp, double* returns,
                            uint32_t* viol, uint8_t* q_final, double* states_final,
                            uint8_t* flags_final, int32_t* steps, double* margin) {
   uint64_t dummy = 0;
-  if (cfg->precision)
-    rollout_range<float>(cfg, states0, flags0, horizon0, q0, seed, rollout_begin,
-                         rollout_begin + n_rollouts, max_steps, gamma, first_discount_exp, nullptr,
-                         nullptr, &dummy, returns, viol, q_final, states_final, flags_final, steps, margin);
-  else
-    rollout_range<double>(cfg, states0, flags0, horizon0, q0, seed, rollout_begin,
-                          rollout_begin + n_rollouts, max_steps, gamma, first_discount_exp, nullptr,
-                          nullptr, &dummy, returns, viol, q_final, states_final, flags_final, steps, margin);
+  rollout_range<double>(cfg, states0, flags0, horizon0, q0, seed, rollout_begin,
+                        rollout_begin + n_rollouts, max_steps, gamma, first_discount_exp, nullptr,
+                        nullptr, &dummy, returns, viol, q_final, states_final, flags_final, steps, margin);
   return 0;
 }
 

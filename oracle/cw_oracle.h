@@ -21,8 +21,9 @@
  * (0 / -800 / -1000) and the action-count / frozen-position behaviour of
  * test/multi_agent_test.cpp:115-139, reproduced in tests/test_cw_oracle.py.
  *
- * Arithmetic runs in double (`precision` 0, the reference's type) or in float
- * (`precision` 1, used to find rollouts that sit within fp32 rounding of a threshold).
+ * Arithmetic runs in double, the reference's type (src/rules_mcts_state.cpp:204-264), on the
+ * parameters as given (no rounding through float).  Every threshold comparison records how
+ * close it came to flipping (`margin` outputs) -- a diagnostic, no test excludes anything on it.
  */
 #ifndef ORACLE_CW_ORACLE_H_
 #define ORACLE_CW_ORACLE_H_
@@ -85,7 +86,7 @@ typedef struct {
       radial_acceleration_weight, desired_velocity_weight, lane_center_weight;
   double prediction_time_span, desired_velocity, discount_factor, goal_reward;
   int32_t reward_vector_size, horizon, use_rule_reward_for_ego_only;
-  int32_t precision; /* 0 double, 1 float */
+  int32_t remove_agents_out_of_map; /* bark "World::remove_agents_out_of_map" (default 0) */
   /* dynamics (bark, un-vendored) */
   double wheel_base, integration_time_delta;
   /* label parameters */
@@ -104,7 +105,7 @@ int32_t cwo_rules_per_agent(const cwo_config* cfg);
 #define CWO_VALID 2
 
 /* CheckTerminal of a state (src/rules_mcts_state.cpp:266-285). */
-int32_t cwo_check_terminal(const cwo_config* cfg, const float* states /*[A][4] x,y,theta,v*/,
+int32_t cwo_check_terminal(const cwo_config* cfg, const double* states /*[A][4] x,y,theta,v*/,
                            const uint8_t* flags /*[A]*/, int32_t horizon);
 
 /* Replay T joint actions (per MCTS agent) from one state; stops once terminal.
@@ -113,22 +114,32 @@ int32_t cwo_check_terminal(const cwo_config* cfg, const float* states /*[A][4] x
  *  label kind, words 1..3 masks over j for kinds 8,9,10), frenet_out [T][A][3]
  *  (lane, s, lat), margin_out [T] (smallest |lhs-rhs| over all threshold comparisons of
  *  the step), term_reward_out [M][V].  Returns the number of steps executed. */
-int32_t cwo_replay(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_replay(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                    int32_t horizon0, const uint8_t* q0, const uint8_t* actions, int32_t T,
                    double* states_out, uint8_t* flags_out, uint8_t* terminal_out, uint8_t* q_out,
                    uint32_t* viol_out, double* rewards_out, uint32_t* labels_out,
                    double* frenet_out, double* margin_out, double* term_reward_out);
 
 /* Random rollouts with Philox actions (same draw rule as gw_oracle.h). */
-int32_t cwo_rollout(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_rollout(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                     int32_t horizon0, const uint8_t* q0, uint64_t seed, uint64_t rollout_begin,
                     uint64_t n_rollouts, int32_t max_steps, double gamma,
-                    int32_t first_discount_exp, int32_t n_threads, double* returns_sum /*[M][V]*/,
+                    int32_t first_discount_exp, double coop_factor, int32_t n_threads,
+                    double* returns_sum /*[M][V], agents mixed with coop_factor*/,
                     uint64_t* viol_sum /*[M][R]*/, uint64_t* agent_steps);
+
+/* value_i = own_i + coop_factor * sum_{j != i} own_j, in place on returns_sum [M][V]. */
+void cwo_coop_mix(double* returns_sum, int32_t M, int32_t V, double coop_factor);
+
+/* MvmctsState::EvaluateRules() (src/rules_mcts_state.cpp:186-197) on one state: q_out / viol_out
+ * [M][R], rewards_out [M][V] (rule penalties only), labels_out [M][4]. */
+int32_t cwo_evaluate_rules(const cwo_config* cfg, const double* states, const uint8_t* flags,
+                           int32_t horizon, const uint8_t* q_in, uint8_t* q_out, uint32_t* viol_out,
+                           double* rewards_out, uint32_t* labels_out);
 
 /* Per-rollout outputs: returns [n][M][V], viol [n][M][R], q [n][M][R], states [n][A][4],
  * flags [n][A], steps [n], margin [n] (min over the rollout). */
-int32_t cwo_rollout_detail(const cwo_config* cfg, const float* states0, const uint8_t* flags0,
+int32_t cwo_rollout_detail(const cwo_config* cfg, const double* states0, const uint8_t* flags0,
                            int32_t horizon0, const uint8_t* q0, uint64_t seed,
                            uint64_t rollout_begin, uint64_t n_rollouts, int32_t max_steps,
                            double gamma, int32_t first_discount_exp, double* returns,

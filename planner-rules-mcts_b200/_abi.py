@@ -86,33 +86,34 @@ CW_PRESENT, CW_VALID = 1, 2
 
 
 class CwParams(C.Structure):
-    _fields_ = [(k, C.c_float) for k in (
+    _fields_ = [(k, C.c_double) for k in (
         "collision_weight", "out_of_map_weight", "potential_weight", "acceleration_weight",
         "radial_acceleration_weight", "desired_velocity_weight", "lane_center_weight",
         "prediction_time_span", "desired_velocity", "discount_factor", "goal_reward")] + [
         ("reward_vector_size", C.c_int32), ("horizon", C.c_int32),
-        ("use_rule_reward_for_ego_only", C.c_int32)] + [(k, C.c_float) for k in (
+        ("use_rule_reward_for_ego_only", C.c_int32), ("remove_agents_out_of_map", C.c_int32)] + [
+        (k, C.c_double) for k in (
             "wheel_base", "integration_time_delta", "sd_reaction_time", "sd_max_decel_rear",
             "sd_max_decel_front", "near_distance")]
 
 
 class CwAgent(C.Structure):
-    _fields_ = [("front", C.c_float), ("rear", C.c_float), ("half_width", C.c_float),
-                ("has_goal", C.c_int32), ("goal", C.c_float * 6), ("n_prims", C.c_int32),
-                ("prim_acc", C.c_float * CW_MAX_PRIMS), ("prim_delta", C.c_float * CW_MAX_PRIMS)]
+    _fields_ = [("front", C.c_double), ("rear", C.c_double), ("half_width", C.c_double),
+                ("goal", C.c_double * 6), ("has_goal", C.c_int32), ("n_prims", C.c_int32),
+                ("prim_acc", C.c_double * CW_MAX_PRIMS), ("prim_delta", C.c_double * CW_MAX_PRIMS)]
 
 
 class CwLane(C.Structure):
-    _fields_ = [("n_pts", C.c_int32), ("successor", C.c_int32), ("flags", C.c_int32),
-                ("half_width", C.c_float), ("s_point", C.c_float),
-                ("pts", (C.c_float * 2) * CW_MAX_PTS)]
+    _fields_ = [("n_pts", C.c_int32), ("successor", C.c_int32), ("flags", C.c_int32), ("_pad", C.c_int32),
+                ("half_width", C.c_double), ("s_point", C.c_double),
+                ("pts", (C.c_double * 2) * CW_MAX_PTS)]
 
 
 class CwScenario(C.Structure):
     _fields_ = [("params", CwParams), ("n_agents", C.c_int32), ("n_mcts_agents", C.c_int32),
-                ("n_lanes", C.c_int32), ("n_road", C.c_int32), ("n_rules", C.c_int32),
+                ("n_lanes", C.c_int32), ("n_road", C.c_int32), ("n_rules", C.c_int32), ("_pad", C.c_int32),
                 ("agents", CwAgent * CW_MAX_AGENTS), ("lanes", CwLane * CW_MAX_LANES),
-                ("road", (C.c_float * 2) * CW_MAX_ROAD), ("rules", Rule * MAX_RULES)]
+                ("road", (C.c_double * 2) * CW_MAX_ROAD), ("rules", Rule * MAX_RULES)]
 
 
 class CwStates(C.Structure):
@@ -137,7 +138,7 @@ SYMBOLS = [
     "brm_cw_configure", "brm_cw_rules_per_agent", "brm_cw_check_terminal", "brm_cw_execute",
     "brm_cw_evaluate_rules", "brm_cw_rollout_root_stats", "brm_gw_rollout_root_stats",
     "brm_cw_get_num_actions", "brm_cw_terminal_reward", "brm_cw_rollout", "brm_cw_replay",
-    "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_synchronize",
+    "brm_create", "brm_destroy", "brm_last_error", "brm_abi_version", "brm_abi_struct_sizes", "brm_synchronize",
     "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
     "brm_gw_configure", "brm_gw_rules_per_agent", "brm_gw_execute", "brm_gw_get_num_actions",
     "brm_gw_is_terminal", "brm_gw_terminal_reward", "brm_gw_rollout", "brm_gw_replay",

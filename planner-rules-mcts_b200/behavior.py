@@ -201,7 +201,7 @@ class BehaviorRulesMcts:
             m.primitives = list(prim)
             m.goal = self.ego_goal if k == 0 else None
             models.append(m)
-        state = np.array([observed_world.agents[i] for i in order], np.float32)
+        state = np.array([observed_world.agents[i] for i in order], np.float64)
         # the uploaded rule list: the common rules, then the rules given to single agents; every
         # MCTS agent gets the list of rule indices that apply to it (its own rule list, in order)
         rules, per_agent = list(self.common_rules_), []
@@ -289,7 +289,7 @@ class BehaviorRulesMcts:
         m = copy.copy(self.shape)
         m.primitives = list(ps.ego_primitives)
         one = RulesMctsEngine([Scenario(tp, [m], 1, observed_world.lanes, np.asarray(observed_world.road), [],
-                                        np.asarray(ego, np.float32)[None])], engine=self._abi_engine)
+                                        np.asarray(ego, np.float64)[None])], engine=self._abi_engine)
         b = one.make_batch(one.scenarios[0].initial_state[None])
         b.terminal[:] = 0   # the primitive is executed whatever CheckTerminal says about the horizon
         nxt, _ = one.execute(b, np.array([[best]], np.uint8))

@@ -54,6 +54,9 @@ class RulesMctsStateParameters:
     DISCOUNT_FACTOR: float = 0.9
     GOAL_REWARD: float = 0.0
     USE_RULE_REWARD_FOR_EGO_ONLY: bool = False
+    # bark "World::remove_agents_out_of_map": Predict removes agents whose shape left the road
+    # polygon; an MCTS agent that vanished earns OUT_OF_MAP_WEIGHT (src/rules_mcts_state.cpp:121-125)
+    REMOVE_AGENTS_OUT_OF_MAP: bool = False
     # bark (un-vendored): SingleTrackModel wheel base, BehaviorMotionPrimitives integration step
     WHEEL_BASE: float = 2.7
     INTEGRATION_TIME_DELTA: float = 0.02
@@ -79,6 +82,7 @@ class RulesMctsStateParameters:
         p.reward_vector_size = self.REWARD_VECTOR_SIZE
         p.horizon = self.HORIZON
         p.use_rule_reward_for_ego_only = 1 if self.USE_RULE_REWARD_FOR_EGO_ONLY else 0
+        p.remove_agents_out_of_map = 1 if self.REMOVE_AGENTS_OUT_OF_MAP else 0
         p.wheel_base = self.WHEEL_BASE
         p.integration_time_delta = self.INTEGRATION_TIME_DELTA
         p.sd_reaction_time = self.SAFE_DISTANCE_REACTION_TIME
@@ -200,7 +204,7 @@ class CwBatch:
 
     @staticmethod
     def zeros(A, M, R, n, track_violations=True):
-        return CwBatch(np.zeros(n, np.int32), np.zeros((A, n, 4), np.float32), np.zeros((A, n), np.uint8),
+        return CwBatch(np.zeros(n, np.int32), np.zeros((A, n, 4), np.float64), np.zeros((A, n), np.uint8),
                        np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros((M, R, n), np.uint8),
                        np.zeros((M, R, n), np.uint32) if track_violations else None)
 
@@ -268,7 +272,7 @@ class RulesMctsEngine:
 
     def make_batch(self, states, scenario=None, flags=None, horizon=None, q=None, track_violations=True):
         """states [n][A][4] (x, y, theta, v); fills `terminal` with CheckTerminal on the GPU."""
-        states = np.asarray(states, np.float32)
+        states = np.asarray(states, np.float64)
         if states.ndim == 2:
             states = states[None]
         n = states.shape[0]
@@ -315,17 +319,17 @@ class RulesMctsEngine:
         return np.asarray(batch.terminal).astype(bool)
 
     def execute(self, batch, actions):
-        """MvmctsState::Execute; actions [M][n] uint8 -> (next_batch, rewards [M][V][n] float32)."""
+        """MvmctsState::Execute; actions [M][n] uint8 -> (next_batch, rewards [M][V][n] float64)."""
         n = batch.n
         if batch.device:
             import torch
             out = CwBatch(*[None if getattr(batch, f) is None else torch.empty_like(getattr(batch, f))
                             for f in CwBatch.FIELDS])
-            rewards = torch.zeros((self.M, self.V, n), dtype=torch.float32, device=batch.agents.device)
+            rewards = torch.zeros((self.M, self.V, n), dtype=torch.float64, device=batch.agents.device)
         else:
             actions = np.ascontiguousarray(actions, np.uint8)
             out = CwBatch.zeros(self.A, self.M, self.R, n, batch.viol is not None)
-            rewards = np.zeros((self.M, self.V, n), np.float32)
+            rewards = np.zeros((self.M, self.V, n), np.float64)
         sin, sout = batch.to_abi(), out.to_abi()
         _abi.check(self.lib.brm_cw_execute(self.engine.handle, C.byref(sin), _ptr(actions), C.byref(sout),
                                            _ptr(rewards)))
@@ -333,16 +337,16 @@ class RulesMctsEngine:
 
     def evaluate_rules(self, batch):
         """MvmctsState::EvaluateRules(): one automaton transition on the labels of the states as
-        they are -> (batch with the new rule states, rule penalties [M][V][n] float32)."""
+        they are -> (batch with the new rule states, rule penalties [M][V][n] float64)."""
         n = batch.n
         if batch.device:
             import torch
             out = CwBatch(*[None if getattr(batch, f) is None else torch.empty_like(getattr(batch, f))
                             for f in CwBatch.FIELDS])
-            rewards = torch.zeros((self.M, self.V, n), dtype=torch.float32, device=batch.agents.device)
+            rewards = torch.zeros((self.M, self.V, n), dtype=torch.float64, device=batch.agents.device)
         else:
             out = CwBatch.zeros(self.A, self.M, self.R, n, batch.viol is not None)
-            rewards = np.zeros((self.M, self.V, n), np.float32)
+            rewards = np.zeros((self.M, self.V, n), np.float64)
         sin, sout = batch.to_abi(), out.to_abi()
         _abi.check(self.lib.brm_cw_evaluate_rules(self.engine.handle, C.byref(sin), C.byref(sout), _ptr(rewards)))
         return out, rewards
@@ -354,7 +358,7 @@ class RulesMctsEngine:
         return out
 
     def terminal_reward(self, batch):
-        out = np.zeros((self.M, self.V, batch.n), np.float32)
+        out = np.zeros((self.M, self.V, batch.n), np.float64)
         s = batch.to_abi()
         _abi.check(self.lib.brm_cw_terminal_reward(self.engine.handle, C.byref(s), _ptr(out)))
         return out
@@ -377,8 +381,8 @@ class RulesMctsEngine:
             out = dict(returns_sum=np.zeros((L, M, V), np.float64), viol_sum=np.zeros((L, M, R), np.uint64),
                        agent_steps=np.zeros(L, np.uint64))
             if detail:
-                out.update(ro_returns=np.zeros((N, M, V), np.float32), ro_viol=np.zeros((N, M, R), np.uint8),
-                           ro_q=np.zeros((N, M, R), np.uint8), ro_agents=np.zeros((N, A, 4), np.float32),
+                out.update(ro_returns=np.zeros((N, M, V), np.float64), ro_viol=np.zeros((N, M, R), np.uint8),
+                           ro_q=np.zeros((N, M, R), np.uint8), ro_agents=np.zeros((N, A, 4), np.float64),
                            ro_flags=np.zeros((N, A), np.uint8), ro_steps=np.zeros(N, np.int32))
         o = _abi.CwRolloutOut()
         for k, _ in _abi.CwRolloutOut._fields_:
@@ -398,11 +402,11 @@ class RulesMctsEngine:
         B, T, M = actions.shape
         assert B == batch0.n and M == self.M and not batch0.device
         A, V, R = self.A, self.V, self.R
-        tr = dict(agents_out=np.zeros((B, T, A, 4), np.float32), flags_out=np.zeros((B, T, A), np.uint8),
+        tr = dict(agents_out=np.zeros((B, T, A, 4), np.float64), flags_out=np.zeros((B, T, A), np.uint8),
                   terminal_out=np.zeros((B, T), np.uint8), q_out=np.zeros((B, T, M, R), np.uint8),
-                  viol_out=np.zeros((B, T, M, R), np.uint32), rewards_out=np.zeros((B, T, M, V), np.float32),
-                  labels_out=np.zeros((B, T, M, 4), np.uint32), frenet_out=np.zeros((B, T, A, 3), np.float32),
-                  term_reward_out=np.zeros((B, M, V), np.float32), steps_out=np.zeros(B, np.int32))
+                  viol_out=np.zeros((B, T, M, R), np.uint32), rewards_out=np.zeros((B, T, M, V), np.float64),
+                  labels_out=np.zeros((B, T, M, 4), np.uint32), frenet_out=np.zeros((B, T, A, 3), np.float64),
+                  term_reward_out=np.zeros((B, M, V), np.float64), steps_out=np.zeros(B, np.int32))
         t = _abi.CwTrace()
         for k, _ in _abi.CwTrace._fields_:
             setattr(t, k, _ptr(tr[k]))

@@ -1,0 +1,803 @@
+// Continuous-world step arithmetic: MvmctsState::Execute
+// (/root/reference/src/rules_mcts_state.cpp:57-128) cut into per-agent work items that
+// operate on a pool of rollouts held in shared memory.
+//
+//   phase 1, item = (rollout, agent that moves):  draw the action (Philox), single-track
+//            kinematics, drivable-area / goal test, lane projection, action cost + potential
+//   phase 2, item = (rollout, MCTS agent):  collision and label predicates against the other
+//            agents of the rollout, rule automata, reward vector, validity, terminal flag
+//   init / finalize items load a leaf into a pool slot and fold a finished rollout into the
+//            per-leaf sums.
+//
+// All state arithmetic is FP64, the reference's type: labels, automaton states and violation
+// counts have to equal the reference's double arithmetic bit for bit, and an fp32 state
+// cannot guarantee that within 1e-5 m of a threshold.  fp32 is only used where it cannot
+// change a result: conservative culling boxes of the lane projection.
+//
+// The code is host/device portable (BRM_HD) and uses explicit fma() -- the library is
+// compiled with --fmad=false -- so that tests/cpp/cw_emul.cpp can run exactly this
+// arithmetic on the CPU (bit-identical to the GPU) against the oracle without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "brm.h"
+
+#if defined(__CUDACC__)
+#define BRM_HD __host__ __device__ __forceinline__
+#else
+#define BRM_HD inline
+#endif
+
+namespace brm {
+
+// ------------------------------------------------------------------ scenario blob
+struct alignas(16) CwSeg {
+  double x0, y0, dx, dy;
+  double inv_len2, len, s0, _pad;
+};
+
+struct alignas(16) CwLaneHdr {
+  int32_t seg_off, n_seg, succ, flags;
+  double hw2, length, s_point, _pad;
+};
+
+struct alignas(16) CwEdge {
+  double ya, yb, xa, m;  // m = (xb - xa) / (yb - ya)
+};
+
+struct alignas(16) CwBox {
+  float x0, y0, x1, y1;
+};
+
+struct alignas(16) CwSlotRec {
+  uint32_t x;  // label-word bit read by each of the 4 APs (a byte each; 31 = always zero)
+  uint32_t y;  // n_aps | priority << 8 | init << 16 | on_violation << 24
+  uint32_t z;  // rule | (rank + 1) << 8 | absorbing-state mask << 16
+  float w;     // weight
+};
+
+constexpr int kCwBlk = 8;                                                // segments per culling block
+constexpr int kCwMaxBlk = (BRM_CW_MAX_PTS - 1 + kCwBlk - 1) / kCwBlk;    // blocks per lane
+constexpr int kCwMaxBlkTotal = BRM_CW_MAX_LANES * kCwMaxBlk;             // 64: one bit each
+constexpr int kCwMaxSegs = BRM_CW_MAX_LANES * (BRM_CW_MAX_PTS - 1);
+
+struct alignas(16) CwBlob {
+  int32_t A, M, V, R, n_lanes, n_road, n_rules, n_sub;
+  int32_t ego_only, total_bytes, n_blk, remove_oom;
+  double w_coll, w_oom, w_pot, w_acc, w_rad, w_vel, w_lane, dt;
+  double v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
+  double near2, c2, t_total, inv_dt;  // c2, t_total: closed form of the Euler sub-steps without steering
+  double front[BRM_CW_MAX_AGENTS], rear[BRM_CW_MAX_AGENTS], hw[BRM_CW_MAX_AGENTS];
+  double off[BRM_CW_MAX_AGENTS], ext[BRM_CW_MAX_AGENTS];  // (front - rear) / 2, (front + rear) / 2
+  double rad[BRM_CW_MAX_AGENTS];  // circumscribed radius of the rectangle about its centre (a hair more)
+  double goal[BRM_CW_MAX_AGENTS][6];
+  double prim_a[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];
+  double prim_k[BRM_CW_MAX_AGENTS][BRM_CW_MAX_PRIMS];  // tan(delta) / wheel_base
+  uint8_t has_goal[BRM_CW_MAX_AGENTS], n_prims[BRM_CW_MAX_AGENTS];
+  CwSlotRec slot_rec[BRM_CW_MAX_SLOTS];
+  uint8_t slot_rule[BRM_CW_MAX_SLOTS];
+  brm_rule rules[BRM_MAX_RULES];  // trans stored with AP k of the letter at bit k
+  CwEdge road_edge[BRM_CW_MAX_ROAD];
+  // culling of the nearest-segment search (fp32, conservative): blocks of kCwBlk consecutive
+  // segments in lane order; blk_gbox = bounding box grown by the lane's half width (a point
+  // outside it is farther than the half width from every segment of the block), blk_box =
+  // bounding box; both grown by a slack that covers the fp32 rounding of coordinates up to
+  // BRM_CW_MAX_COORD.  blk_info = lane | first segment (within the lane) << 8 | count << 16
+  CwBox blk_gbox[kCwMaxBlkTotal];
+  CwBox blk_box[kCwMaxBlkTotal];
+  uint32_t blk_info[kCwMaxBlkTotal];
+  CwLaneHdr lanes[BRM_CW_MAX_LANES];
+  CwSeg segs[kCwMaxSegs];  // last: only the used part is copied
+};
+static_assert(sizeof(CwBlob) % 16 == 0, "blob must be a multiple of 16 bytes");
+static_assert(offsetof(CwBlob, segs) % 16 == 0, "segment array must be 16-byte aligned");
+
+// ------------------------------------------------------------------ the pool
+// P rollout slots of A agents (M of them MCTS agents) in structure-of-arrays form; in the
+// kernels these arrays live in shared memory.
+enum : uint8_t {
+  CW_BIT_OOM = 1,       // drivable-area test of this step: shape not within the road polygon
+  CW_BIT_GOAL = 2,      // shape within the goal
+  CW_BIT_VANISHED = 4,  // left the map during this step (remove_agents_out_of_map)
+};
+
+struct CwPool {
+  int32_t P, A, M, R, V, QW;  // QW = words of packed automaton states per agent = ceil(R / 8)
+  // agent slots [P * A]
+  double *x, *y, *th, *v, *cs, *sn, *s, *lat;
+  int16_t* lane;   // lane of the current position, -1: none
+  uint8_t* flags;  // BRM_CW_PRESENT | BRM_CW_VALID
+  uint8_t* bits;   // CW_BIT_*
+  // MCTS agent slots [P * M]
+  double* cost;       // action cost + potential of the current step (phase 1 -> phase 2)
+  double* acc;        // [P * M][4] discounted return so far
+  uint32_t* rng;      // [P * M][4] Philox block serving steps 4b .. 4b+3
+  uint32_t* qw;       // [P * M][QW] automaton states, 4 bits per rule slot
+  uint32_t* live;     // [P * M] rule slots whose state is not absorbing
+  uint8_t* viol;      // [P * M][R] violations since the slot was filled
+  // rollout slots [P]
+  int32_t *flat, *leaf, *k, *horizon;
+  double* disc;
+  uint32_t* nsteps;   // agents integrated so far
+  uint8_t *busy, *done;
+};
+
+BRM_HD size_t cw_pool_bytes(int P, int A, int M, int R) {
+  const size_t S = static_cast<size_t>(P) * A, Sm = static_cast<size_t>(P) * M;
+  const size_t QW = (R + 7) / 8;
+  size_t b = S * 8 * sizeof(double);
+  b += Sm * (1 + 4) * sizeof(double);
+  b += static_cast<size_t>(P) * sizeof(double);
+  b += Sm * (4 + QW + 1) * sizeof(uint32_t);
+  b += static_cast<size_t>(P) * 5 * sizeof(int32_t);
+  b += S * sizeof(int16_t);
+  b = (b + 3) & ~static_cast<size_t>(3);
+  b += S * 2 + Sm * R + static_cast<size_t>(P) * 2;
+  return (b + 15) & ~static_cast<size_t>(15);
+}
+
+// carve the arrays out of `mem` (16-byte aligned, cw_pool_bytes large)
+BRM_HD void cw_pool_carve(CwPool& p, void* mem, int P, int A, int M, int R, int V) {
+  p.P = P; p.A = A; p.M = M; p.R = R; p.V = V; p.QW = (R + 7) / 8;
+  const size_t S = static_cast<size_t>(P) * A, Sm = static_cast<size_t>(P) * M;
+  double* d = static_cast<double*>(mem);
+  p.x = d; d += S;  p.y = d; d += S;  p.th = d; d += S;  p.v = d; d += S;
+  p.cs = d; d += S; p.sn = d; d += S; p.s = d; d += S;   p.lat = d; d += S;
+  p.cost = d; d += Sm;
+  p.acc = d; d += Sm * 4;
+  p.disc = d; d += P;
+  uint32_t* u = reinterpret_cast<uint32_t*>(d);
+  p.rng = u; u += Sm * 4;
+  p.qw = u; u += Sm * p.QW;
+  p.live = u; u += Sm;
+  int32_t* i = reinterpret_cast<int32_t*>(u);
+  p.flat = i; i += P;  p.leaf = i; i += P;  p.k = i; i += P;  p.horizon = i; i += P;
+  p.nsteps = reinterpret_cast<uint32_t*>(i); i += P;
+  int16_t* h = reinterpret_cast<int16_t*>(i);
+  p.lane = h; h += S;
+  uintptr_t a = (reinterpret_cast<uintptr_t>(h) + 3) & ~static_cast<uintptr_t>(3);
+  uint8_t* b = reinterpret_cast<uint8_t*>(a);
+  p.flags = b; b += S;  p.bits = b; b += S;
+  p.viol = b; b += Sm * R;
+  p.busy = b; b += P;  p.done = b; b += P;
+}
+
+// ------------------------------------------------------------------ small math
+BRM_HD double cw_fma(double a, double b, double c) { return fma(a, b, c); }
+
+// sin and cos of x for moderate |x| (headings): Cody-Waite reduction by pi/2 in three parts,
+// then the fdlibm kernel polynomials on [-pi/4, pi/4].  Below 2 ulp; identical on host and
+// device (only fma, +, *).
+BRM_HD void cw_sincos(double x, double* sn, double* cs) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: (t + magic) - magic = rint(t)
+  const double n = (x * 0.63661977236758134308 + kMagic) - kMagic;
+  double r = cw_fma(-n, 1.5707963267948966, x);
+  r = cw_fma(-n, 6.123233995736766e-17, r);
+  r = cw_fma(-n, -1.4973849048591698e-33, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = cw_fma(ps, z, -2.50507602534068634195e-08);
+  ps = cw_fma(ps, z, 2.75573137070700676789e-06);
+  ps = cw_fma(ps, z, -1.98412698298579493134e-04);
+  ps = cw_fma(ps, z, 8.33333333332248946124e-03);
+  ps = cw_fma(ps, z, -1.66666666666666324348e-01);
+  ps = cw_fma(ps * z, r, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = cw_fma(pc, z, 2.08757232129817482790e-09);
+  pc = cw_fma(pc, z, -2.75573143513906633035e-07);
+  pc = cw_fma(pc, z, 2.48015872894767294178e-05);
+  pc = cw_fma(pc, z, -1.38888888888741095749e-03);
+  pc = cw_fma(pc, z, 4.16666666666666019037e-02);
+  pc = cw_fma(pc * z, z, cw_fma(-0.5, z, 1.0));
+  const int q = static_cast<int>(static_cast<long long>(n)) & 3;
+  const double s0 = (q & 1) ? pc : ps, c0 = (q & 1) ? ps : pc;
+  *sn = (q & 2) ? -s0 : s0;
+  *cs = ((q + 1) & 2) ? -c0 : c0;
+}
+
+// sin and cos of a small angle (|d| <= 1/8): Taylor polynomials, error below 1e-20
+BRM_HD void cw_sincos_small(double d, double* sn, double* cs) {
+  const double z = d * d;
+  double ps = -1.0 / 39916800.0;
+  ps = cw_fma(ps, z, 1.0 / 362880.0);
+  ps = cw_fma(ps, z, -1.0 / 5040.0);
+  ps = cw_fma(ps, z, 1.0 / 120.0);
+  ps = cw_fma(ps, z, -1.0 / 6.0);
+  *sn = cw_fma(ps * z, d, d);
+  double pc = 1.0 / 479001600.0;
+  pc = cw_fma(pc, z, -1.0 / 3628800.0);
+  pc = cw_fma(pc, z, 1.0 / 40320.0);
+  pc = cw_fma(pc, z, -1.0 / 720.0);
+  pc = cw_fma(pc, z, 1.0 / 24.0);
+  pc = cw_fma(pc, z, -0.5);
+  *cs = cw_fma(pc, z, 1.0);
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+BRM_HD uint32_t cw_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+
+// counter = (rollout_lo, rollout_hi, step >> 2, agent), key = seed; word step & 3 serves `step`
+BRM_HD void cw_philox_block(uint64_t seed, uint64_t rollout, uint32_t step, uint32_t agent, uint32_t* out) {
+  uint32_t c0 = static_cast<uint32_t>(rollout), c1 = static_cast<uint32_t>(rollout >> 32);
+  uint32_t c2 = step >> 2, c3 = agent;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = cw_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = cw_mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ------------------------------------------------------------------ kinematics
+struct CwKin {
+  double x, y, th, v, cs, sn;
+};
+
+// bark SingleTrackModel under BehaviorMPContinuousActions (un-vendored): n_sub explicit Euler
+// sub-steps  x += h (v cos th), y += h (v sin th), th += h (v k), v += h a.
+// The speed and the heading never depend on the position, so their recurrences are carried out
+// operation by operation like the reference's loop (no fused multiply-add): v and th are
+// bit-identical to the double-precision loop, always.  Without steering the heading is
+// constant and the position follows the same recurrence literally -- round-number scenarios
+// (straight roads, speeds like 5.0) put agents EXACTLY on thresholds (8.0 m apart), and only
+// the same sequence of roundings decides those the same way.  With steering the heading of
+// sub-step n+1 is obtained by rotating through the small angle h v_n k instead of a fresh
+// sine / cosine per sub-step (positions agree to ~1e-15; they are generic numbers there).
+BRM_HD void cw_integrate(const CwBlob& B, CwKin& t, double acc, double kap) {
+  const int n_sub = B.n_sub;
+  double x = t.x, y = t.y, v = t.v;
+  if (kap == 0.0) {
+    const double cs = t.cs, sn = t.sn;
+    for (int n = 0; n < n_sub; ++n) {
+      const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
+      x = x + h * (v * cs);
+      y = y + h * (v * sn);
+      v = v + h * acc;
+    }
+  } else {
+    double dx = 0.0, dy = 0.0, th = t.th, c = t.cs, s = t.sn;
+    for (int n = 0; n < n_sub; ++n) {
+      const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
+      const double hv = h * v;
+      dx = cw_fma(hv, c, dx);
+      dy = cw_fma(hv, s, dy);
+      // heading of the next sub-step: th += h (v k), the pose rotated by the same angle
+      const double dth = h * (v * kap);
+      th = th + dth;
+      double sd, cd;
+      if (fabs(dth) <= 0.125)
+        cw_sincos_small(dth, &sd, &cd);
+      else
+        cw_sincos(dth, &sd, &cd);
+      const double c1 = cw_fma(c, cd, -(s * sd));
+      s = cw_fma(s, cd, c * sd);
+      c = c1;
+      v = v + h * acc;
+    }
+    x += dx;
+    y += dy;
+    t.th = th;
+    cw_sincos(th, &t.sn, &t.cs);
+  }
+  t.x = x;
+  t.y = y;
+  t.v = v;
+}
+
+// ------------------------------------------------------------------ lane projection
+struct CwFrenet {
+  int lane;
+  double s, lat;
+};
+
+// Nearest point on every lane centre line; the first lane that contains the point wins
+// (the brute-force search over all segments of the oracle).  Two cullings that cannot change
+// the answer: only blocks whose grown box contains the point can hold a segment within the
+// lane's half width; a block whose box is farther than the best distance so far cannot hold
+// a nearer segment.  Distances themselves are FP64.
+BRM_HD void cw_frenet(const CwBlob& B, double x, double y, CwFrenet& f) {
+  f.lane = -1;
+  f.s = 0.0;
+  f.lat = 0.0;
+  const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+  const int nb = B.n_blk;
+  uint32_t lo = 0u, hi = 0u, bit = 1u;
+  const int n0 = nb < 32 ? nb : 32;
+  for (int i = 0; i < n0; ++i, bit <<= 1) {
+    const CwBox g = B.blk_gbox[i];
+    if (xf >= g.x0 && xf <= g.x1 && yf >= g.y0 && yf <= g.y1) lo |= bit;
+  }
+  bit = 1u;
+  for (int i = 32; i < nb; ++i, bit <<= 1) {
+    const CwBox g = B.blk_gbox[i];
+    if (xf >= g.x0 && xf <= g.x1 && yf >= g.y0 && yf <= g.y1) hi |= bit;
+  }
+  unsigned long long mask = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+  int l = -1, n_seg = 0, seg_off = 0, bk = 0;
+  double best = 1e300, btu = 0.0, hw2 = 0.0;
+  for (;;) {
+    int i = -1;
+    if (mask) {
+#if defined(__CUDA_ARCH__)
+      i = __ffsll(static_cast<long long>(mask)) - 1;
+#else
+      i = __builtin_ctzll(mask);
+#endif
+    }
+    const uint32_t info = i >= 0 ? B.blk_info[i] : 0xffu;
+    const int li = static_cast<int>(info & 0xffu);
+    if (li != l) {
+      // lane l is finished: is the point on it?
+      if (l >= 0 && best <= hw2) {
+        const bool interior = !(bk == 0 && btu < 0.0) && !(bk == n_seg - 1 && btu > 1.0);
+        if (interior) {
+          const CwSeg& g = B.segs[seg_off + bk];
+          const double bt = fmin(fmax(btu, 0.0), 1.0);
+          const double wx = x - g.x0, wy = y - g.y0;
+          const double cross = cw_fma(g.dx, wy, -(g.dy * wx));
+          f.lane = l;
+          f.s = cw_fma(bt, g.len, g.s0);
+          const double dd = sqrt(best);
+          f.lat = cross < 0.0 ? -dd : dd;
+          return;
+        }
+      }
+      if (i < 0) return;
+      l = li;
+      const CwLaneHdr& L = B.lanes[l];
+      n_seg = L.n_seg;
+      seg_off = L.seg_off;
+      hw2 = L.hw2;
+      best = 1e300;
+    }
+    mask &= mask - 1ull;
+    const CwBox bb = B.blk_box[i];
+    const float gx = fmaxf(fmaxf(bb.x0 - xf, xf - bb.x1), 0.f);
+    const float gy = fmaxf(fmaxf(bb.y0 - yf, yf - bb.y1), 0.f);
+    if (static_cast<double>(gx * gx + gy * gy) * 0.999999 > best) continue;
+    const int b0 = static_cast<int>((info >> 8) & 0xffu);
+    const int b1 = b0 + static_cast<int>(info >> 16);
+    const CwSeg* seg = B.segs + seg_off;
+    for (int k = b0; k < b1; ++k) {
+      const double wx = x - seg[k].x0, wy = y - seg[k].y0;
+      const double sdx = seg[k].dx, sdy = seg[k].dy;
+      const double tu = cw_fma(wx, sdx, wy * sdy) * seg[k].inv_len2;
+      const double tc = fmin(fmax(tu, 0.0), 1.0);
+      const double ex = cw_fma(-tc, sdx, wx), ey = cw_fma(-tc, sdy, wy);
+      const double d2 = cw_fma(ex, ex, ey * ey);
+      if (d2 < best) {
+        best = d2;
+        bk = k;
+        btu = tu;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ shape predicates
+BRM_HD void cw_corners(const CwBlob& B, const CwKin& t, int a, double (&cx)[4], double (&cy)[4]) {
+  const double f = B.front[a], r = B.rear[a], h = B.hw[a];
+  const double lx[4] = {f, f, -r, -r};
+  const double ly[4] = {h, -h, -h, h};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    cx[k] = t.x + cw_fma(lx[k], t.cs, -(ly[k] * t.sn));
+    cy[k] = t.y + cw_fma(lx[k], t.sn, ly[k] * t.cs);
+  }
+}
+
+// EvaluatorDrivableArea restated: a corner outside the road polygon (crossing number), or a
+// road vertex strictly inside the rectangle
+BRM_HD bool cw_out_of_map(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
+  uint32_t inside = 0;
+  bool vertex_in = false;
+  const double f = B.front[a], r = B.rear[a], h = B.hw[a];
+  const int n_road = B.n_road;
+  for (int e = 0; e < n_road; ++e) {
+    const CwEdge g = B.road_edge[e];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) {
+      const bool cross = ((g.ya > cy[k]) != (g.yb > cy[k])) && (cx[k] < cw_fma(g.m, cy[k] - g.ya, g.xa));
+      inside ^= (cross ? 1u : 0u) << k;
+    }
+    const double dx = g.xa - t.x, dy = g.ya - t.y;
+    const double lx = cw_fma(dx, t.cs, dy * t.sn), ly = cw_fma(dy, t.cs, -(dx * t.sn));
+    vertex_in = (lx > -r && lx < f && fabs(ly) < h) || vertex_in;
+  }
+  return inside != 0xFu || vertex_in;
+}
+
+BRM_HD bool cw_at_goal(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
+  if (!B.has_goal[a]) return false;
+  const double* g = B.goal[a];
+  bool in = true;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) in = in && cx[k] >= g[0] && cx[k] <= g[1] && cy[k] >= g[2] && cy[k] <= g[3];
+  return in && t.th >= g[4] && t.th <= g[5];
+}
+
+// separating-axis test of the rectangles of agents a and j (centre distance already known to
+// be within the sum of the circumscribed radii)
+BRM_HD bool cw_rect_overlap(const CwBlob& B, int a, double xa, double ya, double ca, double sa, int j, double xj,
+                            double yj, double cj, double sj) {
+  const double oi = B.off[a], oj = B.off[j], eix = B.ext[a], ejx = B.ext[j], eiy = B.hw[a], ejy = B.hw[j];
+  const double dx = cw_fma(oj, cj, xj) - cw_fma(oi, ca, xa);
+  const double dy = cw_fma(oj, sj, yj) - cw_fma(oi, sa, ya);
+  const double cd = fabs(cw_fma(ca, cj, sa * sj)), sd = fabs(cw_fma(sa, cj, -(ca * sj)));
+  bool hit = fabs(cw_fma(dx, ca, dy * sa)) <= cw_fma(ejy, sd, cw_fma(ejx, cd, eix));
+  hit = (fabs(cw_fma(dy, ca, -(dx * sa))) <= cw_fma(ejy, cd, cw_fma(ejx, sd, eiy))) && hit;
+  hit = (fabs(cw_fma(dx, cj, dy * sj)) <= cw_fma(eiy, sd, cw_fma(eix, cd, ejx))) && hit;
+  hit = (fabs(cw_fma(dy, cj, -(dx * sj))) <= cw_fma(eiy, cd, cw_fma(eix, sd, ejy))) && hit;
+  return hit;
+}
+
+BRM_HD bool cw_collides(const CwBlob& B, const CwPool& p, int base, int a) {
+  const int A = p.A;
+  const double xa = p.x[base + a], ya = p.y[base + a], ca = p.cs[base + a], sa = p.sn[base + a];
+  const double cxa = cw_fma(B.off[a], ca, xa), cya = cw_fma(B.off[a], sa, ya);
+  bool coll = false;
+  for (int j = 0; j < A; ++j) {
+    if (j == a || !(p.flags[base + j] & BRM_CW_PRESENT)) continue;
+    const double xj = p.x[base + j], yj = p.y[base + j], cj = p.cs[base + j], sj = p.sn[base + j];
+    const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
+    const double rr = B.rad[a] + B.rad[j];
+    if (cw_fma(ddx, ddx, ddy * ddy) > rr * rr) continue;
+    coll = cw_rect_overlap(B, a, xa, ya, ca, sa, j, xj, yj, cj, sj) || coll;
+  }
+  return coll;
+}
+
+// ------------------------------------------------------------------ automaton state packing
+BRM_HD uint32_t cw_q_get(const uint32_t* qw, int sl) { return (qw[sl >> 3] >> ((sl & 7) * 4)) & 0xFu; }
+BRM_HD void cw_q_set(uint32_t* qw, int sl, uint32_t q) {
+  const int sh = (sl & 7) * 4;
+  qw[sl >> 3] = (qw[sl >> 3] & ~(0xFu << sh)) | (q << sh);
+}
+BRM_HD bool cw_slot_absorbing(const CwBlob& B, int sl, uint32_t q) { return (B.slot_rec[sl].z >> (16 + q)) & 1u; }
+
+// ------------------------------------------------------------------ init / finalize items
+// what a batch of states looks like to the pool (device or host pointers)
+struct CwStatesView {
+  const double* agents;  // [A][n][4]
+  const uint8_t* flags;  // [A][n]
+  const uint8_t* q;      // [M][R][n]
+  int64_t n;
+};
+
+// agent j of state `leaf` into slot (r, j): pose, lane projection, automaton states
+BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int r, int j, int64_t leaf) {
+  const int A = p.A, M = p.M, R = p.R;
+  const int s = r * A + j;
+  const double* src = S.agents + (static_cast<int64_t>(j) * S.n + leaf) * 4;
+  CwKin t;
+  t.x = src[0]; t.y = src[1]; t.th = src[2]; t.v = src[3];
+  const uint8_t fl = S.flags[static_cast<int64_t>(j) * S.n + leaf];
+  cw_sincos(t.th, &t.sn, &t.cs);
+  CwFrenet f;
+  f.lane = -1; f.s = 0.0; f.lat = 0.0;
+  if (fl & BRM_CW_PRESENT) cw_frenet(B, t.x, t.y, f);
+  uint8_t bits = 0;
+  if (j == 0 && (fl & BRM_CW_PRESENT) && !(fl & BRM_CW_VALID)) {
+    // a frozen ego never passes phase 1: its drivable-area / goal bits are those of the leaf
+    double cx[4], cy[4];
+    cw_corners(B, t, j, cx, cy);
+    if (cw_out_of_map(B, t, j, cx, cy)) bits |= CW_BIT_OOM;
+    if (cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
+  }
+  p.x[s] = t.x; p.y[s] = t.y; p.th[s] = t.th; p.v[s] = t.v; p.cs[s] = t.cs; p.sn[s] = t.sn;
+  p.s[s] = f.s; p.lat[s] = f.lat;
+  p.lane[s] = static_cast<int16_t>(f.lane);
+  p.flags[s] = fl;
+  p.bits[s] = bits;
+  if (j < M) {
+    const int sm = r * M + j;
+    p.cost[sm] = 0.0;
+    for (int v = 0; v < 4; ++v) p.acc[sm * 4 + v] = 0.0;
+    for (int v = 0; v < 4; ++v) p.rng[sm * 4 + v] = 0u;
+    uint32_t* qw = p.qw + sm * p.QW;
+    for (int w = 0; w < p.QW; ++w) qw[w] = 0u;
+    uint32_t live = 0u;
+    for (int sl = 0; sl < R; ++sl) {
+      const uint32_t q = S.q[(static_cast<int64_t>(j) * R + sl) * S.n + leaf];
+      cw_q_set(qw, sl, q);
+      if (!cw_slot_absorbing(B, sl, q)) live |= 1u << sl;
+      p.viol[sm * R + sl] = 0;
+    }
+    p.live[sm] = live;
+  }
+}
+
+// GetTerminalReward (:148-164) of MCTS agent a in slot r
+BRM_HD void cw_terminal_reward(const CwBlob& B, const CwPool& p, int r, int a, double (&tr)[4]) {
+  tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
+  if (!(p.flags[r * p.A + a] & BRM_CW_PRESENT)) return;
+  const uint32_t* qw = p.qw + (r * p.M + a) * p.QW;
+  for (int sl = 0; sl < p.R; ++sl) {
+    const brm_rule& rule = B.rules[B.slot_rule[sl]];
+    if (!rule.accepting[cw_q_get(qw, sl)]) tr[rule.priority] += static_cast<double>(rule.weight);
+  }
+}
+
+// ------------------------------------------------------------------ phase 1
+struct CwStepCtx {
+  uint64_t seed, rollout_base;
+  const uint8_t* actions;  // given actions (execute: [M][n], replay: [B][T][M]) or null: Philox
+  int64_t n;               // states in the batch (execute action stride)
+  int32_t T;               // replay: steps per trace; 0: execute layout
+};
+
+BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int a) {
+  const uint32_t n_prims = B.n_prims[a];
+  const int k = p.k[r];
+  if (c.actions) {
+    const int64_t i = p.leaf[r];
+    const uint32_t act = c.T > 0 ? c.actions[(i * c.T + k) * p.M + a] : c.actions[static_cast<int64_t>(a) * c.n + i];
+    return act < n_prims ? act : 0u;
+  }
+  uint32_t* blk = p.rng + (r * p.M + a) * 4;
+  if ((k & 3) == 0)
+    cw_philox_block(c.seed, c.rollout_base + static_cast<uint64_t>(p.flat[r]), static_cast<uint32_t>(k),
+                    static_cast<uint32_t>(a), blk);
+  return cw_mulhi32(blk[k & 3], n_prims);
+}
+
+// Predict for one agent that is present and VALID (:69-71), then what of Execute depends on
+// this agent alone: drivable area / goal (:94-96, :110), removal from the map, lane
+// projection, GetActionCost (:202-248) and PotentialReward (:250-264).
+BRM_HD void cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int j) {
+  const int A = p.A, M = p.M;
+  const int s = r * A + j;
+  CwKin t;
+  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  const double v0 = t.v, th0 = t.th;
+  const uint32_t act = j < M ? cw_pick_action(B, p, c, r, j) : 0u;
+  cw_integrate(B, t, B.prim_a[j][act], B.prim_k[j][act]);
+  uint8_t bits = 0;
+  bool present = true;
+  if (j < M || B.remove_oom) {
+    double cx[4], cy[4];
+    cw_corners(B, t, j, cx, cy);
+    if (cw_out_of_map(B, t, j, cx, cy)) bits |= CW_BIT_OOM;
+    if (j < M && cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
+    if (B.remove_oom && (bits & CW_BIT_OOM)) {
+      // World::RemoveInvalidAgents: the agent leaves the world
+      present = false;
+      bits |= CW_BIT_VANISHED;
+      p.flags[s] = 0;
+    }
+  }
+  CwFrenet f;
+  f.lane = -1; f.s = 0.0; f.lat = 0.0;
+  if (present) cw_frenet(B, t.x, t.y, f);
+  if (j < M) {
+    const double dt = B.dt;
+    const double a_lon = (t.v - v0) * B.inv_dt;
+    double cost = B.w_acc * a_lon * a_lon * dt;
+    const double theta_dot = (t.th - th0) * B.inv_dt;
+    const double avg_vel = cw_fma(0.5 * a_lon, dt, v0);
+    const double a_lat = theta_dot * avg_vel;
+    cost = cw_fma(B.w_rad * a_lat * a_lat, dt, cost);
+    cost = cw_fma(B.w_vel * fabs(v0 - B.v_des), dt, cost);
+    if (f.lane >= 0) cost = cw_fma(B.w_lane * fabs(f.lat), dt, cost);
+    const double pot_new = -B.w_pot * dt * fabs(t.v - B.v_des);
+    const double pot_cur = -B.w_pot * dt * fabs(v0 - B.v_des);
+    p.cost[r * M + j] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
+  }
+  p.x[s] = t.x; p.y[s] = t.y; p.th[s] = t.th; p.v[s] = t.v; p.cs[s] = t.cs; p.sn[s] = t.sn;
+  p.s[s] = f.s; p.lat[s] = f.lat;
+  p.lane[s] = static_cast<int16_t>(f.lane);
+  p.bits[s] = bits;
+}
+
+// drivable-area / goal bits of MCTS agent a in slot r as it stands (EvaluateRules() on a state
+// that is not the result of a step in this pool)
+BRM_HD void cw_shape_bits_item(const CwBlob& B, CwPool& p, int r, int a) {
+  const int s = r * p.A + a;
+  CwKin t;
+  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  double cx[4], cy[4];
+  cw_corners(B, t, a, cx, cy);
+  uint8_t bits = 0;
+  if (cw_out_of_map(B, t, a, cx, cy)) bits |= CW_BIT_OOM;
+  if (cw_at_goal(B, t, a, cx, cy)) bits |= CW_BIT_GOAL;
+  p.bits[s] = bits;
+}
+
+// ------------------------------------------------------------------ phase 2
+struct CwEval {
+  double r[4];
+  uint32_t w[4];  // labels: ego bits by kind, masks over j for kinds 8, 9, 10
+};
+
+// Everything of Execute that needs the other agents (:87-120), for MCTS agent a of slot r:
+// collision, labels, rule automata, reward vector, validity; the ego decides CheckTerminal
+// (:266-285) of the new state.  `rules_only`: MvmctsState::EvaluateRules() (:186-197) on the
+// state as it is.  Returns through `o`; accumulates disc * reward into the slot.
+BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_only, CwEval& o) {
+  const int A = p.A, M = p.M, V = p.V;
+  const int base = r * A, s = base + a, sm = r * M + a;
+  o.r[0] = o.r[1] = o.r[2] = o.r[3] = 0.0;
+  o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
+  const uint8_t fl = p.flags[s], bits = p.bits[s];
+  const bool present = fl & BRM_CW_PRESENT;
+  if (!present) {
+    if ((bits & CW_BIT_VANISHED) && !rules_only) {
+      // left the map during this step: the out-of-map penalty and nothing else (:121-125)
+      o.r[0] = B.w_oom;
+      p.acc[sm * 4] = cw_fma(p.disc[r], o.r[0], p.acc[sm * 4]);
+      p.bits[s] = 0;
+      if (a == 0) p.done[r] = 1;  // CheckTerminal: no ego
+    }
+    return;
+  }
+  const bool evaluated = (fl & BRM_CW_VALID) != 0;
+  const bool oom = bits & CW_BIT_OOM, goal = bits & CW_BIT_GOAL;
+  // pairwise predicates against the other agents of the rollout
+  const double xa = p.x[s], ya = p.y[s], ca = p.cs[s], sa = p.sn[s], va = p.v[s], s_a = p.s[s];
+  const int lane_a = p.lane[s];
+  const double cxa = cw_fma(B.off[a], ca, xa), cya = cw_fma(B.off[a], sa, ya);
+  const double my_len = lane_a >= 0 ? B.lanes[lane_a].length : 0.0;
+  const int my_succ = lane_a >= 0 ? B.lanes[lane_a].succ : -2;
+  bool coll = false;
+  int jf = -1;
+  double gf = 0.0, vf = 0.0;
+  uint32_t merged_mask = 0, near_mask = 0;
+  for (int j = 0; j < A; ++j) {
+    if (j == a || !(p.flags[base + j] & BRM_CW_PRESENT)) continue;
+    const double xj = p.x[base + j], yj = p.y[base + j];
+    const double cj = p.cs[base + j], sj = p.sn[base + j];
+    const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
+    const double rr = B.rad[a] + B.rad[j];
+    if (cw_fma(ddx, ddx, ddy * ddy) <= rr * rr) coll = cw_rect_overlap(B, a, xa, ya, ca, sa, j, xj, yj, cj, sj) || coll;
+    if (!evaluated) continue;
+    const int lane_j = p.lane[base + j];
+    if (lane_j >= 0) {
+      const double s_j = p.s[base + j];
+      if (lane_a >= 0) {
+        // gap along my corridor: own lane, then its successor
+        double g = 0.0;
+        bool has = false;
+        if (lane_j == lane_a) {
+          g = s_j - s_a;
+          has = true;
+        } else if (my_succ == lane_j) {
+          g = (my_len - s_a) + s_j;
+          has = true;
+        }
+        if (has && g > 0.0 && (jf < 0 || g < gf)) {
+          jf = j;
+          gf = g;
+          vf = p.v[base + j];
+        }
+      }
+      if (s_j >= B.lanes[lane_j].s_point) merged_mask |= 1u << j;
+    }
+    const double dx = xj - xa, dy = yj - ya;
+    if (cw_fma(dx, dx, dy * dy) < B.near2) near_mask |= 1u << j;
+  }
+  if (evaluated) {
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    auto add_at = [&](int idx, double val) {
+      r0 = idx == 0 ? r0 + val : r0;
+      r1 = idx == 1 ? r1 + val : r1;
+      r2 = idx == 2 ? r2 + val : r2;
+      r3 = idx == 3 ? r3 + val : r3;
+    };
+    if (!rules_only) {
+      r0 += (coll ? 1.0 : 0.0) * B.w_coll;  // :91-92
+      r0 += (oom ? 1.0 : 0.0) * B.w_oom;    // :94-96
+      add_at(V - 1, p.cost[sm]);            // :98-102
+    }
+    // labels (EvaluateRules, :165-185)
+    uint32_t w0 = 0;
+    if (coll) w0 |= 1u << BRM_CW_LABEL_COLLISION_EGO;
+    if (oom) w0 |= 1u << BRM_CW_LABEL_COLLISION_CORRIDOR;
+    if (goal) w0 |= 1u << BRM_CW_LABEL_GOAL_REACHED;
+    bool safe = true;
+    if (jf >= 0) {
+      const double dist = gf - (B.front[a] + B.rear[jf]);
+      const double dsafe = cw_fma(va, B.sd_delta, (va * va) * B.sd_ar) - (vf * vf) * B.sd_af;
+      safe = dist >= dsafe;
+    }
+    if (safe) w0 |= 1u << BRM_CW_LABEL_SAFE_DISTANCE_FRONT;
+    if (lane_a >= 0) {
+      const CwLaneHdr& L = B.lanes[lane_a];
+      if (s_a >= L.s_point) w0 |= 1u << BRM_CW_LABEL_MERGED_E;
+      if (L.flags & 1) w0 |= 1u << BRM_CW_LABEL_RIGHTMOST_LANE;
+      w0 |= 1u << BRM_CW_LABEL_ON_ROAD;
+    }
+    const uint32_t front_mask = jf >= 0 ? (1u << jf) : 0u;
+    o.w[0] = w0; o.w[1] = merged_mask; o.w[2] = front_mask; o.w[3] = near_mask;
+    if (rules_only || !(B.ego_only && a != 0)) {  // :104-108
+      uint32_t* qw = p.qw + sm * p.QW;
+      uint32_t live = p.live[sm];
+      uint32_t todo = live;
+      double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+      while (todo) {
+#if defined(__CUDA_ARCH__)
+        const int sl = __ffs(static_cast<int>(todo)) - 1;
+#else
+        const int sl = __builtin_ctz(todo);
+#endif
+        todo &= todo - 1u;
+        const CwSlotRec rec = B.slot_rec[sl];
+        const int rank = static_cast<int>((rec.z >> 8) & 0xffu) - 1;
+        const int other = rank < 0 ? 0 : (rank < a ? rank : rank + 1);
+        const uint32_t n_aps = rec.y & 0xffu;
+        const uint32_t cur = cw_q_get(qw, sl);
+        // label word of this slot: ego kinds in bits 0..7, the bound agent's kinds in 8..10
+        const uint32_t W = w0 | (((merged_mask >> other) & 1u) << BRM_CW_LABEL_MERGED_X) |
+                           (((front_mask >> other) & 1u) << BRM_CW_LABEL_IN_DIRECT_FRONT_X) |
+                           (((near_mask >> other) & 1u) << BRM_CW_LABEL_NEAR_X);
+        uint32_t letter = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (uint32_t k = 0; k < BRM_MAX_APS; ++k) letter |= ((W >> ((rec.x >> (8 * k)) & 31u)) & 1u) << k;
+        uint32_t nxt = B.rules[rec.z & 0xffu].trans[(cur << n_aps) + letter];
+        if (nxt == BRM_VIOLATION) {
+          p.viol[sm * p.R + sl] += 1;
+          nxt = (rec.y >> 24) ? cur : ((rec.y >> 16) & 0xffu);
+          const int pr = static_cast<int>((rec.y >> 8) & 0xffu);
+          const double wgt = static_cast<double>(rec.w);
+          q0 = pr == 0 ? q0 + wgt : q0;
+          q1 = pr == 1 ? q1 + wgt : q1;
+          q2 = pr == 2 ? q2 + wgt : q2;
+          q3 = pr == 3 ? q3 + wgt : q3;
+        }
+        if (nxt != cur) {
+          cw_q_set(qw, sl, nxt);
+          if (cw_slot_absorbing(B, sl, nxt)) live &= ~(1u << sl);
+        }
+      }
+      p.live[sm] = live;
+      r0 += q0; r1 += q1; r2 += q2; r3 += q3;
+    }
+    if (goal && !rules_only) add_at(V - 1, B.goal_reward);                                 // :110-113
+    if (coll && !rules_only) p.flags[s] = fl & static_cast<uint8_t>(~BRM_CW_VALID);        // :116-120
+    o.r[0] = r0; o.r[1] = r1; o.r[2] = r2; o.r[3] = r3;
+    const double disc = p.disc[r];
+    double* acc = p.acc + sm * 4;
+    acc[0] = cw_fma(disc, r0, acc[0]);
+    acc[1] = cw_fma(disc, r1, acc[1]);
+    acc[2] = cw_fma(disc, r2, acc[2]);
+    acc[3] = cw_fma(disc, r3, acc[3]);
+  }
+  // CheckTerminal of the new state (:266-285)
+  if (a == 0 && !rules_only && (p.horizon[r] - 1 == 0 || oom || coll || goal)) p.done[r] = 1;
+}
+
+// MvmctsState::CheckTerminal (:266-285) of the state in slot r as it is
+BRM_HD bool cw_check_terminal(const CwBlob& B, const CwPool& p, int r) {
+  const int s = r * p.A;
+  if (!(p.flags[s] & BRM_CW_PRESENT)) return true;
+  CwKin t;
+  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  double cx[4], cy[4];
+  cw_corners(B, t, 0, cx, cy);
+  return p.horizon[r] == 0 || cw_out_of_map(B, t, 0, cx, cy) || cw_collides(B, p, s, 0) ||
+         cw_at_goal(B, t, 0, cx, cy);
+}
+
+}  // namespace brm

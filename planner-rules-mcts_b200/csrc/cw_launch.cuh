@@ -1,0 +1,70 @@
+// Launch interface between the continuous-world host API (cw_engine.cu) and the kernels
+// (cw_kernels.cu).
+#pragma once
+#include "common.cuh"
+#include "cw_core.cuh"
+
+namespace brm {
+
+constexpr int kCwThreads = 128;  // CTA size of the continuous-world kernels
+// resident CTAs per SM the kernels are compiled for (register budget 65536 / (3 * 128) = 170)
+#ifndef BRM_CW_CTAS_PER_SM
+#define BRM_CW_CTAS_PER_SM 3
+#endif
+constexpr int kCwCtasPerSm = BRM_CW_CTAS_PER_SM;
+
+enum { MODE_ROLLOUT = 0, MODE_EXECUTE = 1, MODE_RULES = 2, MODE_QUERY = 3, MODE_REPLAY = 4 };
+
+// what the engine knows about the uploaded scenarios
+struct CwLaunchCtx {
+  const uint8_t* blobs = nullptr;       // [n_scenarios] CwBlob, stride blob_stride
+  const int32_t* blob_bytes = nullptr;  // used bytes of each blob (multiple of 16)
+  size_t blob_stride = 0;
+  int32_t blob_cap = 0;  // bytes reserved for the blob in shared memory
+  int32_t A = 0, M = 0, V = 0, R = 0;
+  int32_t P = 0;          // rollout slots of a CTA's pool
+  size_t smem_bytes = 0;  // dynamic shared memory per CTA: blob + pool + scheduler arrays
+};
+
+// bytes of the scheduler arrays that follow the pool in shared memory (cw_pool_kernel)
+inline size_t cw_sched_bytes(int P, int A, int M) {
+  size_t b = static_cast<size_t>(P) * (8 + 5 * 4);
+  b += static_cast<size_t>(P) * (2 * A + M) * 2;
+  b += static_cast<size_t>(P) * 3;
+  return (b + 15) & ~static_cast<size_t>(15);
+}
+
+struct CwArgs {
+  const uint8_t* blobs;
+  const int32_t* blob_bytes;
+  size_t blob_stride;
+  int32_t blob_cap;
+  int32_t A, M, V, R, P;
+  brm_cw_states in;  // leaves (rollouts) / states (batch modes)
+  unsigned long long* work_counter;  // next unclaimed rollout / state (one scenario) or leaf (several); zeroed
+  int64_t total;                     // work units behind the counter
+  int32_t rollouts_per_leaf, max_steps, first_exp;
+  int32_t single_scenario;  // 1: every unit lives in one scenario -> slots draw from the flat range
+  double gamma;
+  uint64_t seed, rollout_base;
+  // rollouts
+  brm_cw_rollout_out out;
+  long long* returns_fx;  // [leaves][M*V] fixed-point sums, zeroed before the launch
+  // batch modes
+  brm_cw_states bout;
+  const uint8_t* actions;  // execute: [M][n]; replay: [B][T][M]
+  double* rewards;         // execute / rules: [M][V][n]
+  uint8_t* num_actions;    // query: [M][n]
+  double* term_reward;     // query: [M][V][n]
+  int32_t do_check_terminal;
+  int32_t T;
+  brm_cw_trace tr;
+};
+
+int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
+                      const brm_rollout_params& rp, const brm_cw_rollout_out& out);
+int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_cw_states& in,
+                    const brm_cw_states* out, const uint8_t* actions, double* rewards, uint8_t* num_actions,
+                    double* term_reward, int do_check_terminal, int32_t T, const brm_cw_trace* tr);
+
+}  // namespace brm

@@ -83,6 +83,15 @@ extern "C" {
 const char* brm_last_error(void) { return brm::g_error; }
 int brm_abi_version(void) { return BRM_ABI_VERSION; }
 
+int brm_abi_struct_sizes(int32_t* out, int32_t n) {
+  const int32_t sizes[] = {sizeof(brm_rule), sizeof(brm_rollout_params), sizeof(brm_gw_params), sizeof(brm_gw_states),
+                           sizeof(brm_cw_params), sizeof(brm_cw_agent), sizeof(brm_cw_lane), sizeof(brm_cw_scenario),
+                           sizeof(brm_cw_states), sizeof(brm_cw_rollout_out), sizeof(brm_cw_trace)};
+  const int32_t count = static_cast<int32_t>(sizeof(sizes) / sizeof(sizes[0]));
+  for (int32_t i = 0; out && i < n && i < count; ++i) out[i] = sizes[i];
+  return count;
+}
+
 int brm_create(int device, void* cuda_stream, brm_engine** out) {
   BRM_REQUIRE(out != nullptr, "brm_create: out is NULL");
   *out = nullptr;

@@ -39,7 +39,7 @@ def straight_road_test_world(n_others=1, rel_distance=7.0, ego_velocity=5.0, vel
     lanes = [Lane(_line((-50.0, -1.75), (400.0, -1.75), 16), LANE_WIDTH / 2, rightmost=False),
              Lane(_line((-50.0, -5.25), (400.0, -5.25), 16), LANE_WIDTH / 2, rightmost=True)]
     road = np.array([(-50.0, 0.0), (-50.0, -7.0), (400.0, -7.0), (400.0, 0.0)])
-    state = np.zeros((A, 4), np.float32)
+    state = np.zeros((A, 4), np.float64)
     state[0] = (0.0, -1.75, 0.0, ego_velocity)
     for i in range(1, A):
         state[i] = (i * (rel_distance + 4.0), -1.75, 0.0, ego_velocity - velocity_difference)
@@ -59,7 +59,7 @@ def highway_scenario(seed=1000, n_others=3, pts_per_lane=64, steer=0.1):
     road = np.array([(-40.0, 0.0), (-40.0, -7.0), (340.0, -7.0), (340.0, 0.0)])
     rules = [RuleMonitor.MakeRule("G safe_distance_front", -1.0, 0),
              RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)]
-    state = np.zeros((1 + n_others, 4), np.float32)
+    state = np.zeros((1 + n_others, 4), np.float64)
     state[0] = (0.0, -1.75, 0.0, 5.0)
     x = 0.0
     for i in range(1, 1 + n_others):
@@ -94,7 +94,7 @@ def merge_scenario(seed=1000, n_agents=4, pts_per_lane=32, primitives=None):
     agents = [AgentModel(primitives=list(prim), goal=(280.0, 330.0, -3.5, 1.75), **CAR) for _ in range(n_agents)]
     rules = [RuleMonitor.MakeRule("G safe_distance_front", -1.0, 0),
              RuleMonitor.MakeRule(ZIP_FORMULA, -1.0, 1)]
-    state = np.zeros((n_agents, 4), np.float32)
+    state = np.zeros((n_agents, 4), np.float64)
     back = [40.0, 62.0]  # distance before the merge point already occupied on main / ramp
     for i in range(n_agents):
         on_ramp = i % 2 == 1
@@ -136,7 +136,7 @@ def intersection_scenario(seed=1000, scenario_id=0, n_agents=10, pts_per_lane=32
              RuleMonitor.MakeRule("G safe_distance_front", -1.0, 1),
              RuleMonitor.MakeRule(ZIP_FORMULA, -1.0, 2),
              RuleMonitor.MakeRule("G !(near_x#0 & in_direct_front_x#0)", -1.0, 2)]
-    state = np.zeros((n_agents, 4), np.float32)
+    state = np.zeros((n_agents, 4), np.float64)
     back = [w + 3.0] * 4
     for i in range(n_agents):
         k = i % 4
@@ -144,6 +144,9 @@ def intersection_scenario(seed=1000, scenario_id=0, n_agents=10, pts_per_lane=32
         back[k] = d + 4.0
         th = dirs[k]
         c, s = math.cos(th), math.sin(th)
-        x, y = -d, -hw
+        # a lateral offset from the centre line per agent: two agents exactly on one line would
+        # project to the SAME arc length on every lane that line crosses, and "who is in front"
+        # (gap > 0) would be decided by rounding noise -- in the reference's double arithmetic too
+        x, y = -d, -hw + rng.uniform(-0.35, 0.35)
         state[i] = (x * c - y * s, x * s + y * c, th, rng.uniform(2.0, 7.0))
     return Scenario(p, agents, n_agents, lanes, road, rules, state)

@@ -95,7 +95,7 @@ int main(int argc, char** argv) {
     std::vector<brm_cw_scenario> scn = read_file<brm_cw_scenario>(argv[2]);
     auto ctx = std::make_shared<brm::RulesMctsContext>(engine, scn);
     std::vector<uint8_t> q(ctx->M * ctx->R, 0), flags(ctx->A, BRM_CW_PRESENT | BRM_CW_VALID);
-    std::vector<float> agents = {0.f, -1.75f, 0.f, 5.f, 11.f, -1.75f, 0.f, 5.f};
+    std::vector<double> agents = {0.0, -1.75, 0.0, 5.0, 11.0, -1.75, 0.0, 5.0};
     brm::MvmctsState s0(ctx, 0, agents, flags, 20, q);
     std::vector<brm::Reward> rewards;
     std::printf("terminal0 %d num_actions %zu\n", s0.IsTerminal() ? 1 : 0, s0.GetNumActions(0));

@@ -4,16 +4,20 @@ import numpy as np
 
 from oracle import cw as ocw
 
-# Tolerances (BASELINE.json north_star): kinematics and rewards within 1e-5 relative of the
-# FP64 oracle; discrete outputs (labels, automaton states, violation counts, flags) bit-exact
-# wherever the oracle's smallest threshold margin exceeds GUARD (fp32 rounding of a ~300 m
-# coordinate is ~3e-5 m; positions accumulate a few ulps over the sub-steps).
-RTOL = 1e-5
-ATOL_POS = 2e-4      # metres (fp32 ulp of a 300 m coordinate is 3e-5)
-GUARD = 5e-4
+# Parity bar (BASELINE.json north_star: discrete outputs bit-exact, floats within 1e-5
+# relative).  The device computes the continuous world in FP64 like the reference, so the
+# tests ask for much more than north_star does:
+#   * labels, automaton states, violation counts, flags, terminal flags, lane indices, step
+#     counts: EQUAL on every trace and every rollout -- no exclusion of any kind;
+#   * kinematics, Frenet coordinates, rewards, returns: within RTOL = 1e-9 relative (measured:
+#     ~1e-13; the device uses closed forms of the Euler sub-steps, fused multiply-adds and its
+#     own sine / cosine, the oracle the sub-stepped loop and libm), ATOL for values that are
+#     exactly 0 in one of the two (lateral offsets on the centre line).
+RTOL = 1e-9
+ATOL = 1e-9
 
 
-def oracle_config(scn, precision=0):
+def oracle_config(scn):
     """cwo_config from a planner_rules_mcts_b200.Scenario."""
     p = scn.params
     c = ocw.Config()
@@ -31,7 +35,7 @@ def oracle_config(scn, precision=0):
     c.reward_vector_size = p.REWARD_VECTOR_SIZE
     c.horizon = p.HORIZON
     c.use_rule_reward_for_ego_only = 1 if p.USE_RULE_REWARD_FOR_EGO_ONLY else 0
-    c.precision = precision
+    c.remove_agents_out_of_map = 1 if p.REMOVE_AGENTS_OUT_OF_MAP else 0
     c.wheel_base = p.WHEEL_BASE
     c.integration_time_delta = p.INTEGRATION_TIME_DELTA
     c.sd_reaction_time = p.SAFE_DISTANCE_REACTION_TIME
@@ -91,37 +95,41 @@ def oracle_config(scn, precision=0):
     return c
 
 
-def close(a, b, rtol=RTOL, atol=0.0):
+def close(a, b, rtol=RTOL, atol=ATOL):
     return np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
 
 
-def compare_trace(tr, b, o, scn, min_exact_frac=0.0):
-    """GPU trace `tr` (batch index b) vs oracle replay `o`.  Discrete outputs must be equal
-    up to the first step whose oracle margin is below GUARD (after that the two runs may
-    legitimately follow different branches); continuous outputs within tolerance on the same
-    prefix.  Returns the number of steps compared."""
+def assert_close(a, b, what, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol,
+                               err_msg=str(what))
+
+
+def compare_trace(tr, b, o, scn):
+    """Trace `tr` (batch index b; brm_cw_trace layout) vs oracle replay `o`: every discrete output
+    equal on every step, continuous outputs within RTOL.  Returns the number of steps."""
     k = o["steps"]
-    safe = k
-    for t in range(k):
-        if o["margin"][t] < GUARD:
-            safe = t
-            break
-    if safe == k:
-        assert tr["steps_out"][b] == k
-    A = len(scn.agents)
-    for t in range(safe):
-        assert np.array_equal(tr["flags_out"][b, t], o["flags"][t]), ("flags", b, t)
-        assert tr["terminal_out"][b, t] == o["terminal"][t], ("terminal", b, t)
-        assert np.array_equal(tr["labels_out"][b, t], o["labels"][t]), ("labels", b, t)
-        assert np.array_equal(tr["q_out"][b, t], o["q"][t]), ("q", b, t)
-        assert np.array_equal(tr["viol_out"][b, t], o["viol"][t]), ("viol", b, t)
-        assert np.array_equal(tr["frenet_out"][b, t, :, 0], o["frenet"][t, :, 0]), ("lane", b, t)
-        assert close(tr["agents_out"][b, t], o["states"][t], atol=ATOL_POS), ("state", b, t)
-        assert close(tr["frenet_out"][b, t, :, 1:], o["frenet"][t, :, 1:], atol=ATOL_POS), ("frenet", b, t)
-        assert close(tr["rewards_out"][b, t], o["rewards"][t], rtol=1e-5, atol=2e-4), ("rewards", b, t)
-    if safe == k:
-        assert close(tr["term_reward_out"][b], o["term_reward"], atol=1e-6)
-    return safe
+    assert tr["steps_out"][b] == k, ("steps", b, tr["steps_out"][b], k)
+    for key_t, key_o in (("flags_out", "flags"), ("terminal_out", "terminal"), ("labels_out", "labels"),
+                         ("q_out", "q"), ("viol_out", "viol")):
+        assert np.array_equal(tr[key_t][b, :k], o[key_o][:k]), (key_t, b)
+    assert np.array_equal(tr["frenet_out"][b, :k, :, 0], o["frenet"][:k, :, 0]), ("lane", b)
+    assert_close(tr["agents_out"][b, :k], o["states"][:k], ("state", b))
+    assert_close(tr["frenet_out"][b, :k, :, 1:], o["frenet"][:k, :, 1:], ("frenet", b))
+    assert_close(tr["rewards_out"][b, :k], o["rewards"][:k], ("rewards", b))
+    assert_close(tr["term_reward_out"][b], o["term_reward"], ("term_reward", b))
+    return k
+
+
+def compare_rollouts(out, ref, what=""):
+    """Per-rollout outputs of brm_cw_rollout (`ro_*`) vs cwo_rollout_detail: all discrete outputs
+    equal on ALL rollouts, final states and returns within RTOL."""
+    assert np.array_equal(out["ro_steps"], ref["steps"]), (what, "steps",
+                                                            int((out["ro_steps"] != ref["steps"]).sum()))
+    assert np.array_equal(out["ro_viol"], ref["viol"]), (what, "viol")
+    assert np.array_equal(out["ro_q"], ref["q"]), (what, "q")
+    assert np.array_equal(out["ro_flags"], ref["flags"]), (what, "flags")
+    assert_close(out["ro_agents"], ref["states"], (what, "states"))
+    assert_close(out["ro_returns"], ref["returns"], (what, "returns"))
 
 
 def smoke_cw():
@@ -144,7 +152,7 @@ def smoke_cw():
         o = orc.replay(cfg, scn.initial_state, flags0, scn.params.HORIZON, acts[b])
         compared += compare_trace(tr, b, o, scn)
     assert compared > 0
-    out = eng.rollout(eng.initial_batch(), 512, seed=5, max_steps=20)
-    ref = orc.rollout(cfg, scn.initial_state, flags0, scn.params.HORIZON, 5, 0, 512, 20, scn.params.DISCOUNT_FACTOR)
-    assert abs(int(out["agent_steps"][0]) - ref["agent_steps"]) <= 0.02 * ref["agent_steps"]
-    assert np.allclose(out["returns_sum"][0], ref["returns_sum"], rtol=2e-2, atol=1.0)
+    out = eng.rollout(eng.initial_batch(), 512, seed=5, max_steps=20, detail=True)
+    ref = orc.rollout_detail(cfg, scn.initial_state, flags0, scn.params.HORIZON, 5, 0, 512, 20,
+                             scn.params.DISCOUNT_FACTOR)
+    compare_rollouts(out, ref, "smoke")

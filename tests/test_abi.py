@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(built):
     for s in syms:
         assert hasattr(lib, s), "libbrm.so does not export %s" % s
     assert sorted(_abi.SYMBOLS) == syms, "planner_rules_mcts_b200._abi.SYMBOLS out of sync with brm.h"
-    assert lib.brm_abi_version() == 2
+    assert lib.brm_abi_version() == 3
 
 
 def test_struct_sizes_match_header(built):
@@ -34,6 +34,17 @@ def test_struct_sizes_match_header(built):
     assert ctypes.sizeof(_abi.RolloutParams) == 48
     assert ctypes.sizeof(_abi.GwParams) == 7 * 4 + 8 * 4 + 4 + 3 * 8
     assert ctypes.sizeof(_abi.GwStates) == 8 + 5 * 8
+
+
+def test_ctypes_layouts_match_the_compiled_library(built):
+    """every struct of the ctypes binding has the size the library was compiled with"""
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    out = (ctypes.c_int32 * 16)()
+    n = lib.brm_abi_struct_sizes(out, 16)
+    mine = [_abi.Rule, _abi.RolloutParams, _abi.GwParams, _abi.GwStates, _abi.CwParams, _abi.CwAgent, _abi.CwLane,
+            _abi.CwScenario, _abi.CwStates, _abi.CwRolloutOut, _abi.CwTrace]
+    assert n == len(mine)
+    assert [ctypes.sizeof(t) for t in mine] == list(out[:n])
 
 
 def test_no_cpu_fallback(built):

@@ -17,7 +17,7 @@ PRIMS = [(0.0, 0.0), (1.0, 0.0), (-1.0, 0.0)]
 
 def make_world(agents, t=0.0):
     base = scenarios.straight_road_test_world()
-    return behavior.ObservedWorld(EGO, {i: np.asarray(s, np.float32) for i, s in agents.items()},
+    return behavior.ObservedWorld(EGO, {i: np.asarray(s, np.float64) for i, s in agents.items()},
                                   base.lanes, base.road, t)
 
 

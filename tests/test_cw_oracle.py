@@ -8,6 +8,7 @@ import pytest
 
 from oracle import cw as ocw
 from planner_rules_mcts_b200 import scenarios
+from planner_rules_mcts_b200.ltl import RuleMonitor
 from tests.cw_common import oracle_config
 
 FL = lambda n: np.full(n, ocw.PRESENT | ocw.VALID, np.uint8)
@@ -72,7 +73,7 @@ def test_reward_terms_follow_reference_formulas(orc):
         o = orc.replay(cfg, scn.initial_state, FL(1), 20, np.array([[act]], np.uint8))
         x0, y0, th0, v0 = scn.initial_state[0].astype(np.float64)
         x1, y1, th1, v1 = o["states"][0, 0]
-        dt = float(np.float32(p.PREDICTION_TIME_SPAN))
+        dt = p.PREDICTION_TIME_SPAN
         a = (v1 - v0) / dt
         cost = p.ACCELERATION_WEIGHT * a * a * dt
         a_lat = (th1 - th0) / dt * (0.5 * a * dt + v0)
@@ -80,7 +81,7 @@ def test_reward_terms_follow_reference_formulas(orc):
         cost += p.DESIRED_VELOCITY_WEIGHT * abs(v0 - p.DESIRED_VELOCITY) * dt
         cost += p.LANE_CENTER_WEIGHT * abs(y1 + 1.75) * dt
         pot = lambda v: -p.POTENTIAL_WEIGHT * dt * abs(v - p.DESIRED_VELOCITY)
-        want = cost + float(np.float32(p.DISCOUNT_FACTOR)) * pot(v1) - pot(v0)
+        want = cost + p.DISCOUNT_FACTOR * pot(v1) - pot(v0)
         assert abs(o["rewards"][0, 0, 0] - want) < 1e-9 * max(1.0, abs(want))
         assert abs(o["frenet"][0, 0, 2] - (y1 + 1.75)) < 1e-9 and o["frenet"][0, 0, 0] == 0
 
@@ -92,10 +93,9 @@ def test_euler_substeps(orc):
     o = orc.replay(cfg, scn.initial_state, FL(1), 20, np.array([[0]], np.uint8))
     x, y, th, v = scn.initial_state[0].astype(np.float64)
     k = np.tan(0.05) / 2.7
-    k = float(np.float32(k))
-    h = float(np.float32(0.02))
+    h = 0.02
     for n in range(15):
-        hh = float(np.float32(0.3 - 14 * 0.02)) if n == 14 else h
+        hh = (0.3 - 14 * 0.02) if n == 14 else h
         x, y, th, v = x + hh * v * np.cos(th), y + hh * v * np.sin(th), th + hh * v * k, v + hh * 2.0
     np.testing.assert_allclose(o["states"][0, 0], [x, y, th, v], rtol=1e-12)
 
@@ -113,13 +113,49 @@ def test_rule_slots_and_zip_on_merge(orc):
     assert orc.rules_per_agent(oracle_config(w)) == 3 + 2 * 9
 
 
-def test_float_instantiation_tracks_double(orc):
-    scn = scenarios.highway_scenario()
-    d = orc.rollout_detail(oracle_config(scn, 0), scn.initial_state, FL(4), 20, 7, 0, 300, 20, 0.9)
-    f = orc.rollout_detail(oracle_config(scn, 1), scn.initial_state, FL(4), 20, 7, 0, 300, 20, 0.9)
-    same = (d["steps"] == f["steps"]) & (d["viol"] == f["viol"]).all(axis=(1, 2))
-    assert same.mean() > 0.98
-    np.testing.assert_allclose(f["states"][same], d["states"][same], rtol=1e-4, atol=1e-2)
+def test_agents_leaving_the_map_are_removed(orc):
+    """bark "World::remove_agents_out_of_map": Predict removes an agent whose shape left the road
+    polygon; an MCTS agent that vanished earns OUT_OF_MAP_WEIGHT at index 0 that step and nothing
+    else (src/rules_mcts_state.cpp:121-125), has one action from then on (:129-141), earns no
+    terminal reward (:154-156); without the ego the state is terminal (:267-270)."""
+    prim = [(0.0, 0.0), (0.0, 0.6)]
+    scn = scenarios.straight_road_test_world(n_others=1, multi_agent=True, primitives=prim, rules=[
+        RuleMonitor.MakeRule("G !collision_corridor", -7.0, 0)])
+    scn.params.REMOVE_AGENTS_OUT_OF_MAP = True
+    scn.initial_state[1] = (30.0, -5.25, 0.0, 5.0)
+    cfg = oracle_config(scn)
+    acts = np.array([[0, 1]] * 12, np.uint8)       # agent 1 steers off the road, the ego keeps its lane
+    o = orc.replay(cfg, scn.initial_state, FL(2), 20, acts)
+    gone = np.flatnonzero(o["flags"][:o["steps"], 1] == 0)
+    assert len(gone) and gone[0] > 0
+    t = gone[0]
+    assert o["rewards"][t, 1, 0] == -800.0 and np.all(o["rewards"][t + 1:o["steps"], 1] == 0.0)
+    assert np.all(o["viol"][:, 1] == 0)             # it never got to see itself off the road: no rule penalty
+    assert o["term_reward"][1, 0] == 0.0 and not o["terminal"][t]
+    # the same sequence with the knob off: the agent stays, the rule fires, no out-of-map bonus branch
+    scn.params.REMOVE_AGENTS_OUT_OF_MAP = False
+    o2 = orc.replay(oracle_config(scn), scn.initial_state, FL(2), 20, acts)
+    assert np.all(o2["flags"][:o2["steps"], 1] & ocw.PRESENT) and o2["viol"][o2["steps"] - 1, 1, 0] > 0
+    assert o2["rewards"][t, 1, 0] == -800.0 - 7.0
+    # the ego leaving the map ends the episode
+    scn.params.REMOVE_AGENTS_OUT_OF_MAP = True
+    o3 = orc.replay(oracle_config(scn), scn.initial_state, FL(2), 20, np.array([[1, 0]] * 12, np.uint8))
+    k = o3["steps"]
+    assert k < 12 and o3["terminal"][k - 1] and o3["flags"][k - 1, 0] == 0 and o3["rewards"][k - 1, 0, 0] == -800.0
+
+
+def test_evaluate_rules_entry_matches_execute_labels(orc):
+    """EvaluateRules() (:186-197) on Execute's successor reproduces the labels Execute saw."""
+    scn = scenarios.merge_scenario(seed=4)
+    cfg = oracle_config(scn)
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 3, size=(6, 4)).astype(np.uint8)
+    o = orc.replay(cfg, scn.initial_state, FL(4), 20, acts)
+    for t in range(1, o["steps"]):
+        e = orc.evaluate_rules(cfg, o["states"][t], o["flags"][t - 1], 20 - t - 1, o["q"][t - 1])
+        ev = (o["flags"][t - 1, :4] & ocw.VALID) != 0
+        assert np.array_equal(e["labels"][ev], o["labels"][t][ev])
+        assert np.array_equal(e["q"][ev], o["q"][t][ev])
 
 
 def test_oracle_reproduces_committed_golden_traces(orc):

@@ -57,9 +57,9 @@ def test_cw_rollout_writes_stay_inside_their_arrays(built, name):
     ref = eng.rollout(leaves, n, seed=5, max_steps=15, detail=True)
     ar = Arena(64 << 20)
     out = dict(returns_sum=ar.take((L, M, V), torch.float64), viol_sum=ar.take((L, M, R), torch.int64),
-               agent_steps=ar.take((L,), torch.int64), ro_returns=ar.take((N, M, V), torch.float32),
+               agent_steps=ar.take((L,), torch.int64), ro_returns=ar.take((N, M, V), torch.float64),
                ro_viol=ar.take((N, M, R), torch.uint8), ro_q=ar.take((N, M, R), torch.uint8),
-               ro_agents=ar.take((N, A, 4), torch.float32), ro_flags=ar.take((N, A), torch.uint8),
+               ro_agents=ar.take((N, A, 4), torch.float64), ro_flags=ar.take((N, A), torch.uint8),
                ro_steps=ar.take((N,), torch.int32))
     d_leaves = leaves.cuda(0)
     torch.cuda.synchronize()   # the engine runs on its own stream
@@ -80,10 +80,10 @@ def test_cw_execute_and_evaluate_rules_writes_stay_inside(built):
     A, M, V, R, n = eng.A, eng.M, eng.V, eng.R, b.n
     for call in ("execute", "evaluate_rules"):
         ar = Arena(8 << 20)
-        out = brm.CwBatch(ar.take((n,), torch.int32), ar.take((A, n, 4), torch.float32), ar.take((A, n), torch.uint8),
+        out = brm.CwBatch(ar.take((n,), torch.int32), ar.take((A, n, 4), torch.float64), ar.take((A, n), torch.uint8),
                           ar.take((n,), torch.int32), ar.take((n,), torch.uint8), ar.take((M, R, n), torch.uint8),
                           ar.take((M, R, n), torch.int32))
-        rew = ar.take((M, V, n), torch.float32)
+        rew = ar.take((M, V, n), torch.float64)
         d_in = b.cuda(0)
         s_in, s_out = d_in.to_abi(), out.to_abi()
         import ctypes as C
