@@ -177,8 +177,13 @@ inline bool cw_build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out, std::
     g.m = (yb != ya) ? (xb - xa) / (yb - ya) : 0.0;
     B->road_edge[e] = g;
   }
-  // lane centre lines -> per-segment records
-  int off = 0, n_blk = 0;
+  // lane centre lines -> per-segment fields (stored field by field, n_seg_total apart)
+  int ns_total = 0;
+  for (int l = 0; l < s.n_lanes; ++l) ns_total += std::max(0, s.lanes[l].n_pts - 1);
+  BRM_BLOB_REQUIRE(ns_total <= kCwMaxSegs, "brm_cw_configure: %d lane segments (limit %d)", ns_total, kCwMaxSegs);
+  B->n_seg_total = ns_total;
+  auto seg = [&](int field, int k) -> double& { return B->segs[static_cast<size_t>(field) * ns_total + k]; };
+  int off = 0;
   for (int l = 0; l < s.n_lanes; ++l) {
     const brm_cw_lane& L = s.lanes[l];
     BRM_BLOB_REQUIRE(L.n_pts >= 2 && L.n_pts <= BRM_CW_MAX_PTS, "brm_cw_configure: lane %d has %d points", l, L.n_pts);
@@ -198,50 +203,148 @@ inline bool cw_build_blob(const brm_cw_scenario& s, CwBlob* B, int* R_out, std::
                        "brm_cw_configure: lane %d point %d outside +-%g m", l, k, BRM_CW_MAX_COORD);
     for (int k = 0; k + 1 < L.n_pts; ++k) {
       const double x0 = L.pts[k][0], y0 = L.pts[k][1], x1 = L.pts[k + 1][0], y1 = L.pts[k + 1][1];
-      CwSeg& g = B->segs[off++];
-      g.x0 = x0;
-      g.y0 = y0;
-      g.dx = x1 - x0;
-      g.dy = y1 - y0;
-      const double l2 = g.dx * g.dx + g.dy * g.dy;
+      const int g = off++;
+      const double dx = x1 - x0, dy = y1 - y0;
+      const double l2 = dx * dx + dy * dy;
       BRM_BLOB_REQUIRE(l2 > 0.0, "brm_cw_configure: lane %d has a zero-length segment at point %d", l, k);
-      g.inv_len2 = 1.0 / l2;
-      g.len = std::sqrt(l2);
-      g.s0 = s0;
-      g._pad = 0.0;
-      s0 += g.len;
+      const double len = std::sqrt(l2);
+      seg(SEG_X0, g) = x0;
+      seg(SEG_Y0, g) = y0;
+      seg(SEG_DX, g) = dx;
+      seg(SEG_DY, g) = dy;
+      seg(SEG_INV, g) = 1.0 / l2;
+      seg(SEG_LEN, g) = len;
+      seg(SEG_S0, g) = s0;
+      s0 += len;
     }
     H.length = s0;
-    // culling boxes for cw_frenet.  A point is tested as its fp32 rounding (error below
-    // 2.5e-4 m up to BRM_CW_MAX_COORD) against fp32 box edges (rounded the same way), so the
-    // boxes are grown by kSlack: a larger box only culls less, never differently.
-    const double kSlack = 2e-3;
+    // cw_frenet: grown bounding box of the lane and the segment ranges of its buckets.  A point
+    // is tested as its fp32 rounding (error below 2.5e-4 m up to BRM_CW_MAX_COORD) with fp32
+    // arithmetic (a few 1e-4 m more), so everything is grown by kSlack: growing only skips
+    // less, never differently.
+    const double kSlack = 4e-3;
     const double grow = L.half_width + kSlack;
-    for (int b0 = 0; b0 < L.n_pts - 1; b0 += kCwBlk) {
-      const int b1 = std::min(b0 + kCwBlk, L.n_pts - 1);
-      double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-      for (int k = b0; k <= b1; ++k) {
-        x0 = std::min(x0, L.pts[k][0]);
-        x1 = std::max(x1, L.pts[k][0]);
-        y0 = std::min(y0, L.pts[k][1]);
-        y1 = std::max(y1, L.pts[k][1]);
-      }
-      BRM_BLOB_REQUIRE(n_blk < kCwMaxBlkTotal, "brm_cw_configure: too many lane segments (more than %d blocks)",
-                       kCwMaxBlkTotal);
-      CwBox tb, gb;
-      tb.x0 = static_cast<float>(x0 - kSlack); tb.y0 = static_cast<float>(y0 - kSlack);
-      tb.x1 = static_cast<float>(x1 + kSlack); tb.y1 = static_cast<float>(y1 + kSlack);
-      gb.x0 = static_cast<float>(x0 - grow); gb.y0 = static_cast<float>(y0 - grow);
-      gb.x1 = static_cast<float>(x1 + grow); gb.y1 = static_cast<float>(y1 + grow);
-      B->blk_box[n_blk] = tb;
-      B->blk_gbox[n_blk] = gb;
-      B->blk_info[n_blk] = static_cast<uint32_t>(l) | (static_cast<uint32_t>(b0) << 8) |
-                           (static_cast<uint32_t>(b1 - b0) << 16);
-      ++n_blk;
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+    for (int k = 0; k < L.n_pts; ++k) {
+      x0 = std::min(x0, L.pts[k][0]);
+      x1 = std::max(x1, L.pts[k][0]);
+      y0 = std::min(y0, L.pts[k][1]);
+      y1 = std::max(y1, L.pts[k][1]);
     }
+    H.gx0 = static_cast<float>(x0 - grow);
+    H.gy0 = static_cast<float>(y0 - grow);
+    H.gx1 = static_cast<float>(x1 + grow);
+    H.gy1 = static_cast<float>(y1 + grow);
+    const int axis = (x1 - x0) >= (y1 - y0) ? 0 : 1;
+    const double c_lo = (axis ? y0 : x0) - grow - kSlack, c_hi = (axis ? y1 : x1) + grow + kSlack;
+    const double width = (c_hi - c_lo) / kCwBuckets;
+    H.b_axis = axis;
+    H.b_org = static_cast<float>(c_lo);
+    H.b_inv = static_cast<float>(1.0 / width);
+    int lo[kCwBuckets], hi[kCwBuckets];
+    for (int b = 0; b < kCwBuckets; ++b) lo[b] = 255, hi[b] = -1;
+    for (int k = 0; k + 1 < L.n_pts; ++k) {
+      const double a0 = std::min(L.pts[k][axis], L.pts[k + 1][axis]) - grow;
+      const double a1 = std::max(L.pts[k][axis], L.pts[k + 1][axis]) + grow;
+      const int b0 = std::max(0, static_cast<int>(std::floor((a0 - c_lo) / width)));
+      const int b1 = std::min(kCwBuckets - 1, static_cast<int>(std::floor((a1 - c_lo) / width)));
+      for (int b = b0; b <= b1; ++b) {
+        lo[b] = std::min(lo[b], k);
+        hi[b] = std::max(hi[b], k);
+      }
+    }
+    for (int b = 0; b < kCwBuckets; ++b)
+      B->bucket[l][b] = hi[b] < 0 ? static_cast<uint16_t>(1) /* lo 1 > hi 0: none */
+                                  : static_cast<uint16_t>(lo[b] | (hi[b] << 8));
   }
-  B->n_blk = n_blk;
-  B->total_bytes = static_cast<int32_t>(offsetof(CwBlob, segs) + static_cast<size_t>(off) * sizeof(CwSeg));
+  // cw_classify_shape: grid over the road polygon.  A cell is INSIDE / OUTSIDE when no edge of
+  // the polygon comes within kCellSlack of it (so that every point the fp32 cell index can map
+  // into the cell is decided like the cell's centre); VERTEX when a road vertex lies within
+  // the largest agent's reach of the cell (only then can a vertex be inside a rectangle whose
+  // centre is in the cell).
+  {
+    const double kCellSlack = 8e-3;
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+    for (int e = 0; e < s.n_road; ++e) {
+      x0 = std::min(x0, s.road[e][0]);
+      x1 = std::max(x1, s.road[e][0]);
+      y0 = std::min(y0, s.road[e][1]);
+      y1 = std::max(y1, s.road[e][1]);
+    }
+    const double margin = 0.05;
+    x0 -= margin; y0 -= margin; x1 += margin; y1 += margin;
+    const double cw = (x1 - x0) / kCwGrid, ch = (y1 - y0) / kCwGrid;
+    B->grid_x0 = static_cast<float>(x0);
+    B->grid_y0 = static_cast<float>(y0);
+    B->grid_ix = static_cast<float>(1.0 / cw);
+    B->grid_iy = static_cast<float>(1.0 / ch);
+    double reach = 0.0;
+    for (int i = 0; i < s.n_agents; ++i) reach = std::max(reach, std::fabs(B->off[i]) + B->rad[i]);
+    auto seg_box_dist = [](double ax, double ay, double bx, double by, double rx0, double ry0, double rx1,
+                           double ry1) {
+      // distance between the segment a-b and the rectangle, by sampling-free clipping: 0 if the
+      // segment enters the rectangle, else the smallest corner / end point distance
+      auto pt_rect = [&](double px, double py) {
+        const double dx = std::max(std::max(rx0 - px, px - rx1), 0.0), dy = std::max(std::max(ry0 - py, py - ry1), 0.0);
+        return std::sqrt(dx * dx + dy * dy);
+      };
+      auto pt_seg = [&](double px, double py) {
+        const double vx = bx - ax, vy = by - ay, l2 = vx * vx + vy * vy;
+        double t = l2 > 0.0 ? ((px - ax) * vx + (py - ay) * vy) / l2 : 0.0;
+        t = std::min(std::max(t, 0.0), 1.0);
+        const double ex = px - (ax + t * vx), ey = py - (ay + t * vy);
+        return std::sqrt(ex * ex + ey * ey);
+      };
+      // Liang-Barsky: does the segment pass through the rectangle?
+      double t0 = 0.0, t1 = 1.0;
+      const double dx = bx - ax, dy = by - ay;
+      const double pp[4] = {-dx, dx, -dy, dy}, qq[4] = {ax - rx0, rx1 - ax, ay - ry0, ry1 - ay};
+      bool hit = true;
+      for (int i = 0; i < 4 && hit; ++i) {
+        if (pp[i] == 0.0) {
+          if (qq[i] < 0.0) hit = false;
+        } else {
+          const double r = qq[i] / pp[i];
+          if (pp[i] < 0.0) t0 = std::max(t0, r); else t1 = std::min(t1, r);
+          if (t0 > t1) hit = false;
+        }
+      }
+      if (hit) return 0.0;
+      double d = std::min(pt_rect(ax, ay), pt_rect(bx, by));
+      d = std::min(d, std::min(std::min(pt_seg(rx0, ry0), pt_seg(rx1, ry0)), std::min(pt_seg(rx0, ry1), pt_seg(rx1, ry1))));
+      return d;
+    };
+    auto inside = [&](double px, double py) {
+      bool in = false;
+      for (int e = 0; e < s.n_road; ++e) {
+        const int f = (e + 1) % s.n_road;
+        const double xa = s.road[e][0], ya = s.road[e][1], xb = s.road[f][0], yb = s.road[f][1];
+        if ((ya > py) != (yb > py) && px < (xb - xa) / (yb - ya) * (py - ya) + xa) in = !in;
+      }
+      return in;
+    };
+    memset(B->grid, 0, sizeof(B->grid));
+    for (int gy = 0; gy < kCwGrid; ++gy)
+      for (int gx = 0; gx < kCwGrid; ++gx) {
+        const double rx0 = x0 + gx * cw, rx1 = rx0 + cw, ry0 = y0 + gy * ch, ry1 = ry0 + ch;
+        double d_edge = 1e300, d_vert = 1e300;
+        for (int e = 0; e < s.n_road; ++e) {
+          const int f = (e + 1) % s.n_road;
+          d_edge = std::min(d_edge, seg_box_dist(s.road[e][0], s.road[e][1], s.road[f][0], s.road[f][1], rx0, ry0,
+                                                 rx1, ry1));
+          const double vx = std::max(std::max(rx0 - s.road[e][0], s.road[e][0] - rx1), 0.0);
+          const double vy = std::max(std::max(ry0 - s.road[e][1], s.road[e][1] - ry1), 0.0);
+          d_vert = std::min(d_vert, std::sqrt(vx * vx + vy * vy));
+        }
+        uint32_t code = 0;
+        if (d_edge > kCellSlack) code |= inside(0.5 * (rx0 + rx1), 0.5 * (ry0 + ry1)) ? CW_CELL_INSIDE : CW_CELL_OUTSIDE;
+        if (d_vert <= reach + kCellSlack) code |= CW_CELL_VERTEX;
+        const int c = gy * kCwGrid + gx;
+        B->grid[c >> 3] |= code << ((c & 7) * 4);
+      }
+  }
+  B->total_bytes = static_cast<int32_t>(offsetof(CwBlob, segs) +
+                                       static_cast<size_t>(SEG_FIELDS) * ns_total * sizeof(double));
   return true;
 }
 

@@ -25,21 +25,45 @@
 
 #if defined(__CUDACC__)
 #define BRM_HD __host__ __device__ __forceinline__
+#define BRM_HD_NOINLINE inline __host__ __device__ __noinline__  // one copy in the kernel: the code has to fit the instruction cache
 #else
 #define BRM_HD inline
+#define BRM_HD_NOINLINE inline
+#endif
+
+// loops whose unrolling costs more instruction-cache misses than it gains
+#if defined(__CUDA_ARCH__) && !defined(BRM_CW_BIG_FRENET)
+#define BRM_LOOP_SMALL _Pragma("unroll 1")
+#else
+#define BRM_LOOP_SMALL
+#endif
+#if defined(__CUDA_ARCH__) && defined(BRM_CW_SMALL_EULER)
+#define BRM_LOOP_EULER _Pragma("unroll 1")
+#elif defined(__CUDA_ARCH__) && defined(BRM_CW_EULER5)
+#define BRM_LOOP_EULER _Pragma("unroll 5")
+#else
+#define BRM_LOOP_EULER
 #endif
 
 namespace brm {
 
 // ------------------------------------------------------------------ scenario blob
-struct alignas(16) CwSeg {
-  double x0, y0, dx, dy;
-  double inv_len2, len, s0, _pad;
-};
+// lane segments are stored field by field (x0[], y0[], dx[], dy[], inv_len2[], len[], s0[], each
+// n_seg_total long): the lanes of a warp project different points onto different segments, and
+// 8-byte strides spread those reads over the shared-memory banks (64-byte records would put
+// every segment on the same two)
+enum { SEG_X0 = 0, SEG_Y0, SEG_DX, SEG_DY, SEG_INV, SEG_LEN, SEG_S0, SEG_FIELDS };
+
+constexpr int kCwBuckets = 64;  // buckets of a lane's segment index (cw_frenet)
 
 struct alignas(16) CwLaneHdr {
   int32_t seg_off, n_seg, succ, flags;
   double hw2, length, s_point, _pad;
+  // fp32, conservative: bounding box of the centre line grown by the half width; the lane's
+  // extent along its longer axis cut into kCwBuckets buckets (origin, 1 / width)
+  float gx0, gy0, gx1, gy1;
+  float b_org, b_inv;
+  int32_t b_axis, _pi;
 };
 
 struct alignas(16) CwEdge {
@@ -57,14 +81,19 @@ struct alignas(16) CwSlotRec {
   float w;     // weight
 };
 
-constexpr int kCwBlk = 8;                                                // segments per culling block
-constexpr int kCwMaxBlk = (BRM_CW_MAX_PTS - 1 + kCwBlk - 1) / kCwBlk;    // blocks per lane
-constexpr int kCwMaxBlkTotal = BRM_CW_MAX_LANES * kCwMaxBlk;             // 64: one bit each
 constexpr int kCwMaxSegs = BRM_CW_MAX_LANES * (BRM_CW_MAX_PTS - 1);
+constexpr int kCwGrid = 64;  // cells per axis of the drivable-area grid
+// drivable-area grid: 4 bits per cell
+enum : uint32_t {
+  CW_CELL_INSIDE = 1,   // the whole cell (and a margin) lies inside the road polygon
+  CW_CELL_OUTSIDE = 2,  // the whole cell (and a margin) lies outside
+  CW_CELL_VERTEX = 4,   // a road vertex lies within the largest agent's reach of the cell
+};
 
 struct alignas(16) CwBlob {
   int32_t A, M, V, R, n_lanes, n_road, n_rules, n_sub;
-  int32_t ego_only, total_bytes, n_blk, remove_oom;
+  int32_t ego_only, total_bytes, _pb, remove_oom;
+  int32_t n_seg_total, _pi0, _pi1, _pi2;
   double w_coll, w_oom, w_pot, w_acc, w_rad, w_vel, w_lane, dt;
   double v_des, gamma, goal_reward, h_sub, h_last, sd_delta, sd_ar, sd_af;
   double near2, c2, t_total, inv_dt;  // c2, t_total: closed form of the Euler sub-steps without steering
@@ -79,16 +108,17 @@ struct alignas(16) CwBlob {
   uint8_t slot_rule[BRM_CW_MAX_SLOTS];
   brm_rule rules[BRM_MAX_RULES];  // trans stored with AP k of the letter at bit k
   CwEdge road_edge[BRM_CW_MAX_ROAD];
-  // culling of the nearest-segment search (fp32, conservative): blocks of kCwBlk consecutive
-  // segments in lane order; blk_gbox = bounding box grown by the lane's half width (a point
-  // outside it is farther than the half width from every segment of the block), blk_box =
-  // bounding box; both grown by a slack that covers the fp32 rounding of coordinates up to
-  // BRM_CW_MAX_COORD.  blk_info = lane | first segment (within the lane) << 8 | count << 16
-  CwBox blk_gbox[kCwMaxBlkTotal];
-  CwBox blk_box[kCwMaxBlkTotal];
-  uint32_t blk_info[kCwMaxBlkTotal];
+  // nearest-segment search (cw_frenet): per lane and bucket of its longer axis the range
+  // [lo, hi] (lo | hi << 8; lo > hi: none) of the segments that come within the half width of
+  // any point of the bucket -- built with a slack that covers the fp32 evaluation of the bucket
+  // index for coordinates up to BRM_CW_MAX_COORD
+  uint16_t bucket[BRM_CW_MAX_LANES][kCwBuckets];
+  // drivable-area test (cw_classify_shape): a grid over the road polygon's bounding box, 4
+  // bits per cell (CW_CELL_*), 8 cells per word; origin and 1 / cell size
+  float grid_x0, grid_y0, grid_ix, grid_iy;
+  uint32_t grid[kCwGrid * kCwGrid / 8];
   CwLaneHdr lanes[BRM_CW_MAX_LANES];
-  CwSeg segs[kCwMaxSegs];  // last: only the used part is copied
+  double segs[SEG_FIELDS * kCwMaxSegs];  // last: only the used part (SEG_FIELDS * n_seg_total) is copied
 };
 static_assert(sizeof(CwBlob) % 16 == 0, "blob must be a multiple of 16 bytes");
 static_assert(offsetof(CwBlob, segs) % 16 == 0, "segment array must be 16-byte aligned");
@@ -100,68 +130,69 @@ enum : uint8_t {
   CW_BIT_OOM = 1,       // drivable-area test of this step: shape not within the road polygon
   CW_BIT_GOAL = 2,      // shape within the goal
   CW_BIT_VANISHED = 4,  // left the map during this step (remove_agents_out_of_map)
+  CW_BIT_PENDING = 8,   // phase 1 could not tell the drivable-area test from the grid: cw_exact_shape_item
+  CW_BIT_BEYOND = 16,   // on a lane, at or beyond its merge point (s >= s_point): merged_e / merged_x#j
 };
+
+// Records are padded to an odd number of 8-byte words, so that the lanes of a warp, which
+// work on neighbouring slots, read a field from different banks.
+constexpr int kAgWords = 9;  // agent record: x, y, th, v, cs, sn, s, lat, meta
+struct CwMeta {              // the 9th word of an agent record
+  int16_t lane;              // lane of the current position, -1: none
+  uint8_t flags;             // BRM_CW_PRESENT | BRM_CW_VALID
+  uint8_t bits;              // CW_BIT_*
+  uint32_t _spare;
+};
+enum { AG_X = 0, AG_Y, AG_TH, AG_V, AG_CS, AG_SN, AG_S, AG_LAT, AG_META };
+// MCTS agent record, in 8-byte words: cost, acc[4], rng[4 x u32], then u32 live, u32 qw[QW],
+// u8 viol[R]
+enum { MC_COST = 0, MC_ACC = 1, MC_RNG = 5, MC_TAIL = 7 };
+// rollout header, 8 x int32: flat, leaf, k, horizon, nsteps, state bytes (busy, done, live, rflag)
+enum { H_FLAT = 0, H_LEAF, H_K, H_HORIZON, H_NSTEPS, H_STATE, H_WORDS = 8 };
+enum { HS_BUSY = 0, HS_DONE = 1, HS_LIVE = 2, HS_RFLAG = 3 };
 
 struct CwPool {
-  int32_t P, A, M, R, V, QW;  // QW = words of packed automaton states per agent = ceil(R / 8)
-  // agent slots [P * A]
-  double *x, *y, *th, *v, *cs, *sn, *s, *lat;
-  int16_t* lane;   // lane of the current position, -1: none
-  uint8_t* flags;  // BRM_CW_PRESENT | BRM_CW_VALID
-  uint8_t* bits;   // CW_BIT_*
-  // MCTS agent slots [P * M]
-  double* cost;       // action cost + potential of the current step (phase 1 -> phase 2)
-  double* acc;        // [P * M][4] discounted return so far
-  uint32_t* rng;      // [P * M][4] Philox block serving steps 4b .. 4b+3
-  uint32_t* qw;       // [P * M][QW] automaton states, 4 bits per rule slot
-  uint32_t* live;     // [P * M] rule slots whose state is not absorbing
-  uint8_t* viol;      // [P * M][R] violations since the slot was filled
-  // rollout slots [P]
-  int32_t *flat, *leaf, *k, *horizon;
-  double* disc;
-  uint32_t* nsteps;   // agents integrated so far
-  uint8_t *busy, *done;
+  int32_t P, A, M, R, V, QW, mw;  // QW = words of packed automaton states per agent; mw = words per MCTS record
+  double* ag;    // [P * A][kAgWords]
+  double* mc;    // [P * M][mw]
+  double* disc;  // [P] discount of the current step
+  int32_t* hdr;  // [P][H_WORDS]
 };
 
+BRM_HD int cw_mc_words(int R) {
+  const int QW = (R + 7) / 8;
+  int w = MC_TAIL + (4 * (1 + QW) + R + 7) / 8;
+  return (w & 1) ? w : w + 1;
+}
+
 BRM_HD size_t cw_pool_bytes(int P, int A, int M, int R) {
-  const size_t S = static_cast<size_t>(P) * A, Sm = static_cast<size_t>(P) * M;
-  const size_t QW = (R + 7) / 8;
-  size_t b = S * 8 * sizeof(double);
-  b += Sm * (1 + 4) * sizeof(double);
+  size_t b = static_cast<size_t>(P) * A * kAgWords * sizeof(double);
+  b += static_cast<size_t>(P) * M * cw_mc_words(R) * sizeof(double);
   b += static_cast<size_t>(P) * sizeof(double);
-  b += Sm * (4 + QW + 1) * sizeof(uint32_t);
-  b += static_cast<size_t>(P) * 5 * sizeof(int32_t);
-  b += S * sizeof(int16_t);
-  b = (b + 3) & ~static_cast<size_t>(3);
-  b += S * 2 + Sm * R + static_cast<size_t>(P) * 2;
+  b += static_cast<size_t>(P) * H_WORDS * sizeof(int32_t);
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
 // carve the arrays out of `mem` (16-byte aligned, cw_pool_bytes large)
 BRM_HD void cw_pool_carve(CwPool& p, void* mem, int P, int A, int M, int R, int V) {
   p.P = P; p.A = A; p.M = M; p.R = R; p.V = V; p.QW = (R + 7) / 8;
-  const size_t S = static_cast<size_t>(P) * A, Sm = static_cast<size_t>(P) * M;
+  p.mw = cw_mc_words(R);
   double* d = static_cast<double*>(mem);
-  p.x = d; d += S;  p.y = d; d += S;  p.th = d; d += S;  p.v = d; d += S;
-  p.cs = d; d += S; p.sn = d; d += S; p.s = d; d += S;   p.lat = d; d += S;
-  p.cost = d; d += Sm;
-  p.acc = d; d += Sm * 4;
+  p.ag = d; d += static_cast<size_t>(P) * A * kAgWords;
+  p.mc = d; d += static_cast<size_t>(P) * M * p.mw;
   p.disc = d; d += P;
-  uint32_t* u = reinterpret_cast<uint32_t*>(d);
-  p.rng = u; u += Sm * 4;
-  p.qw = u; u += Sm * p.QW;
-  p.live = u; u += Sm;
-  int32_t* i = reinterpret_cast<int32_t*>(u);
-  p.flat = i; i += P;  p.leaf = i; i += P;  p.k = i; i += P;  p.horizon = i; i += P;
-  p.nsteps = reinterpret_cast<uint32_t*>(i); i += P;
-  int16_t* h = reinterpret_cast<int16_t*>(i);
-  p.lane = h; h += S;
-  uintptr_t a = (reinterpret_cast<uintptr_t>(h) + 3) & ~static_cast<uintptr_t>(3);
-  uint8_t* b = reinterpret_cast<uint8_t*>(a);
-  p.flags = b; b += S;  p.bits = b; b += S;
-  p.viol = b; b += Sm * R;
-  p.busy = b; b += P;  p.done = b; b += P;
+  p.hdr = reinterpret_cast<int32_t*>(d);
 }
+
+BRM_HD double* cw_ag(const CwPool& p, int s) { return p.ag + s * kAgWords; }
+BRM_HD CwMeta* cw_meta(const CwPool& p, int s) { return reinterpret_cast<CwMeta*>(p.ag + s * kAgWords + AG_META); }
+BRM_HD double* cw_mc(const CwPool& p, int sm) { return p.mc + sm * p.mw; }
+BRM_HD uint32_t* cw_mc_rng(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + MC_RNG); }
+BRM_HD uint32_t* cw_mc_live(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + MC_TAIL); }
+BRM_HD uint32_t* cw_mc_qw(const CwPool& p, int sm) { return cw_mc_live(p, sm) + 1; }
+BRM_HD uint8_t* cw_mc_viol(const CwPool& p, int sm) { return reinterpret_cast<uint8_t*>(cw_mc_qw(p, sm) + p.QW); }
+BRM_HD int32_t* cw_hdr(const CwPool& p, int r) { return p.hdr + r * H_WORDS; }
+BRM_HD uint8_t* cw_hstate(const CwPool& p, int r) { return reinterpret_cast<uint8_t*>(cw_hdr(p, r) + H_STATE); }
 
 // ------------------------------------------------------------------ small math
 BRM_HD double cw_fma(double a, double b, double c) { return fma(a, b, c); }
@@ -263,6 +294,7 @@ BRM_HD void cw_integrate(const CwBlob& B, CwKin& t, double acc, double kap) {
   double x = t.x, y = t.y, v = t.v;
   if (kap == 0.0) {
     const double cs = t.cs, sn = t.sn;
+    BRM_LOOP_EULER
     for (int n = 0; n < n_sub; ++n) {
       const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
       x = x + h * (v * cs);
@@ -271,6 +303,7 @@ BRM_HD void cw_integrate(const CwBlob& B, CwKin& t, double acc, double kap) {
     }
   } else {
     double dx = 0.0, dy = 0.0, th = t.th, c = t.cs, s = t.sn;
+    _Pragma("unroll 1")
     for (int n = 0; n < n_sub; ++n) {
       const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
       const double hv = h * v;
@@ -306,77 +339,54 @@ struct CwFrenet {
 };
 
 // Nearest point on every lane centre line; the first lane that contains the point wins
-// (the brute-force search over all segments of the oracle).  Two cullings that cannot change
-// the answer: only blocks whose grown box contains the point can hold a segment within the
-// lane's half width; a block whose box is farther than the best distance so far cannot hold
-// a nearer segment.  Distances themselves are FP64.
-BRM_HD void cw_frenet(const CwBlob& B, double x, double y, CwFrenet& f) {
+// (the brute-force search over all segments of the oracle).  What is skipped cannot change
+// the answer: a lane whose grown bounding box does not contain the point, and on a lane every
+// segment outside the bucket range of the point's coordinate -- a segment within the half
+// width of the point is in that range, and if none is, the lane does not contain the point.
+// Distances themselves are FP64.
+BRM_HD_NOINLINE CwFrenet cw_frenet(const CwBlob& B, double x, double y) {
+  CwFrenet f;
   f.lane = -1;
   f.s = 0.0;
   f.lat = 0.0;
   const float xf = static_cast<float>(x), yf = static_cast<float>(y);
-  const int nb = B.n_blk;
-  uint32_t lo = 0u, hi = 0u, bit = 1u;
-  const int n0 = nb < 32 ? nb : 32;
-  for (int i = 0; i < n0; ++i, bit <<= 1) {
-    const CwBox g = B.blk_gbox[i];
-    if (xf >= g.x0 && xf <= g.x1 && yf >= g.y0 && yf <= g.y1) lo |= bit;
+  const int ns = B.n_seg_total;
+  const double* X0 = B.segs + SEG_X0 * ns;
+  const double* Y0 = B.segs + SEG_Y0 * ns;
+  const double* DX = B.segs + SEG_DX * ns;
+  const double* DY = B.segs + SEG_DY * ns;
+  const double* INV = B.segs + SEG_INV * ns;
+  // candidate lanes first (uniform loop), then one candidate per round: the lanes of a warp
+  // look at different road lanes, but they all do it at the same time
+  uint32_t cand = 0u;
+  const int n_lanes = B.n_lanes;
+  BRM_LOOP_SMALL
+  for (int l = 0; l < n_lanes; ++l) {
+    const CwLaneHdr& L = B.lanes[l];
+    if (xf >= L.gx0 && xf <= L.gx1 && yf >= L.gy0 && yf <= L.gy1) cand |= 1u << l;
   }
-  bit = 1u;
-  for (int i = 32; i < nb; ++i, bit <<= 1) {
-    const CwBox g = B.blk_gbox[i];
-    if (xf >= g.x0 && xf <= g.x1 && yf >= g.y0 && yf <= g.y1) hi |= bit;
-  }
-  unsigned long long mask = static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
-  int l = -1, n_seg = 0, seg_off = 0, bk = 0;
-  double best = 1e300, btu = 0.0, hw2 = 0.0;
-  for (;;) {
-    int i = -1;
-    if (mask) {
+  while (cand) {
 #if defined(__CUDA_ARCH__)
-      i = __ffsll(static_cast<long long>(mask)) - 1;
+    const int l = __ffs(static_cast<int>(cand)) - 1;
 #else
-      i = __builtin_ctzll(mask);
+    const int l = __builtin_ctz(cand);
 #endif
-    }
-    const uint32_t info = i >= 0 ? B.blk_info[i] : 0xffu;
-    const int li = static_cast<int>(info & 0xffu);
-    if (li != l) {
-      // lane l is finished: is the point on it?
-      if (l >= 0 && best <= hw2) {
-        const bool interior = !(bk == 0 && btu < 0.0) && !(bk == n_seg - 1 && btu > 1.0);
-        if (interior) {
-          const CwSeg& g = B.segs[seg_off + bk];
-          const double bt = fmin(fmax(btu, 0.0), 1.0);
-          const double wx = x - g.x0, wy = y - g.y0;
-          const double cross = cw_fma(g.dx, wy, -(g.dy * wx));
-          f.lane = l;
-          f.s = cw_fma(bt, g.len, g.s0);
-          const double dd = sqrt(best);
-          f.lat = cross < 0.0 ? -dd : dd;
-          return;
-        }
-      }
-      if (i < 0) return;
-      l = li;
-      const CwLaneHdr& L = B.lanes[l];
-      n_seg = L.n_seg;
-      seg_off = L.seg_off;
-      hw2 = L.hw2;
-      best = 1e300;
-    }
-    mask &= mask - 1ull;
-    const CwBox bb = B.blk_box[i];
-    const float gx = fmaxf(fmaxf(bb.x0 - xf, xf - bb.x1), 0.f);
-    const float gy = fmaxf(fmaxf(bb.y0 - yf, yf - bb.y1), 0.f);
-    if (static_cast<double>(gx * gx + gy * gy) * 0.999999 > best) continue;
-    const int b0 = static_cast<int>((info >> 8) & 0xffu);
-    const int b1 = b0 + static_cast<int>(info >> 16);
-    const CwSeg* seg = B.segs + seg_off;
-    for (int k = b0; k < b1; ++k) {
-      const double wx = x - seg[k].x0, wy = y - seg[k].y0;
-      const double sdx = seg[k].dx, sdy = seg[k].dy;
-      const double tu = cw_fma(wx, sdx, wy * sdy) * seg[k].inv_len2;
+    cand &= cand - 1u;
+    const CwLaneHdr& L = B.lanes[l];
+    const float fb = ((L.b_axis ? yf : xf) - L.b_org) * L.b_inv;
+    int b = static_cast<int>(fb);
+    b = b < 0 ? 0 : (b > kCwBuckets - 1 ? kCwBuckets - 1 : b);
+    const uint32_t range = B.bucket[l][b];
+    const int k_lo = static_cast<int>(range & 0xffu), k_hi = static_cast<int>(range >> 8);
+    const int seg_off = L.seg_off;
+    int bk = 0;
+    double best = 1e300, btu = 0.0;
+    BRM_LOOP_SMALL
+    for (int k = k_lo; k <= k_hi; ++k) {
+      const int g = seg_off + k;
+      const double wx = x - X0[g], wy = y - Y0[g];
+      const double sdx = DX[g], sdy = DY[g];
+      const double tu = cw_fma(wx, sdx, wy * sdy) * INV[g];
       const double tc = fmin(fmax(tu, 0.0), 1.0);
       const double ex = cw_fma(-tc, sdx, wx), ey = cw_fma(-tc, sdy, wy);
       const double d2 = cw_fma(ex, ex, ey * ey);
@@ -386,7 +396,27 @@ BRM_HD void cw_frenet(const CwBlob& B, double x, double y, CwFrenet& f) {
         btu = tu;
       }
     }
+    if (best <= L.hw2) {
+      const bool interior = !(bk == 0 && btu < 0.0) && !(bk == L.n_seg - 1 && btu > 1.0);
+      if (interior) {
+        const int g = seg_off + bk;
+        const double bt = fmin(fmax(btu, 0.0), 1.0);
+        const double wx = x - X0[g], wy = y - Y0[g];
+        const double cross = cw_fma(DX[g], wy, -(DY[g] * wx));
+        f.lane = l;
+        f.s = cw_fma(bt, B.segs[SEG_LEN * ns + g], B.segs[SEG_S0 * ns + g]);
+        const double dd = sqrt(best);
+        f.lat = cross < 0.0 ? -dd : dd;
+        return f;
+      }
+    }
   }
+  return f;
+}
+
+// the beyond-point label of a projected agent (EgoBeyondPoint / AgentBeyondPoint label functions)
+BRM_HD uint8_t cw_beyond_bit(const CwBlob& B, const CwFrenet& f) {
+  return (f.lane >= 0 && f.s >= B.lanes[f.lane].s_point) ? CW_BIT_BEYOND : 0;
 }
 
 // ------------------------------------------------------------------ shape predicates
@@ -405,7 +435,7 @@ BRM_HD void cw_corners(const CwBlob& B, const CwKin& t, int a, double (&cx)[4], 
 
 // EvaluatorDrivableArea restated: a corner outside the road polygon (crossing number), or a
 // road vertex strictly inside the rectangle
-BRM_HD bool cw_out_of_map(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
+BRM_HD bool cw_out_of_map_corners(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
   uint32_t inside = 0;
   bool vertex_in = false;
   const double f = B.front[a], r = B.rear[a], h = B.hw[a];
@@ -424,6 +454,46 @@ BRM_HD bool cw_out_of_map(const CwBlob& B, const CwKin& t, int a, const double (
     vertex_in = (lx > -r && lx < f && fabs(ly) < h) || vertex_in;
   }
   return inside != 0xFu || vertex_in;
+}
+
+// the exact test from a pose (everything by value: one out-of-line copy in the kernels)
+BRM_HD_NOINLINE bool cw_out_of_map_pose(const CwBlob& B, double x, double y, double cs, double sn, int a) {
+  CwKin t;
+  t.x = x; t.y = y; t.th = 0.0; t.v = 0.0; t.cs = cs; t.sn = sn;
+  double cx[4], cy[4];
+  cw_corners(B, t, a, cx, cy);
+  return cw_out_of_map_corners(B, t, a, cx, cy);
+}
+BRM_HD bool cw_out_of_map(const CwBlob& B, const CwKin& t, int a, const double (&)[4], const double (&)[4]) {
+  return cw_out_of_map_pose(B, t.x, t.y, t.cs, t.sn, a);
+}
+
+// Drivable-area test through the grid: 1 = certainly out of the map, 0 = certainly inside,
+// -1 = too close to the polygon's boundary or to one of its vertices to tell (the caller runs
+// cw_out_of_map).  A corner in an OUTSIDE cell is outside the polygon; four corners in INSIDE
+// cells with no road vertex within reach of the centre's cell leave nothing that could make
+// the exact test true.
+BRM_HD int cw_classify_shape(const CwBlob& B, const CwKin& t, const double (&cx)[4], const double (&cy)[4]) {
+  auto cell = [&](double px, double py) -> uint32_t {
+    const float fx = (static_cast<float>(px) - B.grid_x0) * B.grid_ix;
+    const float fy = (static_cast<float>(py) - B.grid_y0) * B.grid_iy;
+    if (!(fx >= 0.f && fx < static_cast<float>(kCwGrid) && fy >= 0.f && fy < static_cast<float>(kCwGrid)))
+      return CW_CELL_OUTSIDE;  // the grid covers the polygon and a margin around it
+    const int c = static_cast<int>(fy) * kCwGrid + static_cast<int>(fx);
+    return (B.grid[c >> 3] >> ((c & 7) * 4)) & 0xFu;
+  };
+  uint32_t all = 0xFu, any = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t c = cell(cx[k], cy[k]);
+    all &= c;
+    any |= c;
+  }
+  if (any & CW_CELL_OUTSIDE) return 1;
+  if (!(all & CW_CELL_INSIDE)) return -1;
+  return (cell(t.x, t.y) & CW_CELL_VERTEX) ? -1 : 0;
 }
 
 BRM_HD bool cw_at_goal(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
@@ -452,14 +522,20 @@ BRM_HD bool cw_rect_overlap(const CwBlob& B, int a, double xa, double ya, double
   return hit;
 }
 
+BRM_HD void cw_load_kin(const double* rec, CwKin& t) {
+  t.x = rec[AG_X]; t.y = rec[AG_Y]; t.th = rec[AG_TH]; t.v = rec[AG_V]; t.cs = rec[AG_CS]; t.sn = rec[AG_SN];
+}
+
 BRM_HD bool cw_collides(const CwBlob& B, const CwPool& p, int base, int a) {
   const int A = p.A;
-  const double xa = p.x[base + a], ya = p.y[base + a], ca = p.cs[base + a], sa = p.sn[base + a];
+  const double* ra = cw_ag(p, base + a);
+  const double xa = ra[AG_X], ya = ra[AG_Y], ca = ra[AG_CS], sa = ra[AG_SN];
   const double cxa = cw_fma(B.off[a], ca, xa), cya = cw_fma(B.off[a], sa, ya);
   bool coll = false;
   for (int j = 0; j < A; ++j) {
-    if (j == a || !(p.flags[base + j] & BRM_CW_PRESENT)) continue;
-    const double xj = p.x[base + j], yj = p.y[base + j], cj = p.cs[base + j], sj = p.sn[base + j];
+    if (j == a || !(cw_meta(p, base + j)->flags & BRM_CW_PRESENT)) continue;
+    const double* rj = cw_ag(p, base + j);
+    const double xj = rj[AG_X], yj = rj[AG_Y], cj = rj[AG_CS], sj = rj[AG_SN];
     const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
     const double rr = B.rad[a] + B.rad[j];
     if (cw_fma(ddx, ddx, ddy * ddy) > rr * rr) continue;
@@ -496,7 +572,7 @@ BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int 
   cw_sincos(t.th, &t.sn, &t.cs);
   CwFrenet f;
   f.lane = -1; f.s = 0.0; f.lat = 0.0;
-  if (fl & BRM_CW_PRESENT) cw_frenet(B, t.x, t.y, f);
+  if (fl & BRM_CW_PRESENT) f = cw_frenet(B, t.x, t.y);
   uint8_t bits = 0;
   if (j == 0 && (fl & BRM_CW_PRESENT) && !(fl & BRM_CW_VALID)) {
     // a frozen ego never passes phase 1: its drivable-area / goal bits are those of the leaf
@@ -505,38 +581,52 @@ BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int 
     if (cw_out_of_map(B, t, j, cx, cy)) bits |= CW_BIT_OOM;
     if (cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
   }
-  p.x[s] = t.x; p.y[s] = t.y; p.th[s] = t.th; p.v[s] = t.v; p.cs[s] = t.cs; p.sn[s] = t.sn;
-  p.s[s] = f.s; p.lat[s] = f.lat;
-  p.lane[s] = static_cast<int16_t>(f.lane);
-  p.flags[s] = fl;
-  p.bits[s] = bits;
+  bits |= cw_beyond_bit(B, f);
+  double* rec = cw_ag(p, s);
+  rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
+  rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
+  CwMeta m;
+  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits; m._spare = 0;
+  *cw_meta(p, s) = m;
   if (j < M) {
     const int sm = r * M + j;
-    p.cost[sm] = 0.0;
-    for (int v = 0; v < 4; ++v) p.acc[sm * 4 + v] = 0.0;
-    for (int v = 0; v < 4; ++v) p.rng[sm * 4 + v] = 0u;
-    uint32_t* qw = p.qw + sm * p.QW;
+    double* mc = cw_mc(p, sm);
+    mc[MC_COST] = 0.0;
+    for (int v = 0; v < 4; ++v) mc[MC_ACC + v] = 0.0;
+    uint32_t* rng = cw_mc_rng(p, sm);
+    for (int v = 0; v < 4; ++v) rng[v] = 0u;
+    uint32_t* qw = cw_mc_qw(p, sm);
+    uint8_t* viol = cw_mc_viol(p, sm);
     for (int w = 0; w < p.QW; ++w) qw[w] = 0u;
     uint32_t live = 0u;
     for (int sl = 0; sl < R; ++sl) {
       const uint32_t q = S.q[(static_cast<int64_t>(j) * R + sl) * S.n + leaf];
       cw_q_set(qw, sl, q);
       if (!cw_slot_absorbing(B, sl, q)) live |= 1u << sl;
-      p.viol[sm * R + sl] = 0;
+      viol[sl] = 0;
     }
-    p.live[sm] = live;
+    *cw_mc_live(p, sm) = live;
   }
 }
 
 // GetTerminalReward (:148-164) of MCTS agent a in slot r
 BRM_HD void cw_terminal_reward(const CwBlob& B, const CwPool& p, int r, int a, double (&tr)[4]) {
-  tr[0] = tr[1] = tr[2] = tr[3] = 0.0;
-  if (!(p.flags[r * p.A + a] & BRM_CW_PRESENT)) return;
-  const uint32_t* qw = p.qw + (r * p.M + a) * p.QW;
-  for (int sl = 0; sl < p.R; ++sl) {
-    const brm_rule& rule = B.rules[B.slot_rule[sl]];
-    if (!rule.accepting[cw_q_get(qw, sl)]) tr[rule.priority] += static_cast<double>(rule.weight);
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  if (cw_meta(p, r * p.A + a)->flags & BRM_CW_PRESENT) {
+    const uint32_t* qw = cw_mc_qw(p, r * p.M + a);
+    for (int sl = 0; sl < p.R; ++sl) {
+      const brm_rule& rule = B.rules[B.slot_rule[sl]];
+      if (!rule.accepting[cw_q_get(qw, sl)]) {
+        const double w = static_cast<double>(rule.weight);
+        const int pr = rule.priority;
+        t0 = pr == 0 ? t0 + w : t0;
+        t1 = pr == 1 ? t1 + w : t1;
+        t2 = pr == 2 ? t2 + w : t2;
+        t3 = pr == 3 ? t3 + w : t3;
+      }
+    }
   }
+  tr[0] = t0; tr[1] = t1; tr[2] = t2; tr[3] = t3;
 }
 
 // ------------------------------------------------------------------ phase 1
@@ -549,15 +639,16 @@ struct CwStepCtx {
 
 BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int a) {
   const uint32_t n_prims = B.n_prims[a];
-  const int k = p.k[r];
+  const int32_t* h = cw_hdr(p, r);
+  const int k = h[H_K];
   if (c.actions) {
-    const int64_t i = p.leaf[r];
+    const int64_t i = h[H_LEAF];
     const uint32_t act = c.T > 0 ? c.actions[(i * c.T + k) * p.M + a] : c.actions[static_cast<int64_t>(a) * c.n + i];
     return act < n_prims ? act : 0u;
   }
-  uint32_t* blk = p.rng + (r * p.M + a) * 4;
+  uint32_t* blk = cw_mc_rng(p, r * p.M + a);
   if ((k & 3) == 0)
-    cw_philox_block(c.seed, c.rollout_base + static_cast<uint64_t>(p.flat[r]), static_cast<uint32_t>(k),
+    cw_philox_block(c.seed, c.rollout_base + static_cast<uint64_t>(h[H_FLAT]), static_cast<uint32_t>(k),
                     static_cast<uint32_t>(a), blk);
   return cw_mulhi32(blk[k & 3], n_prims);
 }
@@ -565,11 +656,15 @@ BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, i
 // Predict for one agent that is present and VALID (:69-71), then what of Execute depends on
 // this agent alone: drivable area / goal (:94-96, :110), removal from the map, lane
 // projection, GetActionCost (:202-248) and PotentialReward (:250-264).
-BRM_HD void cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int j) {
+// Returns true when the drivable-area test could not be decided from the grid: the caller
+// then runs cw_exact_shape_item for this agent before phase 2.
+BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int j) {
   const int A = p.A, M = p.M;
   const int s = r * A + j;
+  double* rec = cw_ag(p, s);
+  CwMeta* meta = cw_meta(p, s);
   CwKin t;
-  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  cw_load_kin(rec, t);
   const double v0 = t.v, th0 = t.th;
   const uint32_t act = j < M ? cw_pick_action(B, p, c, r, j) : 0u;
   cw_integrate(B, t, B.prim_a[j][act], B.prim_k[j][act]);
@@ -578,18 +673,20 @@ BRM_HD void cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
   if (j < M || B.remove_oom) {
     double cx[4], cy[4];
     cw_corners(B, t, j, cx, cy);
-    if (cw_out_of_map(B, t, j, cx, cy)) bits |= CW_BIT_OOM;
+    const int cls = cw_classify_shape(B, t, cx, cy);
+    if (cls > 0) bits |= CW_BIT_OOM;
+    if (cls < 0) bits |= CW_BIT_PENDING;
     if (j < M && cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
     if (B.remove_oom && (bits & CW_BIT_OOM)) {
       // World::RemoveInvalidAgents: the agent leaves the world
       present = false;
       bits |= CW_BIT_VANISHED;
-      p.flags[s] = 0;
     }
   }
   CwFrenet f;
   f.lane = -1; f.s = 0.0; f.lat = 0.0;
-  if (present) cw_frenet(B, t.x, t.y, f);
+  if (present) f = cw_frenet(B, t.x, t.y);
+  bits |= cw_beyond_bit(B, f);
   if (j < M) {
     const double dt = B.dt;
     const double a_lon = (t.v - v0) * B.inv_dt;
@@ -602,12 +699,42 @@ BRM_HD void cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
     if (f.lane >= 0) cost = cw_fma(B.w_lane * fabs(f.lat), dt, cost);
     const double pot_new = -B.w_pot * dt * fabs(t.v - B.v_des);
     const double pot_cur = -B.w_pot * dt * fabs(v0 - B.v_des);
-    p.cost[r * M + j] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
+    cw_mc(p, r * M + j)[MC_COST] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
   }
-  p.x[s] = t.x; p.y[s] = t.y; p.th[s] = t.th; p.v[s] = t.v; p.cs[s] = t.cs; p.sn[s] = t.sn;
-  p.s[s] = f.s; p.lat[s] = f.lat;
-  p.lane[s] = static_cast<int16_t>(f.lane);
-  p.bits[s] = bits;
+  rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
+  rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
+  CwMeta m;
+  m.lane = static_cast<int16_t>(f.lane);
+  m.flags = present ? meta->flags : 0;
+  m.bits = bits;
+  m._spare = 0;
+  *meta = m;
+  return (bits & CW_BIT_PENDING) != 0;
+}
+
+// the exact drivable-area test for an agent phase 1 left pending (near the polygon's boundary)
+BRM_HD void cw_exact_shape_item(const CwBlob& B, CwPool& p, int r, int j) {
+  const int s = r * p.A + j;
+  double* rec = cw_ag(p, s);
+  CwMeta* meta = cw_meta(p, s);
+  CwKin t;
+  cw_load_kin(rec, t);
+  double cx[4], cy[4];
+  cw_corners(B, t, j, cx, cy);
+  CwMeta m = *meta;
+  m.bits &= static_cast<uint8_t>(~CW_BIT_PENDING);
+  if (cw_out_of_map(B, t, j, cx, cy)) {
+    m.bits |= CW_BIT_OOM;
+    if (B.remove_oom) {
+      m.bits |= CW_BIT_VANISHED;
+      m.bits &= static_cast<uint8_t>(~CW_BIT_BEYOND);
+      m.flags = 0;
+      m.lane = -1;
+      rec[AG_S] = 0.0;
+      rec[AG_LAT] = 0.0;
+    }
+  }
+  *meta = m;
 }
 
 // drivable-area / goal bits of MCTS agent a in slot r as it stands (EvaluateRules() on a state
@@ -615,13 +742,13 @@ BRM_HD void cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
 BRM_HD void cw_shape_bits_item(const CwBlob& B, CwPool& p, int r, int a) {
   const int s = r * p.A + a;
   CwKin t;
-  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  cw_load_kin(cw_ag(p, s), t);
   double cx[4], cy[4];
   cw_corners(B, t, a, cx, cy);
-  uint8_t bits = 0;
+  uint8_t bits = cw_meta(p, s)->bits & CW_BIT_BEYOND;
   if (cw_out_of_map(B, t, a, cx, cy)) bits |= CW_BIT_OOM;
   if (cw_at_goal(B, t, a, cx, cy)) bits |= CW_BIT_GOAL;
-  p.bits[s] = bits;
+  cw_meta(p, s)->bits = bits;
 }
 
 // ------------------------------------------------------------------ phase 2
@@ -639,23 +766,27 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
   const int base = r * A, s = base + a, sm = r * M + a;
   o.r[0] = o.r[1] = o.r[2] = o.r[3] = 0.0;
   o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
-  const uint8_t fl = p.flags[s], bits = p.bits[s];
+  CwMeta* meta = cw_meta(p, s);
+  const CwMeta mt = *meta;
+  const uint8_t fl = mt.flags, bits = mt.bits;
+  double* mc = cw_mc(p, sm);
   const bool present = fl & BRM_CW_PRESENT;
   if (!present) {
     if ((bits & CW_BIT_VANISHED) && !rules_only) {
       // left the map during this step: the out-of-map penalty and nothing else (:121-125)
       o.r[0] = B.w_oom;
-      p.acc[sm * 4] = cw_fma(p.disc[r], o.r[0], p.acc[sm * 4]);
-      p.bits[s] = 0;
-      if (a == 0) p.done[r] = 1;  // CheckTerminal: no ego
+      mc[MC_ACC] = cw_fma(p.disc[r], o.r[0], mc[MC_ACC]);
+      meta->bits = 0;
+      if (a == 0) cw_hstate(p, r)[HS_DONE] = 1;  // CheckTerminal: no ego
     }
     return;
   }
   const bool evaluated = (fl & BRM_CW_VALID) != 0;
   const bool oom = bits & CW_BIT_OOM, goal = bits & CW_BIT_GOAL;
   // pairwise predicates against the other agents of the rollout
-  const double xa = p.x[s], ya = p.y[s], ca = p.cs[s], sa = p.sn[s], va = p.v[s], s_a = p.s[s];
-  const int lane_a = p.lane[s];
+  const double* ra = cw_ag(p, s);
+  const double xa = ra[AG_X], ya = ra[AG_Y], ca = ra[AG_CS], sa = ra[AG_SN], va = ra[AG_V], s_a = ra[AG_S];
+  const int lane_a = mt.lane;
   const double cxa = cw_fma(B.off[a], ca, xa), cya = cw_fma(B.off[a], sa, ya);
   const double my_len = lane_a >= 0 ? B.lanes[lane_a].length : 0.0;
   const int my_succ = lane_a >= 0 ? B.lanes[lane_a].succ : -2;
@@ -664,16 +795,19 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
   double gf = 0.0, vf = 0.0;
   uint32_t merged_mask = 0, near_mask = 0;
   for (int j = 0; j < A; ++j) {
-    if (j == a || !(p.flags[base + j] & BRM_CW_PRESENT)) continue;
-    const double xj = p.x[base + j], yj = p.y[base + j];
-    const double cj = p.cs[base + j], sj = p.sn[base + j];
+    if (j == a) continue;
+    const CwMeta mj = *cw_meta(p, base + j);
+    if (!(mj.flags & BRM_CW_PRESENT)) continue;
+    const double* rj = cw_ag(p, base + j);
+    const double xj = rj[AG_X], yj = rj[AG_Y];
+    const double cj = rj[AG_CS], sj = rj[AG_SN];
     const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
     const double rr = B.rad[a] + B.rad[j];
     if (cw_fma(ddx, ddx, ddy * ddy) <= rr * rr) coll = cw_rect_overlap(B, a, xa, ya, ca, sa, j, xj, yj, cj, sj) || coll;
     if (!evaluated) continue;
-    const int lane_j = p.lane[base + j];
+    const int lane_j = mj.lane;
     if (lane_j >= 0) {
-      const double s_j = p.s[base + j];
+      const double s_j = rj[AG_S];
       if (lane_a >= 0) {
         // gap along my corridor: own lane, then its successor
         double g = 0.0;
@@ -688,11 +822,11 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
         if (has && g > 0.0 && (jf < 0 || g < gf)) {
           jf = j;
           gf = g;
-          vf = p.v[base + j];
+          vf = rj[AG_V];
         }
       }
-      if (s_j >= B.lanes[lane_j].s_point) merged_mask |= 1u << j;
     }
+    if (mj.bits & CW_BIT_BEYOND) merged_mask |= 1u << j;
     const double dx = xj - xa, dy = yj - ya;
     if (cw_fma(dx, dx, dy * dy) < B.near2) near_mask |= 1u << j;
   }
@@ -707,7 +841,7 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
     if (!rules_only) {
       r0 += (coll ? 1.0 : 0.0) * B.w_coll;  // :91-92
       r0 += (oom ? 1.0 : 0.0) * B.w_oom;    // :94-96
-      add_at(V - 1, p.cost[sm]);            // :98-102
+      add_at(V - 1, mc[MC_COST]);           // :98-102
     }
     // labels (EvaluateRules, :165-185)
     uint32_t w0 = 0;
@@ -723,15 +857,16 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
     if (safe) w0 |= 1u << BRM_CW_LABEL_SAFE_DISTANCE_FRONT;
     if (lane_a >= 0) {
       const CwLaneHdr& L = B.lanes[lane_a];
-      if (s_a >= L.s_point) w0 |= 1u << BRM_CW_LABEL_MERGED_E;
+      if (bits & CW_BIT_BEYOND) w0 |= 1u << BRM_CW_LABEL_MERGED_E;
       if (L.flags & 1) w0 |= 1u << BRM_CW_LABEL_RIGHTMOST_LANE;
       w0 |= 1u << BRM_CW_LABEL_ON_ROAD;
     }
     const uint32_t front_mask = jf >= 0 ? (1u << jf) : 0u;
     o.w[0] = w0; o.w[1] = merged_mask; o.w[2] = front_mask; o.w[3] = near_mask;
     if (rules_only || !(B.ego_only && a != 0)) {  // :104-108
-      uint32_t* qw = p.qw + sm * p.QW;
-      uint32_t live = p.live[sm];
+      uint32_t* qw = cw_mc_qw(p, sm);
+      uint8_t* viol = cw_mc_viol(p, sm);
+      uint32_t live = *cw_mc_live(p, sm);
       uint32_t todo = live;
       double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
       while (todo) {
@@ -757,7 +892,7 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
         for (uint32_t k = 0; k < BRM_MAX_APS; ++k) letter |= ((W >> ((rec.x >> (8 * k)) & 31u)) & 1u) << k;
         uint32_t nxt = B.rules[rec.z & 0xffu].trans[(cur << n_aps) + letter];
         if (nxt == BRM_VIOLATION) {
-          p.viol[sm * p.R + sl] += 1;
+          viol[sl] += 1;
           nxt = (rec.y >> 24) ? cur : ((rec.y >> 16) & 0xffu);
           const int pr = static_cast<int>((rec.y >> 8) & 0xffu);
           const double wgt = static_cast<double>(rec.w);
@@ -771,32 +906,31 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
           if (cw_slot_absorbing(B, sl, nxt)) live &= ~(1u << sl);
         }
       }
-      p.live[sm] = live;
+      *cw_mc_live(p, sm) = live;
       r0 += q0; r1 += q1; r2 += q2; r3 += q3;
     }
     if (goal && !rules_only) add_at(V - 1, B.goal_reward);                                 // :110-113
-    if (coll && !rules_only) p.flags[s] = fl & static_cast<uint8_t>(~BRM_CW_VALID);        // :116-120
+    if (coll && !rules_only) meta->flags = fl & static_cast<uint8_t>(~BRM_CW_VALID);       // :116-120
     o.r[0] = r0; o.r[1] = r1; o.r[2] = r2; o.r[3] = r3;
     const double disc = p.disc[r];
-    double* acc = p.acc + sm * 4;
-    acc[0] = cw_fma(disc, r0, acc[0]);
-    acc[1] = cw_fma(disc, r1, acc[1]);
-    acc[2] = cw_fma(disc, r2, acc[2]);
-    acc[3] = cw_fma(disc, r3, acc[3]);
+    mc[MC_ACC + 0] = cw_fma(disc, r0, mc[MC_ACC + 0]);
+    mc[MC_ACC + 1] = cw_fma(disc, r1, mc[MC_ACC + 1]);
+    mc[MC_ACC + 2] = cw_fma(disc, r2, mc[MC_ACC + 2]);
+    mc[MC_ACC + 3] = cw_fma(disc, r3, mc[MC_ACC + 3]);
   }
   // CheckTerminal of the new state (:266-285)
-  if (a == 0 && !rules_only && (p.horizon[r] - 1 == 0 || oom || coll || goal)) p.done[r] = 1;
+  if (a == 0 && !rules_only && (cw_hdr(p, r)[H_HORIZON] - 1 == 0 || oom || coll || goal)) cw_hstate(p, r)[HS_DONE] = 1;
 }
 
 // MvmctsState::CheckTerminal (:266-285) of the state in slot r as it is
 BRM_HD bool cw_check_terminal(const CwBlob& B, const CwPool& p, int r) {
   const int s = r * p.A;
-  if (!(p.flags[s] & BRM_CW_PRESENT)) return true;
+  if (!(cw_meta(p, s)->flags & BRM_CW_PRESENT)) return true;
   CwKin t;
-  t.x = p.x[s]; t.y = p.y[s]; t.th = p.th[s]; t.v = p.v[s]; t.cs = p.cs[s]; t.sn = p.sn[s];
+  cw_load_kin(cw_ag(p, s), t);
   double cx[4], cy[4];
   cw_corners(B, t, 0, cx, cy);
-  return p.horizon[r] == 0 || cw_out_of_map(B, t, 0, cx, cy) || cw_collides(B, p, s, 0) ||
+  return cw_hdr(p, r)[H_HORIZON] == 0 || cw_out_of_map(B, t, 0, cx, cy) || cw_collides(B, p, s, 0) ||
          cw_at_goal(B, t, 0, cx, cy);
 }
 

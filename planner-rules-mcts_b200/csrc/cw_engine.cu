@@ -136,29 +136,44 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
     bytes[i] = (B.total_bytes + 15) & ~15;
     if (bytes[i] > cap) cap = bytes[i];
   }
-  // pool size: as many rollout slots as fit beside the blob in the CTA's share of the SM's
-  // shared memory (one slot per thread at most: S1 of the kernel maps a thread to a slot)
+  // pool size: every warp keeps its own pool; as many rollout slots (at most 32: S1 of the
+  // kernel maps a lane to a slot) as fit beside the blob in the CTA's share of the SM's shared
+  // memory
   int smem_optin = 0, smem_sm = 0, reserved = 0;
   BRM_CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
   BRM_CUDA_CHECK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, e->device));
   BRM_CUDA_CHECK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, e->device));
-  int P = 0;
-  size_t smem = 0;
-  for (int ctas = kCwCtasPerSm; ctas >= 1 && P == 0; --ctas) {
-    const size_t budget = std::min<size_t>(smem_optin, static_cast<size_t>(smem_sm) / ctas - reserved - 256);
-    for (int cand = kCwThreads; cand >= 1; --cand) {
-      const size_t need = static_cast<size_t>(cap) + cw_pool_bytes(cand, A, M, R) + cw_sched_bytes(cand, A, M);
-      if (need <= budget) {
-        P = cand;
-        smem = need;
-        break;
+  // one large CTA per SM when there is one scenario (one blob per SM, the largest pools), small
+  // CTAs when the CTAs walk over scenarios
+  const int shapes[2][2] = {{kCwThreadsLarge, 1}, {kCwThreadsSmall, kCwCtasSmall}};
+  int P = 0, threads = 0;
+  size_t smem = 0, warp_bytes = 0;
+  for (int sh = (n_scenarios == 1 ? 0 : 1); sh < 2 && P == 0; ++sh) {
+    const int n_warps = shapes[sh][0] / 32;
+    for (int ctas = shapes[sh][1]; ctas >= 1 && P == 0; --ctas) {
+      const size_t budget = std::min<size_t>(smem_optin, static_cast<size_t>(smem_sm) / ctas - reserved - 256);
+      for (int cand = 32; cand >= 1; --cand) {
+        const size_t wb = cw_pool_bytes(cand, A, M, R) + cw_sched_bytes(cand, A, M, R);
+        const size_t need = static_cast<size_t>(cap) + wb * n_warps;
+        if (need <= budget) {
+          P = cand;
+          smem = need;
+          warp_bytes = wb;
+          threads = shapes[sh][0];
+          break;
+        }
       }
+      // fewer resident CTAs are better than pools that cannot fill a warp's lanes
+      if (P * A < 32 && ctas > 1) P = 0;
     }
-    // fewer resident CTAs are better than a pool that cannot fill the CTA's lanes
-    if (P * A < kCwThreads && ctas > 1) P = 0;
   }
   BRM_REQUIRE(P >= 1, "brm_cw_configure: the scenario (%d bytes) leaves no room for a rollout in %d bytes of "
               "shared memory", cap, smem_optin);
+  // phase-1 items per warp and iteration the kernel starts out with: every agent of every slot,
+  // rounded down to full rounds of 32 (the warps lower it when frozen agents leave their pool
+  // unable to get there)
+  int target = (P * A) / 32 * 32;
+  if (target < 32) target = 32;
   uint8_t* d_blobs = nullptr;
   int32_t* d_bytes = nullptr;
   const size_t stride = sizeof(CwBlob);
@@ -189,6 +204,9 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
   c->ctx.V = V;
   c->ctx.R = R;
   c->ctx.P = P;
+  c->ctx.threads = threads;
+  c->ctx.target_items = target;
+  c->ctx.warp_bytes = warp_bytes;
   c->ctx.smem_bytes = smem;
   e->cw = c;
   return BRM_OK;

@@ -4,12 +4,14 @@
 //   REPLAY   K6  given action sequences with a full trace
 //   QUERY        CheckTerminal / GetNumActions / GetTerminalReward
 //
-// A CTA keeps a POOL of P rollouts (states) in shared memory and advances all of them one
-// step per iteration.  The step is cut into per-agent work items (cw_core.cuh) that are
-// compacted into lists, so that the lanes of a warp always work on agents that have work:
-//   S1  one thread per rollout slot: bookkeeping of the last step, finished rollouts are
-//       recorded for finalisation and their slot takes the next rollout at once (claimed from
-//       a global counter); agents of continuing rollouts are pushed on the phase lists
+// Every WARP keeps a pool of up to 32 rollouts (states) in its own piece of shared memory and
+// advances all of them one step per iteration; warps never wait for one another.  The step is
+// cut into per-agent work items (cw_core.cuh) that are compacted into lists, so that the
+// lanes always work on agents that have work:
+//   S1  lane = rollout slot: bookkeeping of the last step; finished rollouts are recorded for
+//       finalisation and free slots take new rollouts (claimed from a global counter) -- as
+//       many as keep the number of phase-1 items at the warp's target, a multiple of 32;
+//       agents of continuing rollouts are pushed on the phase lists
 //   S2  recycle items (slot, agent): fold the finished rollout into the per-leaf sums, load
 //       the new leaf's agent (pose, lane projection, automaton states)
 //   P1  phase-1 items (slot, agent that moves): action, kinematics, drivable area, projection
@@ -29,7 +31,6 @@ namespace brm {
 
 namespace {
 
-constexpr int kThreads = kCwThreads;
 constexpr double kFixScale = 16777216.0;  // 2^24: fixed-point scale of the per-leaf return sums
 
 // (re)stage the blob of scenario `scn`; all threads of the CTA call this together
@@ -54,16 +55,12 @@ __device__ __forceinline__ void cw_stage(uint8_t* smem, uint64_t* bar, const CwA
   cur_scn = scn;
 }
 
-// append `val` to a shared-memory list for the lanes whose `pred` holds (one atomic per warp);
-// must be reached by all 32 lanes of the warp
-__device__ __forceinline__ void cw_push(uint16_t* list, int* cnt, bool pred, uint16_t val) {
+// append `val` to a warp-private list for the lanes whose `pred` holds; `n` is the list length,
+// kept in a warp-uniform register.  Must be reached by all 32 lanes.
+__device__ __forceinline__ void cw_push(uint16_t* list, int& n, bool pred, uint16_t val) {
   const unsigned mask = __ballot_sync(0xffffffffu, pred);
-  if (!mask) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(static_cast<int>(mask)) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(cnt, __popc(mask));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) list[base + __popc(mask & ((1u << lane) - 1u))] = val;
+  if (pred) list[n + __popc(mask & ((1u << (threadIdx.x & 31)) - 1u))] = val;
+  n += __popc(mask);
 }
 
 // which agents of a live rollout go on the phase lists, by mode
@@ -79,33 +76,95 @@ __device__ __forceinline__ bool cw_in_list2(uint8_t f, int j) {
   return (f & BRM_CW_PRESENT) && ((f & BRM_CW_VALID) || j == 0);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, kCwCtasPerSm) cw_pool_kernel(const CwArgs args) {
+// agent j of `leaf`, projected and packed the way a pool slot holds it, into the warp's cache
+__device__ __forceinline__ void cw_cache_fill(const CwBlob& B, const CwStatesView& S, const CwPool& p,
+                                              double* cache_ag, uint32_t* cache_mc, int j, int64_t leaf) {
+  // build the records in a one-slot pool view that points at the cache
+  CwPool c = p;
+  c.ag = cache_ag;
+  c.P = 1;
+  const double* src = S.agents + (static_cast<int64_t>(j) * S.n + leaf) * 4;
+  CwKin t;
+  t.x = src[0]; t.y = src[1]; t.th = src[2]; t.v = src[3];
+  const uint8_t fl = S.flags[static_cast<int64_t>(j) * S.n + leaf];
+  cw_sincos(t.th, &t.sn, &t.cs);
+  CwFrenet f;
+  f.lane = -1; f.s = 0.0; f.lat = 0.0;
+  if (fl & BRM_CW_PRESENT) f = cw_frenet(B, t.x, t.y);
+  uint8_t bits = 0;
+  if (j == 0 && (fl & BRM_CW_PRESENT) && !(fl & BRM_CW_VALID)) {
+    double cx[4], cy[4];
+    cw_corners(B, t, j, cx, cy);
+    if (cw_out_of_map(B, t, j, cx, cy)) bits |= CW_BIT_OOM;
+    if (cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
+  }
+  bits |= cw_beyond_bit(B, f);
+  double* rec = cache_ag + j * kAgWords;
+  rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
+  rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
+  CwMeta m;
+  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits; m._spare = 0;
+  *reinterpret_cast<CwMeta*>(rec + AG_META) = m;
+  if (j < p.M) {
+    uint32_t* w = cache_mc + j * (1 + p.QW);  // live, qw[QW]
+    for (int k = 0; k < p.QW; ++k) w[1 + k] = 0u;
+    uint32_t live = 0u;
+    for (int sl = 0; sl < p.R; ++sl) {
+      const uint32_t q = S.q[(static_cast<int64_t>(j) * p.R + sl) * S.n + leaf];
+      cw_q_set(w + 1, sl, q);
+      if (!cw_slot_absorbing(B, sl, q)) live |= 1u << sl;
+    }
+    w[0] = live;
+  }
+}
+
+// slot (r, j) from the cached leaf
+__device__ __forceinline__ void cw_init_from_cache(CwPool& p, const double* cache_ag, const uint32_t* cache_mc, int r,
+                                                   int j) {
+  const double* src = cache_ag + j * kAgWords;
+  double* rec = cw_ag(p, r * p.A + j);
+#pragma unroll
+  for (int k = 0; k < kAgWords; ++k) rec[k] = src[k];
+  if (j < p.M) {
+    const int sm = r * p.M + j;
+    double* mc = cw_mc(p, sm);
+#pragma unroll
+    for (int k = 0; k < MC_TAIL; ++k) mc[k] = 0.0;  // cost, acc, rng
+    const uint32_t* w = cache_mc + j * (1 + p.QW);
+    uint32_t* dst = cw_mc_live(p, sm);
+    for (int k = 0; k < 1 + p.QW; ++k) dst[k] = w[k];
+    uint8_t* viol = cw_mc_viol(p, sm);
+    for (int sl = 0; sl < p.R; ++sl) viol[sl] = 0;
+  }
+}
+
+template <int MODE, int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int s_cnt[2][4];  // per iteration parity: items on list 1, list 2, recycle list
-  __shared__ int s_any, s_next, s_end;
+  __shared__ int s_next, s_end;
   __shared__ unsigned long long s_unit;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int P = args.P, A = args.A, M = args.M, R = args.R, V = args.V;
+  const unsigned full = 0xffffffffu;
   const CwBlob& B = *reinterpret_cast<const CwBlob*>(smem);
+  // this warp's piece of shared memory: pool, then what a finished rollout leaves behind for
+  // its finalisation, then the three item lists
+  uint8_t* wmem = smem + args.blob_cap + static_cast<size_t>(wid) * args.warp_bytes;
   CwPool p;
-  cw_pool_carve(p, smem + args.blob_cap, P, A, M, R, V);
-  // scheduler arrays behind the pool
-  uint8_t* sp = smem + args.blob_cap + cw_pool_bytes(P, A, M, R);
+  cw_pool_carve(p, wmem, P, A, M, R, V);
+  uint8_t* sp = wmem + cw_pool_bytes(P, A, M, R);
   double* fin_disc = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(P) * 8;
-  int32_t* fin_flat = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 4;
-  int32_t* fin_leaf = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 4;
-  int32_t* fin_k = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 4;
-  int32_t* fin_horizon = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 4;
-  uint32_t* fin_nsteps = reinterpret_cast<uint32_t*>(sp); sp += static_cast<size_t>(P) * 4;
+  int32_t* fin_rec = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 8 * 4;  // flat, leaf, k, horizon, nsteps, done
+  // the leaf most rollouts of the warp's current chunk start from, ready to be copied into a slot
+  double* cache_ag = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(A) * kAgWords * 8;
+  uint32_t* cache_mc = reinterpret_cast<uint32_t*>(sp); sp += static_cast<size_t>(M) * (1 + p.QW) * 4;
   uint16_t* list1 = reinterpret_cast<uint16_t*>(sp); sp += static_cast<size_t>(P) * A * 2;
   uint16_t* list2 = reinterpret_cast<uint16_t*>(sp); sp += static_cast<size_t>(P) * M * 2;
-  uint16_t* listR = reinterpret_cast<uint16_t*>(sp); sp += static_cast<size_t>(P) * A * 2;
-  uint8_t* rflag = sp; sp += P;
-  uint8_t* livef = sp; sp += P;
-  uint8_t* fin_done = sp; sp += P;
+  uint16_t* listR = reinterpret_cast<uint16_t*>(sp);  // recycle items; reused for the pending shape tests
+  int cache_leaf = -1;                                // warp-uniform
+  long long c_lo = 0, c_hi = 0;                       // warp-uniform: claimed, not yet handed out
 
   const bool single = args.single_scenario != 0;
   const int n_per_leaf = args.rollouts_per_leaf;
@@ -126,56 +185,40 @@ __global__ void __launch_bounds__(kThreads, kCwCtasPerSm) cw_pool_kernel(const C
   ctx.n = args.in.n;
   ctx.T = MODE == MODE_REPLAY ? args.T : 0;
 
-  if (tid < P) {
-    p.busy[tid] = 0;
-    livef[tid] = 0;
+  if (lane < P) {
+    uint8_t* hs = cw_hstate(p, lane);
+    hs[HS_BUSY] = 0;
+    hs[HS_DONE] = 0;
+    hs[HS_LIVE] = 0;
+    hs[HS_RFLAG] = 0;
   }
   if (tid == 0) {
-    s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = 0;
-    s_cnt[1][0] = s_cnt[1][1] = s_cnt[1][2] = 0;
-    s_any = 0;
     s_next = 0;
     s_end = 0;
   }
   int cur_scn = -1;
   uint32_t tma_phase = 0;
   int unit_leaf = 0;
-  bool need_unit = !single;
   if (single) cw_stage(smem, &bar, args, MODE == MODE_ROLLOUT ? 0 : args.in.scenario[0], cur_scn, tma_phase);
   __syncthreads();
-
-  // next unclaimed work unit for the lanes that want one (-1: none left)
-  auto claim = [&](bool want) -> long long {
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (!mask) return -1;
-    const int lane = tid & 31, leader = __ffs(static_cast<int>(mask)) - 1;
-    long long base = 0;
-    if (lane == leader) {
-      if (single)
-        base = static_cast<long long>(atomicAdd(args.work_counter, static_cast<unsigned long long>(__popc(mask))));
-      else
-        base = atomicAdd(&s_next, __popc(mask));
-    }
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (!want) return -1;
-    const long long id = base + __popc(mask & ((1u << lane) - 1u));
-    if (single) return id < args.total ? id : -1;
-    return id < s_end ? static_cast<long long>(unit_leaf) * n_per_leaf + id : -1;
-  };
 
   // ---- what is written when a rollout (state) leaves the pool
   auto finalize = [&](int r, int j) {
     const int s = r * A + j, sm = r * M + j;
-    const int64_t flat = fin_flat[r];
-    const int64_t leaf = fin_leaf[r];
+    const int32_t* fr = fin_rec + r * 8;
+    const int64_t flat = fr[0];
+    const int64_t leaf = fr[1];
+    const double* rec = cw_ag(p, s);
+    const uint8_t flags = cw_meta(p, s)->flags;
     if (MODE == MODE_ROLLOUT) {
       if (j < M) {
         double tr[4];
         cw_terminal_reward(B, p, r, j, tr);
+        const double* mc = cw_mc(p, sm);
 #pragma unroll
         for (int v = 0; v < BRM_MAX_REWARD; ++v) {
           if (v >= V) break;
-          const double ret = fma(fin_disc[r], tr[v], p.acc[sm * 4 + v]);
+          const double ret = fma(fin_disc[r], tr[v], mc[MC_ACC + v]);
           // fixed point per rollout: the integer sums do not depend on the order of the atomics
           const long long fx = __double2ll_rn(ret * kFixScale);
           if (fx)
@@ -183,57 +226,60 @@ __global__ void __launch_bounds__(kThreads, kCwCtasPerSm) cw_pool_kernel(const C
                       static_cast<unsigned long long>(fx));
           if (args.out.ro_returns) args.out.ro_returns[(flat * M + j) * V + v] = ret;
         }
+        const uint8_t* viol = cw_mc_viol(p, sm);
+        const uint32_t* qw = cw_mc_qw(p, sm);
         for (int sl = 0; sl < R; ++sl) {
-          const uint8_t vv = p.viol[sm * R + sl];
+          const uint8_t vv = viol[sl];
           if (vv && args.out.viol_sum)
             atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.viol_sum[(leaf * M + j) * R + sl]),
                       static_cast<unsigned long long>(vv));
           if (args.out.ro_viol) args.out.ro_viol[(flat * M + j) * R + sl] = vv;
-          if (args.out.ro_q) args.out.ro_q[(flat * M + j) * R + sl] = static_cast<uint8_t>(cw_q_get(p.qw + sm * p.QW, sl));
+          if (args.out.ro_q) args.out.ro_q[(flat * M + j) * R + sl] = static_cast<uint8_t>(cw_q_get(qw, sl));
         }
       }
       if (args.out.ro_agents) {
         double* o = args.out.ro_agents + (flat * A + j) * 4;
-        reinterpret_cast<double2*>(o)[0] = make_double2(p.x[s], p.y[s]);
-        reinterpret_cast<double2*>(o)[1] = make_double2(p.th[s], p.v[s]);
+        reinterpret_cast<double2*>(o)[0] = make_double2(rec[AG_X], rec[AG_Y]);
+        reinterpret_cast<double2*>(o)[1] = make_double2(rec[AG_TH], rec[AG_V]);
       }
-      if (args.out.ro_flags) args.out.ro_flags[flat * A + j] = p.flags[s];
+      if (args.out.ro_flags) args.out.ro_flags[flat * A + j] = flags;
       if (j == 0) {
-        if (args.out.agent_steps && fin_nsteps[r])
+        if (args.out.agent_steps && fr[4])
           atomicAdd(reinterpret_cast<unsigned long long*>(&args.out.agent_steps[leaf]),
-                    static_cast<unsigned long long>(fin_nsteps[r]));
-        if (args.out.ro_steps) args.out.ro_steps[flat] = fin_k[r];
+                    static_cast<unsigned long long>(static_cast<uint32_t>(fr[4])));
+        if (args.out.ro_steps) args.out.ro_steps[flat] = fr[2];
       }
     } else if (MODE == MODE_EXECUTE || MODE == MODE_RULES) {
       const int64_t n = args.in.n, i = leaf;
       double* o = args.bout.agents + (static_cast<int64_t>(j) * n + i) * 4;
-      reinterpret_cast<double2*>(o)[0] = make_double2(p.x[s], p.y[s]);
-      reinterpret_cast<double2*>(o)[1] = make_double2(p.th[s], p.v[s]);
-      args.bout.flags[static_cast<int64_t>(j) * n + i] = p.flags[s];
+      reinterpret_cast<double2*>(o)[0] = make_double2(rec[AG_X], rec[AG_Y]);
+      reinterpret_cast<double2*>(o)[1] = make_double2(rec[AG_TH], rec[AG_V]);
+      args.bout.flags[static_cast<int64_t>(j) * n + i] = flags;
       if (j == 0) {
-        args.bout.horizon[i] = fin_horizon[r];
+        args.bout.horizon[i] = fr[3];
         // CheckTerminal of the new state; "no ego" (:267-270) is not seen by any work item
         args.bout.terminal[i] = MODE == MODE_RULES ? args.in.terminal[i]
-                                                   : ((fin_done[r] || !(p.flags[s] & BRM_CW_PRESENT)) ? 1 : 0);
+                                                   : ((fr[5] || !(flags & BRM_CW_PRESENT)) ? 1 : 0);
         args.bout.scenario[i] = args.in.scenario[i];
       }
       if (j < M) {
-        for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(j) * V + v) * n + i] = p.acc[sm * 4 + v];
+        const double* mc = cw_mc(p, sm);
+        const uint8_t* viol = cw_mc_viol(p, sm);
+        const uint32_t* qw = cw_mc_qw(p, sm);
+        for (int v = 0; v < V; ++v) args.rewards[(static_cast<int64_t>(j) * V + v) * n + i] = mc[MC_ACC + v];
         for (int sl = 0; sl < R; ++sl) {
           const int64_t off = (static_cast<int64_t>(j) * R + sl) * n + i;
-          args.bout.q[off] = static_cast<uint8_t>(cw_q_get(p.qw + sm * p.QW, sl));
-          if (args.bout.viol) args.bout.viol[off] = (args.in.viol ? args.in.viol[off] : 0u) + p.viol[sm * R + sl];
+          args.bout.q[off] = static_cast<uint8_t>(cw_q_get(qw, sl));
+          if (args.bout.viol) args.bout.viol[off] = (args.in.viol ? args.in.viol[off] : 0u) + viol[sl];
         }
       }
     } else if (MODE == MODE_QUERY) {
       const int64_t n = args.in.n, i = leaf;
-      if (j == 0 && args.do_check_terminal) args.in.terminal[i] = fin_done[r];
+      if (j == 0 && args.do_check_terminal) args.in.terminal[i] = fr[5] ? 1 : 0;
       if (j < M) {
-        if (args.num_actions) {
-          const uint8_t f = p.flags[s];
+        if (args.num_actions)
           args.num_actions[static_cast<int64_t>(j) * n + i] =
-              ((f & BRM_CW_PRESENT) && (f & BRM_CW_VALID)) ? B.n_prims[j] : 1;
-        }
+              ((flags & BRM_CW_PRESENT) && (flags & BRM_CW_VALID)) ? B.n_prims[j] : 1;
         if (args.term_reward) {
           double tr[4];
           cw_terminal_reward(B, p, r, j, tr);
@@ -242,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, kCwCtasPerSm) cw_pool_kernel(const C
       }
     } else {  // MODE_REPLAY
       const int64_t i = leaf;
-      if (j == 0) args.tr.steps_out[i] = fin_k[r];
+      if (j == 0) args.tr.steps_out[i] = fr[2];
       if (j < M) {
         double tr[4];
         cw_terminal_reward(B, p, r, j, tr);
@@ -251,185 +297,249 @@ __global__ void __launch_bounds__(kThreads, kCwCtasPerSm) cw_pool_kernel(const C
     }
   };
 
-  for (int it = 0;; ++it) {
-    if (need_unit) {
-      // several scenarios: the blob is CTA-wide, so the CTA works on the rollouts of one leaf
-      // at a time (claimed from the global counter), the pool drains in between
+  for (;;) {
+    if (!single) {
+      // several scenarios: the blob is CTA-wide, so the CTA's warps work on the rollouts of one
+      // leaf at a time (claimed from the global counter); the pools drain in between
+      __syncthreads();  // every warp has drained its pool
       if (tid == 0) {
-        const unsigned long long u = atomicAdd(args.work_counter, 1ull);
-        s_unit = u;
+        s_unit = atomicAdd(args.work_counter, 1ull);
         s_next = 0;
         s_end = n_per_leaf;
-        // the pool is drained: both parities of the list counters start from zero
-        s_cnt[0][0] = s_cnt[0][1] = s_cnt[0][2] = 0;
-        s_cnt[1][0] = s_cnt[1][1] = s_cnt[1][2] = 0;
       }
       __syncthreads();
       if (s_unit >= static_cast<unsigned long long>(args.in.n)) break;
       unit_leaf = static_cast<int>(s_unit);
       cw_stage(smem, &bar, args, args.in.scenario[unit_leaf], cur_scn, tma_phase);
-      need_unit = false;
     }
-    int* cnt = s_cnt[it & 1];
-    // ------------------------------------------------------------ S1: rollout slots
-    {
-      const int r = tid;
-      const bool in_range = r < P;
-      bool fin = false, init = false, busy = false, cont_live = false;
-      if (in_range) {
-        busy = p.busy[r] != 0;
-        if (busy) {
-          if (livef[r]) {
-            p.k[r] += 1;
-            if (kSteps) {
-              p.disc[r] *= gamma;
-              p.horizon[r] -= 1;
+    for (;;) {
+      int n1 = 0, n2 = 0, nR = 0;
+      // ---------------------------------------------------------- S1: lane = rollout slot
+      {
+        const int r = lane;
+        const bool in_range = r < P;
+        int32_t* h = cw_hdr(p, in_range ? r : 0);
+        uint8_t* hs = cw_hstate(p, in_range ? r : 0);
+        bool fin = false, busy = false;
+        if (in_range) {
+          busy = hs[HS_BUSY] != 0;
+          if (busy) {
+            if (hs[HS_LIVE]) {
+              h[H_K] += 1;
+              if (kSteps) {
+                p.disc[r] *= gamma;
+                h[H_HORIZON] -= 1;
+              }
+            }
+            if (hs[HS_DONE] || h[H_K] >= max_steps) {
+              fin = true;
+              int32_t* fr = fin_rec + r * 8;
+              fr[0] = h[H_FLAT]; fr[1] = h[H_LEAF]; fr[2] = h[H_K]; fr[3] = h[H_HORIZON]; fr[4] = h[H_NSTEPS];
+              fr[5] = hs[HS_DONE];
+              fin_disc[r] = p.disc[r];
             }
           }
-          if (p.done[r] || p.k[r] >= max_steps) {
-            fin = true;
-            fin_flat[r] = p.flat[r];
-            fin_leaf[r] = p.leaf[r];
-            fin_k[r] = p.k[r];
-            fin_horizon[r] = p.horizon[r];
-            fin_nsteps[r] = p.nsteps[r];
-            fin_disc[r] = p.disc[r];
-            fin_done[r] = p.done[r];
-          }
         }
-      }
-      const bool want = in_range && (!busy || fin);
-      const long long id = claim(want);
-      if (in_range) {
+        // agents of the rollouts that go on: phase lists (and the agent-steps they will add)
+        const bool cont = in_range && busy && !fin;
+        const uint16_t e0 = static_cast<uint16_t>(r << 4);
+        int moved = 0;
+        for (int j = 0; j < A; ++j) {
+          const uint8_t f = cont ? cw_meta(p, r * A + j)->flags : 0;
+          const bool p1 = cont && cw_in_list1<MODE>(f);
+          if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, n1, p1, static_cast<uint16_t>(e0 | j));
+          moved += p1 ? 1 : 0;
+          if (j < M) cw_push(list2, n2, cont && cw_in_list2<MODE>(f, j), static_cast<uint16_t>(e0 | j));
+        }
+        if (cont) {
+          h[H_NSTEPS] += moved;
+          hs[HS_LIVE] = 1;
+          hs[HS_RFLAG] = 0;
+        }
+        // free slots take new work: as many as keep the phase-1 items at the target
+        const bool want = in_range && (!busy || fin);
+        const unsigned wmask = __ballot_sync(full, want);
+        // how many of the free slots to fill: the phases run in rounds of 32 items, so aim at the
+        // number of FULL rounds the pool could sustain if every free slot were filled (A items
+        // per new rollout) -- a pool whose agents froze keeps fewer rollouts in flight rather than
+        // a last round with a few lanes
+        int allow = __popc(wmask);
+        if (MODE == MODE_ROLLOUT && allow > 0) {
+          int target = ((n1 + allow * A) >> 5) << 5;
+          if (target < 32) target = 32;
+          const int k = target > n1 ? (target - n1) / A : 0;
+          allow = k < allow ? k : allow;
+          if (allow < 1 && n1 == 0) allow = 1;
+        }
+        // ids come from the warp's chunk of consecutive ids (mostly one leaf: its projected pose
+        // is cached); an empty chunk is replaced from the global counter, in sizes that shrink
+        // towards the end of the work
+        int n_take = min(__popc(wmask), allow);
+        if (n_take > 0 && c_lo >= c_hi) {
+          long long base = 0, size = 0;
+          if (lane == 0) {
+            if (single) {
+              const long long left = args.total - static_cast<long long>(*reinterpret_cast<volatile unsigned long long*>(args.work_counter));
+              size = left / (2ll * args.n_warps_total);
+              size = size < 4 ? 4 : (size > 64 ? 64 : size);
+              base = static_cast<long long>(atomicAdd(args.work_counter, static_cast<unsigned long long>(size)));
+              size = base + size > args.total ? (args.total > base ? args.total - base : 0) : size;
+            } else {
+              size = P;
+              const int b = atomicAdd(&s_next, static_cast<int>(size));
+              base = static_cast<long long>(unit_leaf) * n_per_leaf + b;
+              size = b + size > s_end ? (s_end > b ? s_end - b : 0) : size;
+            }
+          }
+          c_lo = __shfl_sync(full, base, 0);
+          c_hi = c_lo + __shfl_sync(full, size, 0);
+        }
+        if (c_hi - c_lo < n_take) n_take = static_cast<int>(c_hi - c_lo);
+        const int my_rank = __popc(wmask & ((1u << lane) - 1u));
+        const bool take = want && my_rank < n_take;
+        const long long id = take ? c_lo + my_rank : -1;
+        c_lo += n_take;
+        bool init = false;
         if (want) {
           if (id >= 0) {
             const int leaf = static_cast<int>(id / n_per_leaf);
-            p.flat[r] = static_cast<int>(id);
-            p.leaf[r] = leaf;
-            p.k[r] = 0;
-            p.horizon[r] = args.in.horizon[leaf];
+            h[H_FLAT] = static_cast<int>(id);
+            h[H_LEAF] = leaf;
+            h[H_K] = 0;
+            h[H_HORIZON] = args.in.horizon[leaf];
+            h[H_NSTEPS] = 0;
             p.disc[r] = disc0;
-            p.nsteps[r] = 0;
-            p.busy[r] = 1;
-            p.done[r] = (MODE == MODE_ROLLOUT || MODE == MODE_REPLAY) ? (args.in.terminal[leaf] != 0 ? 1 : 0) : 0;
+            const bool done0 = (MODE == MODE_ROLLOUT || MODE == MODE_REPLAY) && args.in.terminal[leaf] != 0;
+            hs[HS_BUSY] = 1;
+            hs[HS_DONE] = done0 ? 1 : 0;
+            hs[HS_LIVE] = (!done0 && max_steps > 0) ? 1 : 0;
             init = true;
-            busy = true;
           } else {
-            p.busy[r] = 0;
-            busy = false;
+            hs[HS_BUSY] = 0;
+            hs[HS_LIVE] = 0;
+          }
+          hs[HS_RFLAG] = static_cast<uint8_t>((fin ? 1 : 0) | (init ? 2 : 0));
+        }
+        for (int j = 0; j < A; ++j) cw_push(listR, nR, want && (fin || init), static_cast<uint16_t>(e0 | j));
+        if (!__ballot_sync(full, in_range && (busy || init))) break;  // pool empty, no work left
+        // the leaf the new rollouts start from: project it once (lanes = agents), copy it per slot
+        const unsigned imask = __ballot_sync(full, init);
+        if (imask) {
+          const int new_leaf = __shfl_sync(full, h[H_LEAF], __ffs(static_cast<int>(imask)) - 1);
+          if (new_leaf != cache_leaf && n_per_leaf >= 4) {  // more rollouts of this leaf will follow
+            cache_leaf = new_leaf;
+            __syncwarp();
+            for (int j = lane; j < A; j += 32) cw_cache_fill(B, view, p, cache_ag, cache_mc, j, new_leaf);
           }
         }
-        const bool live = busy && !p.done[r] && p.k[r] < max_steps;
-        livef[r] = live ? 1 : 0;
-        rflag[r] = static_cast<uint8_t>((fin ? 1 : 0) | (init ? 2 : 0));
-        cont_live = live && !init;
-        if (busy || fin) s_any = 1;
       }
-      const uint16_t e0 = static_cast<uint16_t>(r << 4);
-      for (int j = 0; j < A; ++j) {
-        cw_push(listR, &cnt[2], in_range && (fin || init), static_cast<uint16_t>(e0 | j));
-        const uint8_t f = cont_live ? p.flags[r * A + j] : 0;
-        if (MODE != MODE_RULES && MODE != MODE_QUERY)
-          cw_push(list1, &cnt[0], cont_live && cw_in_list1<MODE>(f), static_cast<uint16_t>(e0 | j));
-        if (j < M) cw_push(list2, &cnt[1], cont_live && cw_in_list2<MODE>(f, j), static_cast<uint16_t>(e0 | j));
-      }
-    }
-    __syncthreads();
-    if (!s_any) {
-      if (single) break;
-      need_unit = true;
-      __syncthreads();  // everybody has read s_any before thread 0 touches the counters again
-      continue;
-    }
-    // ------------------------------------------------------------ S2: recycle items
-    {
-      const int nR = cnt[2];
-      for (int i0 = 0; i0 < nR; i0 += kThreads) {
-        const int i = i0 + tid;
+      __syncwarp();
+      // ---------------------------------------------------------- S2: recycle items
+      for (int i0 = 0; i0 < nR; i0 += 32) {
+        const int i = i0 + lane;
         bool p1 = false, p2 = false;
         uint16_t e = 0;
         if (i < nR) {
           e = listR[i];
           const int r = e >> 4, j = e & 15;
-          const uint8_t rf = rflag[r];
+          const uint8_t* hs = cw_hstate(p, r);
+          const uint8_t rf = hs[HS_RFLAG];
           if (rf & 1) finalize(r, j);
           if (rf & 2) {
-            cw_init_item(B, p, view, r, j, p.leaf[r]);
-            if (livef[r]) {
-              const uint8_t f = p.flags[r * A + j];
+            const int leaf = cw_hdr(p, r)[H_LEAF];
+            if (leaf == cache_leaf)
+              cw_init_from_cache(p, cache_ag, cache_mc, r, j);
+            else
+              cw_init_item(B, p, view, r, j, leaf);
+            if (hs[HS_LIVE]) {
+              const uint8_t f = cw_meta(p, r * A + j)->flags;
               p1 = cw_in_list1<MODE>(f);
               p2 = j < M && cw_in_list2<MODE>(f, j);
+              if (p1) atomicAdd(&cw_hdr(p, r)[H_NSTEPS], 1);
             }
           }
         }
-        if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, &cnt[0], p1, e);
-        cw_push(list2, &cnt[1], p2, e);
+        if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, n1, p1, e);
+        cw_push(list2, n2, p2, e);
       }
-    }
-    __syncthreads();
-    // ------------------------------------------------------------ phase 1
-    const int n1 = cnt[0], n2 = cnt[1];
-    if (tid == 0) {
-      int* nxt = s_cnt[(it & 1) ^ 1];
-      nxt[0] = nxt[1] = nxt[2] = 0;
-      s_any = 0;
-    }
-    if (MODE == MODE_RULES) {
-      for (int i = tid; i < n2; i += kThreads) {
-        const uint16_t e = list2[i];
-        cw_shape_bits_item(B, p, e >> 4, e & 15);
-      }
-    } else if (MODE != MODE_QUERY) {
-      for (int i = tid; i < n1; i += kThreads) {
-        const uint16_t e = list1[i];
-        const int r = e >> 4;
-        cw_phase1_item(B, p, ctx, r, e & 15);
-        atomicAdd(&p.nsteps[r], 1u);
-      }
-    }
-    __syncthreads();
-    // ------------------------------------------------------------ phase 2
-    for (int i = tid; i < n2; i += kThreads) {
-      const uint16_t e = list2[i];
-      const int r = e >> 4, a = e & 15;
-      if (MODE == MODE_QUERY) {
-        if (args.do_check_terminal) p.done[r] = cw_check_terminal(B, p, r) ? 1 : 0;
-      } else {
-        CwEval ev;
-        cw_phase2_item(B, p, r, a, MODE == MODE_RULES, ev);
-        if (MODE == MODE_REPLAY) {
-          const int64_t bt = static_cast<int64_t>(p.leaf[r]) * args.T + p.k[r];
-          for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = ev.r[v];
-          for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = ev.w[w];
+      __syncwarp();
+      // ---------------------------------------------------------- phase 1
+      if (MODE == MODE_RULES) {
+        for (int i = lane; i < n2; i += 32) {
+          const uint16_t e = list2[i];
+          cw_shape_bits_item(B, p, e >> 4, e & 15);
+        }
+      } else if (MODE != MODE_QUERY) {
+        int nX = 0;
+        for (int i0 = 0; i0 < n1; i0 += 32) {
+          const int i = i0 + lane;
+          uint16_t e = 0;
+          bool pending = false;
+          if (i < n1) {
+            e = list1[i];
+            pending = cw_phase1_item(B, p, ctx, e >> 4, e & 15);
+          }
+          cw_push(listR, nX, pending, e);
+        }
+        __syncwarp();
+        // phase 1b: the exact drivable-area test for the few agents the grid could not decide
+        for (int i = lane; i < nX; i += 32) {
+          const uint16_t e = listR[i];
+          cw_exact_shape_item(B, p, e >> 4, e & 15);
         }
       }
-    }
-    __syncthreads();
-    if (MODE == MODE_REPLAY) {
-      // the trace of this step: every agent of every rollout that executed it
-      for (int s = tid; s < P * A; s += kThreads) {
-        const int r = s / A, j = s - r * A;
-        if (!livef[r]) continue;
-        const int k = p.k[r];
-        const int64_t bt = static_cast<int64_t>(p.leaf[r]) * args.T + k;
-        double* o = args.tr.agents_out + (bt * A + j) * 4;
-        o[0] = p.x[s]; o[1] = p.y[s]; o[2] = p.th[s]; o[3] = p.v[s];
-        args.tr.flags_out[bt * A + j] = p.flags[s];
-        double* fo = args.tr.frenet_out + (bt * A + j) * 3;
-        fo[0] = static_cast<double>(p.lane[s]); fo[1] = p.s[s]; fo[2] = p.lat[s];
-        if (j == 0) args.tr.terminal_out[bt] = p.done[r];
-        if (j < M) {
-          const int sm = r * M + j;
-          for (int sl = 0; sl < R; ++sl) {
-            const uint32_t prev = k > 0 ? args.tr.viol_out[((bt - 1) * M + j) * R + sl] : 0u;
-            args.tr.viol_out[(bt * M + j) * R + sl] = prev + p.viol[sm * R + sl];
-            p.viol[sm * R + sl] = 0;
-            args.tr.q_out[(bt * M + j) * R + sl] = static_cast<uint8_t>(cw_q_get(p.qw + sm * p.QW, sl));
+      __syncwarp();
+      // ---------------------------------------------------------- phase 2
+      for (int i = lane; i < n2; i += 32) {
+        const uint16_t e = list2[i];
+        const int r = e >> 4, a = e & 15;
+        if (MODE == MODE_QUERY) {
+          if (args.do_check_terminal) cw_hstate(p, r)[HS_DONE] = cw_check_terminal(B, p, r) ? 1 : 0;
+        } else {
+          CwEval ev;
+          cw_phase2_item(B, p, r, a, MODE == MODE_RULES, ev);
+          if (MODE == MODE_REPLAY) {
+            const int32_t* h = cw_hdr(p, r);
+            const int64_t bt = static_cast<int64_t>(h[H_LEAF]) * args.T + h[H_K];
+            for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = ev.r[v];
+            for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = ev.w[w];
           }
         }
       }
-      __syncthreads();
+      __syncwarp();
+      if (MODE == MODE_REPLAY) {
+        // the trace of this step: every agent of every rollout that executed it
+        for (int s = lane; s < P * A; s += 32) {
+          const int r = s / A, j = s - r * A;
+          const uint8_t* hs = cw_hstate(p, r);
+          if (!hs[HS_BUSY] || !hs[HS_LIVE]) continue;
+          const int32_t* h = cw_hdr(p, r);
+          const int k = h[H_K];
+          const int64_t bt = static_cast<int64_t>(h[H_LEAF]) * args.T + k;
+          const double* rec = cw_ag(p, s);
+          const CwMeta mt = *cw_meta(p, s);
+          double* o = args.tr.agents_out + (bt * A + j) * 4;
+          o[0] = rec[AG_X]; o[1] = rec[AG_Y]; o[2] = rec[AG_TH]; o[3] = rec[AG_V];
+          args.tr.flags_out[bt * A + j] = mt.flags;
+          double* fo = args.tr.frenet_out + (bt * A + j) * 3;
+          fo[0] = static_cast<double>(mt.lane); fo[1] = rec[AG_S]; fo[2] = rec[AG_LAT];
+          if (j == 0) args.tr.terminal_out[bt] = hs[HS_DONE];
+          if (j < M) {
+            const int sm = r * M + j;
+            uint8_t* viol = cw_mc_viol(p, sm);
+            const uint32_t* qw = cw_mc_qw(p, sm);
+            for (int sl = 0; sl < R; ++sl) {
+              const uint32_t prev = k > 0 ? args.tr.viol_out[((bt - 1) * M + j) * R + sl] : 0u;
+              args.tr.viol_out[(bt * M + j) * R + sl] = prev + viol[sl];
+              viol[sl] = 0;
+              args.tr.q_out[(bt * M + j) * R + sl] = static_cast<uint8_t>(cw_q_get(qw, sl));
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
+    if (single) break;
   }
 }
 
@@ -452,24 +562,37 @@ __global__ void cw_finalize_returns_kernel(const long long* __restrict__ fx, dou
   out[i] = coop != 0.0 ? own + coop * others : own;
 }
 
-template <int MODE>
-int launch_mode(brm_engine* e, const CwLaunchCtx& ctx, CwArgs& a, int64_t units) {
+template <int MODE, int NT, int CTAS>
+int launch_config(brm_engine* e, const CwLaunchCtx& ctx, CwArgs& a, int64_t units) {
+  constexpr int kThreads = NT, kWarps = NT / 32;
+  auto kernel = cw_pool_kernel<MODE, NT, CTAS>;
   // the opt-in shared-memory size is a per-device attribute of the function: set it on every
   // launch (an engine per GPU in one process is a supported use)
-  BRM_CUDA_CHECK(cudaFuncSetAttribute(cw_pool_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  BRM_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(ctx.smem_bytes)));
   int per_sm = 0;
-  BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cw_pool_kernel<MODE>, kThreads, ctx.smem_bytes));
+  BRM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, ctx.smem_bytes));
   BRM_REQUIRE(per_sm >= 1, "continuous-world kernel does not fit on an SM (%zu bytes of shared memory)",
               ctx.smem_bytes);
   int64_t grid = static_cast<int64_t>(e->sm_count) * per_sm;
-  const int64_t need = a.single_scenario ? (units + ctx.P - 1) / ctx.P : units;
+  const int64_t per_cta = static_cast<int64_t>(ctx.P) * kWarps;
+  const int64_t need = a.single_scenario ? (units + per_cta - 1) / per_cta : units;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  cw_pool_kernel<MODE><<<static_cast<int>(grid), kThreads, ctx.smem_bytes, e->stream>>>(a);
+  a.n_warps_total = static_cast<int32_t>(grid) * kWarps;
+  kernel<<<static_cast<int>(grid), kThreads, ctx.smem_bytes, e->stream>>>(a);
   e->launches++;
   BRM_CUDA_CHECK(cudaGetLastError());
   return BRM_OK;
+}
+
+// two shapes of the same kernel: one large CTA per SM (one copy of the scenario blob, the largest
+// pools) when every rollout lives in one scenario; three small CTAs per SM when the CTAs walk
+// over scenarios (a CTA's warps share the rollouts of one leaf at a time)
+template <int MODE>
+int launch_mode(brm_engine* e, const CwLaunchCtx& ctx, CwArgs& a, int64_t units) {
+  if (ctx.threads == kCwThreadsLarge) return launch_config<MODE, kCwThreadsLarge, 1>(e, ctx, a, units);
+  return launch_config<MODE, kCwThreadsSmall, kCwCtasSmall>(e, ctx, a, units);
 }
 
 void fill_common(const CwLaunchCtx& ctx, CwArgs& a) {
@@ -478,6 +601,9 @@ void fill_common(const CwLaunchCtx& ctx, CwArgs& a) {
   a.blob_stride = ctx.blob_stride;
   a.blob_cap = ctx.blob_cap;
   a.A = ctx.A; a.M = ctx.M; a.V = ctx.V; a.R = ctx.R; a.P = ctx.P;
+  a.warp_bytes = static_cast<int32_t>(ctx.warp_bytes);
+  a.n_warps_total = 1;
+  a.target_items = 32 * 1024;  // batch modes: every free slot takes a state
 }
 
 }  // namespace
@@ -497,6 +623,7 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   a.first_exp = rp.first_discount_exp;
   a.gamma = rp.discount_factor;
   a.single_scenario = n_scenarios == 1 ? 1 : 0;
+  a.target_items = ctx.target_items;
   a.total = static_cast<int64_t>(leaves.n) * rp.rollouts_per_leaf;
   BRM_REQUIRE(a.total + 4 * 32 < (1ll << 31), "brm_cw_rollout: %lld rollouts in one call (limit 2^31)",
               static_cast<long long>(a.total));

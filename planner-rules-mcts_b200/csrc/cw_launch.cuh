@@ -6,12 +6,11 @@
 
 namespace brm {
 
-constexpr int kCwThreads = 128;  // CTA size of the continuous-world kernels
-// resident CTAs per SM the kernels are compiled for (register budget 65536 / (3 * 128) = 170)
-#ifndef BRM_CW_CTAS_PER_SM
-#define BRM_CW_CTAS_PER_SM 3
-#endif
-constexpr int kCwCtasPerSm = BRM_CW_CTAS_PER_SM;
+// The two launch shapes of the continuous-world kernels (threads per CTA x resident CTAs per
+// SM; register budget 65536 / (CTAs * threads) = 170)
+constexpr int kCwThreadsLarge = 384;  // x 1
+constexpr int kCwThreadsSmall = 128;  // x 3
+constexpr int kCwCtasSmall = 3;
 
 enum { MODE_ROLLOUT = 0, MODE_EXECUTE = 1, MODE_RULES = 2, MODE_QUERY = 3, MODE_REPLAY = 4 };
 
@@ -22,15 +21,20 @@ struct CwLaunchCtx {
   size_t blob_stride = 0;
   int32_t blob_cap = 0;  // bytes reserved for the blob in shared memory
   int32_t A = 0, M = 0, V = 0, R = 0;
-  int32_t P = 0;          // rollout slots of a CTA's pool
-  size_t smem_bytes = 0;  // dynamic shared memory per CTA: blob + pool + scheduler arrays
+  int32_t threads = 0;       // CTA size: kCwThreadsLarge or kCwThreadsSmall
+  int32_t P = 0;             // rollout slots of a warp's pool (<= 32)
+  int32_t target_items = 0;  // phase-1 items a warp aims at per iteration (multiple of 32)
+  size_t warp_bytes = 0;     // shared memory of one warp: pool + finalisation records + item lists
+  size_t smem_bytes = 0;     // dynamic shared memory per CTA: blob + the warps' pieces
 };
 
-// bytes of the scheduler arrays that follow the pool in shared memory (cw_pool_kernel)
-inline size_t cw_sched_bytes(int P, int A, int M) {
-  size_t b = static_cast<size_t>(P) * (8 + 5 * 4);
+// bytes of the arrays that follow a warp's pool in shared memory (cw_pool_kernel): what a
+// finished rollout leaves behind for its finalisation (8 + 8 * 4 bytes) and the three item lists
+inline size_t cw_sched_bytes(int P, int A, int M, int R) {
+  size_t b = static_cast<size_t>(P) * (8 + 8 * 4);
+  b += static_cast<size_t>(A) * kAgWords * 8 + static_cast<size_t>(M) * (1 + (R + 7) / 8) * 4;  // cached leaf
+  b = (b + 7) & ~static_cast<size_t>(7);
   b += static_cast<size_t>(P) * (2 * A + M) * 2;
-  b += static_cast<size_t>(P) * 3;
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
@@ -40,6 +44,7 @@ struct CwArgs {
   size_t blob_stride;
   int32_t blob_cap;
   int32_t A, M, V, R, P;
+  int32_t warp_bytes, target_items, n_warps_total;
   brm_cw_states in;  // leaves (rollouts) / states (batch modes)
   unsigned long long* work_counter;  // next unclaimed rollout / state (one scenario) or leaf (several); zeroed
   int64_t total;                     // work units behind the counter

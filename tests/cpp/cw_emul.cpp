@@ -35,7 +35,7 @@ struct Emul {
     mem = aligned_alloc(16, bytes);
     memset(mem, 0xA5, bytes);  // stale contents must never matter
     cw_pool_carve(pool, mem, P, B->A, B->M, R, B->V);
-    for (int r = 0; r < P; ++r) pool.busy[r] = 0;
+    for (int r = 0; r < P; ++r) cw_hstate(pool, r)[HS_BUSY] = 0;
     return true;
   }
 };
@@ -71,14 +71,15 @@ OneState make_state(const CwBlob& B, int R, const double* states0, const uint8_t
 void fill_slot(Emul& e, OneState& st, int r, int horizon, int flat, double disc0) {
   CwPool& p = e.pool;
   const CwStatesView v = st.view(p.A);
-  p.flat[r] = flat;
-  p.leaf[r] = 0;
-  p.k[r] = 0;
-  p.horizon[r] = horizon;
+  int32_t* h = cw_hdr(p, r);
+  h[H_FLAT] = flat;
+  h[H_LEAF] = 0;
+  h[H_K] = 0;
+  h[H_HORIZON] = horizon;
+  h[H_NSTEPS] = 0;
   p.disc[r] = disc0;
-  p.nsteps[r] = 0;
-  p.busy[r] = 1;
-  p.done[r] = 0;
+  cw_hstate(p, r)[HS_BUSY] = 1;
+  cw_hstate(p, r)[HS_DONE] = 0;
   for (int j = 0; j < p.A; ++j) cw_init_item(*e.B, p, v, r, j, 0);
 }
 
@@ -89,21 +90,23 @@ void step_slot(Emul& e, const CwStepCtx& c, int r, CwEval* ev /*[M]*/, double ga
   const int A = p.A, M = p.M;
   std::vector<int> l1, l2;
   for (int j = 0; j < A; ++j) {
-    const uint8_t f = p.flags[r * A + j];
+    const uint8_t f = cw_meta(p, r * A + j)->flags;
     if ((f & BRM_CW_PRESENT) && (f & BRM_CW_VALID)) l1.push_back(j);
     if (j < M && (f & BRM_CW_PRESENT) && ((f & BRM_CW_VALID) || j == 0)) l2.push_back(j);
   }
+  std::vector<int> lx;
   for (int j : l1) {
-    cw_phase1_item(B, p, c, r, j);
-    p.nsteps[r] += 1;
+    if (cw_phase1_item(B, p, c, r, j)) lx.push_back(j);
+    cw_hdr(p, r)[H_NSTEPS] += 1;
   }
+  for (int j : lx) cw_exact_shape_item(B, p, r, j);  // the kernels' phase 1b
   for (int a = 0; a < M; ++a) {
     memset(&ev[a], 0, sizeof(CwEval));
   }
   for (int a : l2) cw_phase2_item(B, p, r, a, false, ev[a]);
-  p.k[r] += 1;
+  cw_hdr(p, r)[H_K] += 1;
   p.disc[r] *= gamma;
-  p.horizon[r] -= 1;
+  cw_hdr(p, r)[H_HORIZON] -= 1;
 }
 
 }  // namespace
@@ -120,12 +123,28 @@ int cwe_frenet(const brm_cw_scenario* scn, double x, double y, double* out /*lan
     g_err = e.err;
     return -1;
   }
-  CwFrenet f;
-  cw_frenet(*e.B, x, y, f);
+  const CwFrenet f = cw_frenet(*e.B, x, y);
   out[0] = f.lane;
   out[1] = f.s;
   out[2] = f.lat;
   return 0;
+}
+
+// fraction of phase-1 items whose drivable-area test the grid could not decide (diagnostic)
+int cwe_classify(const brm_cw_scenario* scn, double x, double y, double th, int agent) {
+  Emul e;
+  if (!e.setup(scn, 1)) {
+    g_err = e.err;
+    return -2;
+  }
+  CwKin t;
+  t.x = x; t.y = y; t.th = th; t.v = 0.0;
+  cw_sincos(th, &t.sn, &t.cs);
+  double cx[4], cy[4];
+  cw_corners(*e.B, t, agent, cx, cy);
+  const int cls = cw_classify_shape(*e.B, t, cx, cy);
+  const int exact = cw_out_of_map(*e.B, t, agent, cx, cy) ? 1 : 0;
+  return cls < 0 ? 2 + exact : (cls == exact ? cls : -3 - cls);  // 0/1 decided and right, 2/3 pending, < -2 WRONG
 }
 
 int cwe_check_terminal(const brm_cw_scenario* scn, const double* states0, const uint8_t* flags0, int horizon0) {
@@ -161,24 +180,25 @@ int cwe_replay(const brm_cw_scenario* scn, const double* states0, const uint8_t*
   std::vector<uint32_t> viol32(static_cast<size_t>(M) * R, 0);
   int t = 0;
   for (; t < T && !terminal; ++t) {
-    p.done[r] = 0;
+    cw_hstate(p, r)[HS_DONE] = 0;
     step_slot(e, c, r, ev.data(), 1.0);
-    terminal = p.done[r] != 0;
+    terminal = cw_hstate(p, r)[HS_DONE] != 0;
     for (int i = 0; i < A; ++i) {
       const int s = r * A + i;
+      const double* rec = cw_ag(p, s);
       double* o = states_out + (static_cast<size_t>(t) * A + i) * 4;
-      o[0] = p.x[s]; o[1] = p.y[s]; o[2] = p.th[s]; o[3] = p.v[s];
-      flags_out[t * A + i] = p.flags[s];
+      o[0] = rec[AG_X]; o[1] = rec[AG_Y]; o[2] = rec[AG_TH]; o[3] = rec[AG_V];
+      flags_out[t * A + i] = cw_meta(p, s)->flags;
       double* fo = frenet_out + (static_cast<size_t>(t) * A + i) * 3;
-      fo[0] = p.lane[s]; fo[1] = p.s[s]; fo[2] = p.lat[s];
+      fo[0] = cw_meta(p, s)->lane; fo[1] = rec[AG_S]; fo[2] = rec[AG_LAT];
     }
     terminal_out[t] = terminal;
     for (int a = 0; a < M; ++a) {
       const int sm = r * M + a;
       for (int k = 0; k < R; ++k) {
-        viol32[a * R + k] += p.viol[sm * R + k];
-        p.viol[sm * R + k] = 0;
-        q_out[(static_cast<size_t>(t) * M + a) * R + k] = static_cast<uint8_t>(cw_q_get(p.qw + sm * p.QW, k));
+        viol32[a * R + k] += cw_mc_viol(p, sm)[k];
+        cw_mc_viol(p, sm)[k] = 0;
+        q_out[(static_cast<size_t>(t) * M + a) * R + k] = static_cast<uint8_t>(cw_q_get(cw_mc_qw(p, sm), k));
         viol_out[(static_cast<size_t>(t) * M + a) * R + k] = viol32[a * R + k];
       }
       for (int v = 0; v < V; ++v) rewards_out[(static_cast<size_t>(t) * M + a) * V + v] = ev[a].r[v];
@@ -216,26 +236,27 @@ int cwe_rollout_detail(const brm_cw_scenario* scn, const double* states0, const 
   for (uint64_t i = 0; i < n_rollouts; ++i) {
     const int r = static_cast<int>(i % P);  // slots are reused without being cleared
     fill_slot(e, st, r, horizon0, static_cast<int>(i), first_exp ? gamma : 1.0);
-    p.done[r] = leaf_terminal ? 1 : 0;
-    while (!p.done[r] && p.k[r] < max_steps) step_slot(e, c, r, ev.data(), gamma);
+    cw_hstate(p, r)[HS_DONE] = leaf_terminal ? 1 : 0;
+    while (!cw_hstate(p, r)[HS_DONE] && cw_hdr(p, r)[H_K] < max_steps) step_slot(e, c, r, ev.data(), gamma);
     for (int a = 0; a < M; ++a) {
       const int sm = r * M + a;
       double tr[4];
       cw_terminal_reward(B, p, r, a, tr);
-      for (int v = 0; v < V; ++v) returns[(i * M + a) * V + v] = fma(p.disc[r], tr[v], p.acc[sm * 4 + v]);
+      for (int v = 0; v < V; ++v) returns[(i * M + a) * V + v] = fma(p.disc[r], tr[v], cw_mc(p, sm)[MC_ACC + v]);
       for (int k = 0; k < R; ++k) {
-        viol[(i * M + a) * R + k] = p.viol[sm * R + k];
-        q_final[(i * M + a) * R + k] = static_cast<uint8_t>(cw_q_get(p.qw + sm * p.QW, k));
+        viol[(i * M + a) * R + k] = cw_mc_viol(p, sm)[k];
+        q_final[(i * M + a) * R + k] = static_cast<uint8_t>(cw_q_get(cw_mc_qw(p, sm), k));
       }
     }
     for (int j = 0; j < A; ++j) {
       const int s = r * A + j;
+      const double* rec = cw_ag(p, s);
       double* o = states_final + (i * A + j) * 4;
-      o[0] = p.x[s]; o[1] = p.y[s]; o[2] = p.th[s]; o[3] = p.v[s];
-      flags_final[i * A + j] = p.flags[s];
+      o[0] = rec[AG_X]; o[1] = rec[AG_Y]; o[2] = rec[AG_TH]; o[3] = rec[AG_V];
+      flags_final[i * A + j] = cw_meta(p, s)->flags;
     }
-    steps[i] = p.k[r];
-    *agent_steps += p.nsteps[r];
+    steps[i] = cw_hdr(p, r)[H_K];
+    *agent_steps += static_cast<uint32_t>(cw_hdr(p, r)[H_NSTEPS]);
   }
   return 0;
 }
@@ -257,14 +278,14 @@ int cwe_evaluate_rules(const brm_cw_scenario* scn, const double* states0, const 
   for (int a = 0; a < M; ++a) {
     CwEval ev;
     memset(&ev, 0, sizeof(ev));
-    const uint8_t f = p.flags[a];
+    const uint8_t f = cw_meta(p, a)->flags;
     if ((f & BRM_CW_PRESENT) && (f & BRM_CW_VALID)) {
       cw_shape_bits_item(B, p, 0, a);  // the drivable-area / goal labels of the state as it is
       cw_phase2_item(B, p, 0, a, true, ev);
     }
     for (int k = 0; k < R; ++k) {
-      q_out[a * R + k] = static_cast<uint8_t>(cw_q_get(p.qw + a * p.QW, k));
-      viol_out[a * R + k] = p.viol[a * R + k];
+      q_out[a * R + k] = static_cast<uint8_t>(cw_q_get(cw_mc_qw(p, a), k));
+      viol_out[a * R + k] = cw_mc_viol(p, a)[k];
     }
     for (int v = 0; v < V; ++v) rewards_out[a * V + v] = ev.r[v];
     for (int w = 0; w < 4; ++w) labels_out[a * 4 + w] = ev.w[w];

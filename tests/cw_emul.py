@@ -52,6 +52,15 @@ class CwEmul:
         self._check(self.lib.cwe_frenet(C.byref(abi), C.c_double(x), C.c_double(y), _p(out, C.c_double)))
         return int(out[0]), out[1], out[2]
 
+    def classify(self, scn, x, y, th, agent=0):
+        """grid classification of the drivable-area test at a pose: 0 / 1 = decided (and equal to the
+        exact test), 2 / 3 = left to the exact test (which says 0 / 1); raises if the grid is wrong"""
+        abi = scn.to_abi()
+        rc = self.lib.cwe_classify(C.byref(abi), C.c_double(x), C.c_double(y), C.c_double(th), C.c_int(agent))
+        if rc < 0:
+            raise AssertionError("grid classification disagrees with the exact test at (%r, %r, %r): %d" % (x, y, th, rc))
+        return rc
+
     def check_terminal(self, scn, states, flags, horizon):
         abi = scn.to_abi()
         states = np.ascontiguousarray(states, np.float64)

@@ -81,6 +81,60 @@ def test_lane_projection_is_the_brute_force_search(em, orc, name):
 
 
 @pytest.mark.parametrize("name", sorted(SCN))
+def test_lane_projection_at_the_band_edges(em, orc, name):
+    """Points within a hair of a lane's half width, of its ends and of its segment joints: where a
+    culled search would go wrong first."""
+    scn = SCN[name]()
+    cfg = oracle_config(scn)
+    rng = np.random.default_rng(5)
+    A = len(scn.agents)
+    checked = 0
+    for lane in scn.lanes:
+        pts = np.asarray(lane.points, np.float64)
+        for _ in range(40):
+            k = rng.integers(0, len(pts) - 1)
+            t = rng.choice([0.0, 1.0, rng.random(), 1e-9, 1 - 1e-9, -1e-7, 1 + 1e-7])
+            d = pts[k + 1] - pts[k]
+            nrm = np.array([-d[1], d[0]]) / np.hypot(*d)
+            off = rng.choice([1.0, -1.0]) * lane.half_width * rng.choice([1.0, 1 - 1e-9, 1 + 1e-9, 1 - 1e-4, 1 + 1e-4, 0.5])
+            x, y = pts[k] + t * d + off * nrm
+            got = em.frenet(scn, float(x), float(y))
+            st = scn.initial_state.copy()
+            st[A - 1] = (x, y, 0.3, 0.0)
+            fl = FL(A)
+            fl[A - 1] = ocw.PRESENT
+            o = orc.replay(cfg, st, fl, 5, np.zeros((1, scn.n_mcts_agents), np.uint8))
+            if o["steps"] == 0:
+                continue
+            want = o["frenet"][0, A - 1]
+            assert got[0] == int(want[0]), (x, y, got, want)
+            np.testing.assert_allclose(got[1:], want[1:], rtol=1e-12, atol=1e-12)
+            checked += 1
+    assert checked > 20
+
+
+@pytest.mark.parametrize("name", sorted(SCN))
+def test_drivable_area_grid_never_disagrees_with_the_exact_test(em, name):
+    """cw_classify_shape (fp32 grid over the road polygon) either decides like cw_out_of_map or
+    leaves the pose to it; poses all over the map and hugging every edge and vertex."""
+    scn = SCN[name]()
+    road = np.asarray(scn.road, np.float64)
+    rng = np.random.default_rng(9)
+    lo, hi = road.min(0) - 6.0, road.max(0) + 6.0
+    counts = np.zeros(4, int)
+    for _ in range(1500):
+        x, y = rng.uniform(lo, hi)
+        counts[em.classify(scn, float(x), float(y), float(rng.uniform(-np.pi, np.pi)))] += 1
+    for e in range(len(road)):
+        a, b = road[e], road[(e + 1) % len(road)]
+        for _ in range(60):
+            p = a + rng.random() * (b - a) + rng.normal(0, rng.choice([1e-3, 0.05, 1.5]), 2)
+            counts[em.classify(scn, float(p[0]), float(p[1]), float(rng.uniform(-np.pi, np.pi)))] += 1
+    decided = counts[0] + counts[1]
+    assert counts[0] > 0 and counts[1] > 0 and decided > 0.5 * counts.sum(), counts
+
+
+@pytest.mark.parametrize("name", sorted(SCN))
 def test_replay_matches_oracle(em, orc, name):
     scn = SCN[name]()
     cfg = oracle_config(scn)
