@@ -444,7 +444,9 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
  * brm_root_stats_reduce on the device, before anything is copied back (host batches: one upload,
  * three launches, one download, one synchronisation).  out->returns_sum may be NULL for host
  * batches when only the statistics are wanted.  stats is ACCUMULATED into, like
- * brm_root_stats_reduce; leaf_first_action [n][A] uint8 (A = MCTS agents). */
+ * brm_root_stats_reduce; leaf_first_action [n][A] uint8 (A = MCTS agents), every entry
+ * < n_actions; n_actions must be at least the number of actions (motion primitives) an agent
+ * has in the configured world (BRM_ERR_INVALID otherwise). */
 int brm_gw_rollout_root_stats(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
                               const brm_gw_rollout_out* out, const uint8_t* leaf_first_action,
                               int32_t n_actions, double* stats);

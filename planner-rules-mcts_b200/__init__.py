@@ -17,7 +17,7 @@ __all__ = ["Engine", "BrmError", "GridWorldEngine", "GridWorldState", "GridWorld
            "GwBatch", "RuleMonitor", "compile_rule", "ZIP_FORMULA", "make_default_rules", "ltl"]
 from .continuous import (AgentModel, CwBatch, Lane, MvmctsState, RulesMctsEngine,  # noqa: E402,F401
                          RulesMctsStateParameters, Scenario)
-from . import behavior, gridworld_env, mcts, parallel, planner, scenarios  # noqa: E402,F401
+from . import behavior, mcts, parallel, planner, scenarios  # noqa: E402,F401
 
 __all__ += ["AgentModel", "CwBatch", "Lane", "MvmctsState", "RulesMctsEngine", "RulesMctsStateParameters",
-            "Scenario", "scenarios", "planner", "parallel", "mcts", "gridworld_env", "behavior"]
+            "Scenario", "scenarios", "planner", "parallel", "mcts", "behavior"]

@@ -14,6 +14,7 @@ namespace brm {
 
 struct CwEngine {
   int n_scenarios = 0;
+  int max_prims = 0;  // largest number of motion primitives of an MCTS agent in any scenario
   uint8_t* d_blobs = nullptr;
   int32_t* d_blob_bytes = nullptr;
   CwLaunchCtx ctx;
@@ -193,6 +194,8 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
   brm_cw_release(e);
   CwEngine* c = new CwEngine();
   c->n_scenarios = n_scenarios;
+  for (int i = 0; i < n_scenarios; ++i)
+    for (int a = 0; a < M; ++a) c->max_prims = std::max<int>(c->max_prims, blobs[i].n_prims[a]);
   c->d_blobs = d_blobs;
   c->d_blob_bytes = d_bytes;
   c->ctx.blobs = d_blobs;
@@ -395,6 +398,10 @@ int brm_cw_rollout_root_stats(brm_engine* e, const brm_cw_states* leaves, const 
                               const brm_cw_rollout_out* out, const uint8_t* leaf_first_action, int32_t n_actions,
                               double* stats) {
   BRM_REQUIRE(leaf_first_action && stats && n_actions >= 1, "brm_cw_rollout_root_stats: bad arguments");
+  BRM_TRY(check_ready(e, "brm_cw_rollout_root_stats"));
+  BRM_REQUIRE(n_actions >= cw_of(e)->max_prims,
+              "brm_cw_rollout_root_stats: n_actions %d is smaller than the %d motion primitives an agent has "
+              "(statistics of the actions beyond it would be dropped)", n_actions, cw_of(e)->max_prims);
   return cw_rollout_impl(e, leaves, rp, out, leaf_first_action, n_actions, stats);
 }
 

@@ -3,6 +3,7 @@
 #include <cstdarg>
 
 #include "common.cuh"
+#include "staging.cuh"
 
 namespace brm {
 
@@ -243,22 +244,17 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
     BRM_CUDA_CHECK(cudaGetLastError());
     return BRM_OK;
   }
+  brm::Stager st(e);  // releases the staged buffers on every path out of here
   uint8_t* d_fa = nullptr;
   double *d_rs = nullptr, *d_st = nullptr;
-  BRM_CUDA_CHECK(cudaMallocAsync(&d_fa, fa_bytes, e->stream));
-  BRM_CUDA_CHECK(cudaMallocAsync(&d_rs, rs_bytes, e->stream));
-  BRM_CUDA_CHECK(cudaMallocAsync(&d_st, st_bytes, e->stream));
-  BRM_CUDA_CHECK(cudaMemcpyAsync(d_fa, leaf_first_action, fa_bytes, cudaMemcpyHostToDevice, e->stream));
-  BRM_CUDA_CHECK(cudaMemcpyAsync(d_rs, returns_sum, rs_bytes, cudaMemcpyHostToDevice, e->stream));
-  BRM_CUDA_CHECK(cudaMemcpyAsync(d_st, stats, st_bytes, cudaMemcpyHostToDevice, e->stream));
+  BRM_TRY(st.in(leaf_first_action, fa_bytes, &d_fa));
+  BRM_TRY(st.in(returns_sum, rs_bytes / sizeof(double), &d_rs));
+  BRM_TRY(st.in(stats, st_bytes / sizeof(double), &d_st));
   brm::root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(
       n_leaves, n_agents, n_actions, reward_vec_size, d_fa, d_rs, rollouts_per_leaf, d_st);
   e->launches++;
   BRM_CUDA_CHECK(cudaGetLastError());
-  BRM_CUDA_CHECK(cudaMemcpyAsync(stats, d_st, st_bytes, cudaMemcpyDeviceToHost, e->stream));
-  BRM_CUDA_CHECK(cudaFreeAsync(d_fa, e->stream));
-  BRM_CUDA_CHECK(cudaFreeAsync(d_rs, e->stream));
-  BRM_CUDA_CHECK(cudaFreeAsync(d_st, e->stream));
+  BRM_TRY(st.out(stats, d_st, st_bytes / sizeof(double)));
   BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   return BRM_OK;
 }

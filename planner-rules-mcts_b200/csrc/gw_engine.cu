@@ -87,7 +87,10 @@ int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rule
   BRM_REQUIRE(n_rules >= 0 && n_rules <= BRM_MAX_RULES, "brm_gw_configure: n_rules %d not in [0,%d]",
               n_rules, BRM_MAX_RULES);
   BRM_REQUIRE(n_rules == 0 || rules, "brm_gw_configure: rules is NULL");
-  GwBlob& B = e->gw_blob;
+  // built in a local copy: a reconfiguration that fails half-way (a bad rule, too many rule
+  // states) must leave the engine exactly as it was -- host sizes and device tables in step
+  GwBlob local;
+  GwBlob& B = local;
   memset(&B, 0, sizeof(B));
   B.A = p->n_agents;
   B.V = p->reward_vec_size;
@@ -173,8 +176,12 @@ int brm_gw_configure(brm_engine* e, const brm_gw_params* p, const brm_rule* rule
   B.R = R;
   BRM_CUDA_CHECK(cudaSetDevice(e->device));
   if (!e->d_gw_blob) BRM_CUDA_CHECK(cudaMalloc(&e->d_gw_blob, sizeof(GwBlob)));
+  // the device copy is about to change: until it has, the engine is not configured
+  e->gw_ready = false;
+  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
   BRM_CUDA_CHECK(cudaMemcpyAsync(e->d_gw_blob, &B, sizeof(GwBlob), cudaMemcpyHostToDevice, e->stream));
   BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->gw_blob = B;
   e->gw_ready = true;
   return BRM_OK;
 }
@@ -314,6 +321,10 @@ int brm_gw_rollout_root_stats(brm_engine* e, const brm_gw_states* leaves, const 
                               const brm_gw_rollout_out* out, const uint8_t* leaf_first_action, int32_t n_actions,
                               double* stats) {
   BRM_REQUIRE(leaf_first_action && stats && n_actions >= 1, "brm_gw_rollout_root_stats: bad arguments");
+  BRM_TRY(check_ready(e, "brm_gw_rollout_root_stats"));
+  BRM_REQUIRE(n_actions >= e->gw_blob.n_actions,
+              "brm_gw_rollout_root_stats: n_actions %d is smaller than the %d actions of the world (statistics of "
+              "the actions beyond it would be dropped)", n_actions, e->gw_blob.n_actions);
   return gw_rollout_impl(e, leaves, rp, out, leaf_first_action, n_actions, stats);
 }
 

@@ -449,8 +449,9 @@ int grid_for(const brm_engine* e, int64_t threads_needed, int block, int ctas_pe
 
 }  // namespace
 
-// second-stage reduction shared with the continuous-world rollout kernel
-void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t n_agents, int32_t V,
+// second-stage reduction of the GridWorld rollout kernel (own[] in leaf_reduce_kernel is sized
+// for BRM_GW_MAX_AGENTS * BRM_MAX_REWARD values: GridWorld shapes only)
+static void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_leaf, int32_t n_agents, int32_t V,
                         double coop, double* out, int32_t n_leaves) {
   leaf_reduce_kernel<<<n_leaves, 128, 0, e->stream>>>(part, per_leaf, n_agents, V, coop, out);
   e->launches++;

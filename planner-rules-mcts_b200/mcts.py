@@ -37,7 +37,8 @@ class MctsParameters:
 
     def __init__(self, V, discount_factor=0.9, exploration_constant=1.42, lower_bound=None, upper_bound=None,
                  threshold=None, max_rollout_steps=30, rollouts_per_expansion=16, seed=1000, coop_factor=0.0,
-                 statistic="uct", decay1=0.8, decay2=0.12, batch_size=1):
+                 statistic="uct", decay1=0.8, decay2=0.12, batch_size=1, rank=None):
+        self.rank = rank                          # root-parallel rank (None: from torch.distributed, else 0)
         self.DISCOUNT_FACTOR = discount_factor
         self.COOP_FACTOR = coop_factor            # src/util.cpp:28-29
         # "uct": ThresUCTStatistic; "greedy": ThresGreedyStatistic (epsilon-greedy on the thresholded
@@ -68,12 +69,16 @@ class Mcts:
         self.p = params
         self.root = None
         self.iterations = 0
-        self._next_rollout = 0
+        # root-parallel search: every rank grows its own tree from its own random streams (Philox
+        # rollout ids and the host generator of the epsilon-greedy statistic); identical streams
+        # would make the merged statistics N copies of one tree
+        self.rank = parallel.rank_and_world()[0] if params.rank is None else int(params.rank)
+        self._next_rollout = self.rank * parallel.TREE_RANK_STRIDE
         # selection compares normalised values (+ exploration bonus), so the thresholds are
         # normalised with the same bounds
         span = np.maximum(self.p.UPPER_BOUND - self.p.LOWER_BOUND, 1e-9)
         self._thr_norm = None if self.p.THRESHOLD is None else (self.p.THRESHOLD - self.p.LOWER_BOUND) / span
-        self._rng = np.random.default_rng(self.p.seed)
+        self._rng = np.random.default_rng([int(self.p.seed), self.rank])
 
     # -- helpers -----------------------------------------------------------------------
     def _make_node(self, state):

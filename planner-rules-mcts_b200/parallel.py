@@ -13,6 +13,21 @@ a single in-place all_reduce (NCCL on GPU tensors, gloo in the CPU tests).
 import numpy as np
 
 
+def rank_and_world(group=None):
+    """(rank, world size) of this process in the root-parallel group; (0, 1) without one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(group), dist.get_world_size(group)
+    except ImportError:
+        pass
+    return 0, 1
+
+
+# rollout ids of a host tree: every rank draws from its own 2^40-wide range
+TREE_RANK_STRIDE = 1 << 40
+
+
 def rollout_base(rank, decision, rollouts_per_decision, world_size=None):
     """First global rollout id of `rank` for decision number `decision`.  Ranks and decisions
     get disjoint id ranges, so no two rollouts anywhere share a Philox counter."""

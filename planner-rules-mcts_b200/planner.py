@@ -83,7 +83,8 @@ class BehaviorRulesMcts:
         roots = state_batch.select(np.zeros(L, np.int64))
         leaves, step_rewards = eng.execute(roots, ja.T.copy())
         per_leaf = max(1, self.params.MaxNumIterations // L)
-        base = parallel.rollout_base(0, self.decision, L * per_leaf)
+        # root-parallel: every rank evaluates the root's joint actions with its own rollouts
+        base = parallel.rollout_base(parallel.rank_and_world()[0], self.decision, L * per_leaf)
         gamma = self.scenario.params.DISCOUNT_FACTOR
         out = eng.rollout(leaves, per_leaf, seed=self.params.RandomSeed, rollout_base=base,
                           max_steps=self.params.MaxNumIterationsRandomHeuristic, discount_factor=gamma,

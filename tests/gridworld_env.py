@@ -1,5 +1,5 @@
-"""GridWorld test environment and closed-loop runner on the device engine (SURVEY.md 8f, row
-N2; configs[0] of BASELINE.json).
+"""TEST SCAFFOLDING (not part of the product package) -- GridWorld test environment and
+closed-loop runner on the device engine (configs[0] of BASELINE.json).
 
 Mirrors /root/reference/gridworld/base_test_env.{h,cpp} (`BaseTestEnv`: three agents before a
 merging point, `G !collision` + zipper rule per agent, the mvmcts parameter set of
@@ -15,8 +15,9 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .gridworld import GridWorldEngine, GridWorldState, GridWorldStateParameter, make_default_rules
-from .mcts import Mcts, MctsParameters
+from planner_rules_mcts_b200.gridworld import (GridWorldEngine, GridWorldState, GridWorldStateParameter,
+                                               make_default_rules)
+from planner_rules_mcts_b200.mcts import Mcts, MctsParameters
 
 
 def MakeMctsParameters(thres, rollouts_per_expansion=16, seed=1000, statistic="uct", batch_size=1):

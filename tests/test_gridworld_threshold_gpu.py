@@ -6,7 +6,7 @@ Execute / rollout / terminal reward runs in libbrm.so."""
 import numpy as np
 import pytest
 
-from planner_rules_mcts_b200 import gridworld_env as ge
+from tests import gridworld_env as ge
 from planner_rules_mcts_b200.planner import write_state_history_tsv
 
 pytestmark = pytest.mark.gpu

@@ -61,6 +61,16 @@ WORKER = textwrap.dedent("""
     spans = [None] * world
     dist.all_gather_object(spans, (lo, hi))
     assert spans[0][0] == 0 and spans[-1][1] == 4096 and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+    # every rank grows its own tree: Philox rollout ids and the host generator differ per rank
+    # (identical streams would make the merged statistics `world` copies of one tree)
+    from planner_rules_mcts_b200.mcts import Mcts, MctsParameters
+    assert parallel.rank_and_world() == (rank, world)
+    m = Mcts(None, MctsParameters(3, statistic="greedy"))
+    streams = [None] * world
+    dist.all_gather_object(streams, (m._next_rollout, float(m._rng.random())))
+    assert len({s[0] for s in streams}) == world and len({s[1] for s in streams}) == world, streams
+    assert all(abs(streams[i][0] - streams[j][0]) >= 2 ** 40 for i in range(world) for j in range(i))
+    assert parallel.rollout_base(rank, 3, 1000) != parallel.rollout_base((rank + 1) %% world, 3, 1000)
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")

@@ -3,7 +3,7 @@ tests/test_gridworld_threshold_gpu.py): usage gw_threshold_sweep.py <iterations>
 import sys, time
 import numpy as np
 sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
-from planner_rules_mcts_b200 import gridworld_env as ge
+from tests import gridworld_env as ge
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 rpe = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 BIG = np.finfo(np.float64).max
