@@ -104,175 +104,238 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workloads
+def first_actions(kind, rank, L, M, n_act):
+    """The root joint action every leaf of the decision descends from (same on both arms)."""
+    if kind == "W":
+        return np.zeros((L, M), np.uint8)
+    return np.random.default_rng(1000 + rank).integers(0, n_act, size=(L, M)).astype(np.uint8)
+
+
+def workload_scenarios(kind, rank, L):
+    from planner_rules_mcts_b200 import scenarios
+    if kind == "W":
+        return [scenarios.intersection_scenario(seed=1000, scenario_id=rank * L + k) for k in range(L)]
+    return [scenarios.merge_scenario(seed=1000) if kind in ("M", "R") else scenarios.highway_scenario(seed=1000)]
+
+
 def build_workload(kind, device, rank, cuda_stream=None):
     """Returns a dict with the engine, host leaves, first actions, sizes and oracle hooks."""
     import planner_rules_mcts_b200 as brm
-    from planner_rules_mcts_b200 import scenarios
     w = dict(WORKLOADS[kind])
-    rng = np.random.default_rng(1000 + rank)
     L = w["leaves"]
     if kind == "G":
         eng = brm.GridWorldEngine(device=device, cuda_stream=cuda_stream)
         root = eng.base_test_env_batch(L)
-        first = rng.integers(0, 3, size=(L, eng.A)).astype(np.uint8)
+        first = first_actions(kind, rank, L, eng.A, 3)
         leaves, _ = eng.execute(root, first.T.copy())
         leaves.depth[:] = 0  # TestRunner::RunTest resets the depth after every real step
         w.update(engine=eng, leaves=leaves, first=first, M=eng.A, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
                  gamma=0.95, dtype="i32", state_bytes=16, scn=None)
         return w
+    scns = workload_scenarios(kind, rank, L)
+    eng = brm.RulesMctsEngine(scns, device=device, cuda_stream=cuda_stream)
     if kind == "W":
-        scns = [scenarios.intersection_scenario(seed=1000, scenario_id=rank * L + k) for k in range(L)]
-        eng = brm.RulesMctsEngine(scns, device=device, cuda_stream=cuda_stream)
         leaves = eng.initial_batch()
-        first = np.zeros((L, eng.M), np.uint8)
+        first = first_actions(kind, rank, L, eng.M, 3)
         w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=3,
                  gamma=0.9, dtype="f64", state_bytes=32, scn=scns)
         return w
-    scn = scenarios.merge_scenario(seed=1000) if kind in ("M", "R") else scenarios.highway_scenario(seed=1000)
-    eng = brm.RulesMctsEngine([scn], device=device, cuda_stream=cuda_stream)
+    scn = scns[0]
     n_act = len(scn.agents[0].primitives)
     # leaves = children of the root under random first joint actions (tree kept on the host)
     root = eng.make_batch(np.broadcast_to(scn.initial_state, (L,) + scn.initial_state.shape))
-    first = rng.integers(0, n_act, size=(L, eng.M)).astype(np.uint8)
+    first = first_actions(kind, rank, L, eng.M, n_act)
     leaves, _ = eng.execute(root, first.T.copy())
-    bad = np.flatnonzero(leaves.terminal != 0)
-    for l in bad:  # a terminal child gets no rollouts in MCTS: fall back to the no-op action
-        first[l] = 0
-    if len(bad):
-        leaves, _ = eng.execute(root, first.T.copy())
+    assert not leaves.terminal.any(), "a child of the root is terminal: pick another seed"
     w.update(engine=eng, leaves=leaves, first=first, M=eng.M, A=eng.A, V=eng.V, R=eng.R, n_actions=n_act,
              gamma=scn.params.DISCOUNT_FACTOR, dtype="f64", state_bytes=32, scn=[scn])
     return w
-
-
-def cpu_rollouts(kind, w, n_rollouts, n_threads, seed, leaf=0, impl=None):
-    """Runs the CPU implementation of the same rollouts on `n_threads` host threads.
-    Returns (agent_steps, seconds, kind)."""
-    if kind == "G":
-        from oracle import gw as ogw
-        from tests.gw_common import oracle_config_from_engine
-        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgw_ref.so"))
-        which = impl or ("ref" if have_ref else "port")
-        orc = ogw.GwOracle(which)
-        cfg = oracle_config_from_engine(w["engine"])
-        lv = w["leaves"]
-        agents0 = np.ascontiguousarray(lv.agents[:, leaf, :])
-        term0 = np.array([(int(lv.term[leaf]) >> a) & 1 for a in range(w["A"])], np.uint8)
-        t0 = time.perf_counter()
-        r = orc.rollout(cfg, agents0, term0, 0, seed, 0, n_rollouts, w["max_steps"], w["gamma"],
-                        n_threads=n_threads, q0=np.ascontiguousarray(lv.q[:, :, leaf]))
-        return r["agent_steps"], time.perf_counter() - t0, ("reference" if which == "ref" else "port")
-    from oracle import cw as ocw
-    from tests.cw_common import oracle_config
-    orc = ocw.CwOracle()
-    lv = w["leaves"]
-    scn = w["scn"][int(lv.scenario[leaf])]
-    cfg = oracle_config(scn)
-    t0 = time.perf_counter()
-    r = orc.rollout(cfg, np.ascontiguousarray(lv.agents[:, leaf, :]), np.ascontiguousarray(lv.flags[:, leaf]),
-                    int(lv.horizon[leaf]), seed, 0, n_rollouts, w["max_steps"], w["gamma"], n_threads=n_threads,
-                    q0=np.ascontiguousarray(lv.q[:, :, leaf]))
-    return r["agent_steps"], time.perf_counter() - t0, "port"
-
-
-def cpu_baseline(kind, w, target_seconds=12.0):
-    cores = os.cpu_count() or 1
-    steps, sec, impl_kind = cpu_rollouts(kind, w, 2000, cores, 1)
-    rate = steps / max(sec, 1e-9)
-    per_rollout = steps / 2000.0
-    n = int(max(2000, min(5e7, target_seconds * rate / max(per_rollout, 1e-9))))
-    steps, sec, impl_kind = cpu_rollouts(kind, w, n, cores, 2)
-    return dict(value=steps / sec, unit=UNIT, cores=cores, kind=impl_kind,
-                sample="%d rollouts from leaf 0 of workload %s on %d host threads (%.1f s)" % (n, kind, cores, sec))
-
-
-# ----------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    import __graft_entry__ as g
-    g.build(only_missing=True)
-    # building the workload needs the engine only for leaf construction on a GPU; the CPU arm
-    # must also run where the GPU is busy/absent, so leaves are produced by the oracle itself.
-    kind = args.workload
-    w = reference_workload(kind)
-    cores = os.cpu_count() or 1
-    per_step = w["ref_rollouts_per_step"]
-    for i in range(args.warmup):
-        cpu_rollouts(kind, w, max(200, per_step // 10), cores, 100 + i)
-    total_steps, total_sec, impl_kind = 0, 0.0, "port"
-    for i in range(args.steps):
-        s, sec, impl_kind = cpu_rollouts(kind, w, per_step, cores, 200 + i)
-        total_steps += s
-        total_sec += sec
-    value = total_steps / max(total_sec, 1e-9)
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * total_sec / max(args.steps, 1), higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload=w["name"], description=w["desc"], leaves=WORKLOADS[kind]["leaves"],
-                            rollouts_per_leaf=w["rollouts_per_leaf"], max_steps=w["max_steps"],
-                            note="each reference step is a bounded sample of %d rollouts of the same workload" % per_step),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=impl_kind,
-                                  sample="%d rollouts per step x %d steps on %d host threads" % (per_step, args.steps, cores)),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
-    return 0
 
 
 class _HostLeaves:
     pass
 
 
-def reference_workload(kind):
-    """Leaf state for the CPU arm without touching a GPU: the root state of the scenario
-    (leaf 0 of the GPU arm is one Execute further; rollouts from either cost the same)."""
+def reference_workload(kind, rank=0):
+    """The SAME leaves as the GPU arm of this rank, produced without a GPU: the root's children
+    under the same first joint actions, stepped by the CPU implementation itself (one replayed
+    Execute per leaf).  Nothing of libbrm.so is loaded on this path."""
     w = dict(WORKLOADS[kind])
+    L = w["leaves"]
     if kind == "G":
         from oracle import gw as ogw
-        import planner_rules_mcts_b200 as brm
-        agents, term = ogw.base_test_env_state()
-        lv = _HostLeaves()
-        lv.agents = agents[:, None, :].copy()
-        lv.term = np.zeros(1, np.uint8)
-        rules = brm.make_default_rules()
-        q = np.zeros((3, 3, 1), np.uint8)
-        lv.q = q
+        import planner_rules_mcts_b200.gridworld as gwm   # host-side rule tables only (no engine)
+        from tests.gw_common import oracle_config_from_engine
+        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgw_ref.so"))
+        orc = ogw.GwOracle("ref" if have_ref else "port")
 
         class _E:  # what oracle_config_from_engine reads
-            params = brm.GridWorldStateParameter()
-        _E.rules = rules
-        w.update(engine=_E, leaves=lv, A=3, gamma=0.95, ref_rollouts_per_step=200000)
+            params = gwm.GridWorldStateParameter()
+            rules = gwm.make_default_rules()
+        cfg = oracle_config_from_engine(_E)
+        agents0, term0 = ogw.base_test_env_state()
+        first = first_actions(kind, rank, L, 3, 3)
+        R = orc.rules_per_agent(cfg)
+        lv = _HostLeaves()
+        lv.agents = np.zeros((3, L, 4), np.int32)
+        lv.term = np.zeros(L, np.uint8)
+        lv.q = np.zeros((3, R, L), np.uint8)
+        for l in range(L):
+            o = orc.replay(cfg, agents0, term0, 0, first[l][None, :])
+            lv.agents[:, l, :] = o["agents"][0]
+            lv.term[l] = sum(int(o["term"][0, a]) << a for a in range(3))
+            lv.q[:, :, l] = o["q"][0]
+        w.update(lv=lv, n_leaves=L, cfg=cfg, orc=orc, A=3, gamma=0.95, kind_name="reference" if have_ref else "port")
         return w
-    from planner_rules_mcts_b200 import scenarios
-    scn = {"M": scenarios.merge_scenario, "R": scenarios.merge_scenario, "S": scenarios.highway_scenario,
-           "W": scenarios.intersection_scenario}[kind](seed=1000)
-    A = len(scn.agents)
+    from oracle import cw as ocw
+    from tests.cw_common import oracle_config
+    scns = workload_scenarios(kind, rank, L)
+    orc = ocw.CwOracle()
+    A, M = len(scns[0].agents), scns[0].n_mcts_agents
+    n_act = len(scns[0].agents[0].primitives)
+    first = first_actions(kind, rank, L, M, n_act)
     lv = _HostLeaves()
-    lv.scenario = np.zeros(1, np.int32)
-    lv.agents = scn.initial_state[:, None, :].astype(np.float64).copy()
-    lv.flags = np.full((A, 1), 3, np.uint8)
-    lv.horizon = np.array([scn.params.HORIZON], np.int32)
-    M = scn.n_mcts_agents
-    R = sum((A - 1) if r.IsAgentSpecific() else 1 for r in scn.rules)
-    q = np.zeros((M, R, 1), np.uint8)
-    s = 0
-    for r in scn.rules:
-        reps = (A - 1) if r.IsAgentSpecific() else 1
-        q[:, s:s + reps, 0] = r.table.init
-        s += reps
-    lv.q = q
-    w.update(leaves=lv, scn=[scn], A=A, gamma=scn.params.DISCOUNT_FACTOR,
-             ref_rollouts_per_step={"M": 60000, "R": 60000, "S": 100000, "W": 20000}[kind])
+    lv.scenario = np.arange(L, dtype=np.int32) if kind == "W" else np.zeros(L, np.int32)
+    lv.agents = np.zeros((A, L, 4))
+    lv.flags = np.zeros((A, L), np.uint8)
+    lv.horizon = np.zeros(L, np.int32)
+    cfgs = [oracle_config(s) for s in scns]
+    R = orc.rules_per_agent(cfgs[0])
+    lv.q = np.zeros((M, R, L), np.uint8)
+    for l in range(L):
+        scn, cfg = scns[lv.scenario[l]], cfgs[lv.scenario[l]]
+        fl = np.full(A, 3, np.uint8)
+        if kind == "W":   # the sweep starts every scenario from its root
+            lv.agents[:, l, :], lv.flags[:, l], lv.horizon[l] = scn.initial_state, fl, scn.params.HORIZON
+            continue
+        o = orc.replay(cfg, scn.initial_state, fl, scn.params.HORIZON, first[l][None, :])
+        assert o["steps"] == 1 and not o["terminal"][0]
+        lv.agents[:, l, :], lv.flags[:, l], lv.horizon[l] = o["states"][0], o["flags"][0], scn.params.HORIZON - 1
+        lv.q[:, :, l] = o["q"][0]
+    if kind == "W":
+        s = 0
+        for r in scns[0].rules:      # initial automaton states (host-side table data)
+            reps = (A - 1) if r.IsAgentSpecific() else 1
+            lv.q[:, s:s + reps, :] = r.table.init
+            s += reps
+    w.update(lv=lv, n_leaves=L, cfgs=cfgs, scn=scns, orc=orc, A=A, gamma=scns[0].params.DISCOUNT_FACTOR, kind_name="port")
     return w
 
 
+def cpu_rollouts(kind, w, leaf_ids, n_per_leaf, n_threads, seed, rollout_base):
+    """Rollouts [rollout_base + l * rollouts_per_leaf, ... + n_per_leaf) of the leaves `leaf_ids` on
+    `n_threads` host threads -- the ids the GPU arm gives the same leaves.  One leaf per task, the
+    tasks spread over a pool of `n_threads` workers (the oracle call releases the GIL), so every
+    core runs whole leaves back to back.  Returns (agent_steps, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    orc, lv = w["orc"], w["lv"]
+    n = w["rollouts_per_leaf"]
+
+    def one(l):
+        base = rollout_base + l * n
+        if kind == "G":
+            term0 = np.array([(int(lv.term[l]) >> a) & 1 for a in range(w["A"])], np.uint8)
+            r = orc.rollout(w["cfg"], np.ascontiguousarray(lv.agents[:, l, :]), term0, 0, seed, base, n_per_leaf,
+                            w["max_steps"], w["gamma"], n_threads=1, q0=np.ascontiguousarray(lv.q[:, :, l]))
+        else:
+            r = orc.rollout(w["cfgs"][int(lv.scenario[l])], np.ascontiguousarray(lv.agents[:, l, :]),
+                            np.ascontiguousarray(lv.flags[:, l]), int(lv.horizon[l]), seed, base, n_per_leaf,
+                            w["max_steps"], w["gamma"], n_threads=1, q0=np.ascontiguousarray(lv.q[:, :, l]))
+        return r["agent_steps"]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, n_threads)) as pool:
+        steps = sum(pool.map(one, list(leaf_ids)))
+    return steps, time.perf_counter() - t0
+
+
+def cpu_sample(kind, w, target_seconds):
+    """How many leaves (with all their rollouts) the CPU arm runs per step: about `target_seconds`
+    of work, judged from a probe of two leaves."""
+    cores = os.cpu_count() or 1
+    n = w["rollouts_per_leaf"]
+    probe = list(range(min(cores, w["n_leaves"])))
+    steps, sec = cpu_rollouts(kind, w, probe, n, cores, 1000, 0)
+    per_leaf = max(sec / len(probe), 1e-6)          # wall time per leaf with all cores busy
+    k = int(max(cores, min(w["n_leaves"], target_seconds / per_leaf)))
+    return min(w["n_leaves"], (k + cores - 1) // cores * cores)
+
+
+def cpu_baseline(kind, rank, target_seconds=12.0):
+    from planner_rules_mcts_b200 import parallel
+    w = reference_workload(kind, rank)
+    cores = os.cpu_count() or 1
+    k = cpu_sample(kind, w, target_seconds)
+    base = parallel.rollout_base(rank, 0, w["n_leaves"] * w["rollouts_per_leaf"])
+    steps, sec = cpu_rollouts(kind, w, range(k), w["rollouts_per_leaf"], cores, 1000, base)
+    return dict(value=steps / sec, unit=UNIT, cores=cores, kind=w["kind_name"],
+                sample="leaves 0..%d of the decision's %d (same leaves, same rollout ids as the GPU arm), %d rollouts "
+                       "each, on %d host threads (%.1f s)" % (k - 1, w["n_leaves"], w["rollouts_per_leaf"], cores, sec))
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The CPU implementation of the path on the host cores: oracle/_ref (the reference's own
+    GridWorld sources) for workload G, the FP64 restatement in oracle/ for S / M / W.  Only the
+    oracle is built and loaded here -- never libbrm.so."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/gridworld"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, stdout=subprocess.DEVNULL)
+    from planner_rules_mcts_b200 import parallel
+    kind = args.workload
+    w = reference_workload(kind, 0)
+    cores = os.cpu_count() or 1
+    k = cpu_sample(kind, w, 4.0)        # leaves per step: a bounded sample of the decision
+    n = w["rollouts_per_leaf"]
+    per_decision = w["n_leaves"] * n
+    for i in range(args.warmup):
+        cpu_rollouts(kind, w, range(min(2, k)), n, cores, 1000, parallel.rollout_base(0, i, per_decision))
+    total_steps, total_sec = 0, 0.0
+    for i in range(args.steps):
+        s, sec = cpu_rollouts(kind, w, range(k), n, cores, 1000, parallel.rollout_base(0, args.warmup + i, per_decision))
+        total_steps += s
+        total_sec += sec
+    value = total_steps / max(total_sec, 1e-9)
+    sample = ("leaves 0..%d of the decision's %d, %d rollouts each per step (same leaves and rollout ids as the GPU "
+              "arm), x %d steps on %d host threads" % (k - 1, w["n_leaves"], n, args.steps, cores))
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total_sec / max(args.steps, 1), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64" if kind != "G" else "i32", data="synthetic", impl="reference",
+                config=dict(workload=w["name"], description=w["desc"], leaves=w["n_leaves"], rollouts_per_leaf=n,
+                            max_steps=w["max_steps"], same_leaves_as_gpu_arm=True,
+                            note="each reference step is a bounded sample of the decision: " + sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=w["kind_name"], sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
 # ----------------------------------------------------------------------------- GPU arm
+def kernel_source_hash():
+    """sha256 over the CUDA sources the library is built from: ties profiles/inst_counts.json (ncu
+    instruction counts per agent-step) to the kernels that are running."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "planner-rules-mcts_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_inst_counts(kind):
     path = os.path.join(ROOT, "profiles", "inst_counts.json")
     if os.path.exists(path):
         try:
             d = json.load(open(path))
+            stale = d.get("csrc_sha16") != kernel_source_hash()
+            for v in d.values():
+                if isinstance(v, dict):
+                    v["stale"] = stale
             if kind != "R":
                 return d.get(kind)
             # R runs M's kernel on M's scenario: per-agent-step counts carry over, per-launch traffic does not
@@ -316,6 +379,9 @@ def run_gpu(args):
     sampler.start()
     w = build_workload(kind, local_rank, rank, cuda_stream=stream.cuda_stream)
     eng, L, n = w["engine"], w["leaves"], w["rollouts_per_leaf"]
+    # root-parallel merge behind the C ABI: with more than one rank every brm_*_rollout_root_stats
+    # call returns statistics summed over the box (NCCL on the engine's stream, before the D2H)
+    parallel.init_comm(eng.engine)
     n_leaves = L.n
     M, V, R, A = w["M"], w["V"], w["R"], w["A"]
     rollouts_per_step = n_leaves * n
@@ -337,10 +403,8 @@ def run_gpu(args):
 
     def device_step(step_idx):
         stats.zero_()
-        eng.rollout(d_leaves, n, out=out, **rollout_kwargs(step_idx))
-        eng.root_stats_reduce(d_first, out["returns_sum"], n, stats, n_actions=w["n_actions"])
-        if world > 1:
-            parallel.merge_root_stats(stats)  # root-parallel merge: one small NCCL allreduce (sum)
+        # one C-ABI call: rollouts, per-leaf sums, root statistics and (world > 1) their merge
+        eng.rollout(d_leaves, n, out=out, first_action=d_first, stats=stats, **rollout_kwargs(step_idx))
         steps_acc.add_(out["agent_steps"].sum())
 
     for i in range(args.warmup):
@@ -395,11 +459,9 @@ def run_gpu(args):
     def e2e_step(step_idx):
         h_stats[:] = 0
         # one C-ABI call per decision: rollouts + root statistics, one upload / download / synchronisation
+        # (with more than one rank the statistics come back merged: the allreduce runs on the
+        # device inside the call, between the root-statistics kernel and the download)
         eng.rollout(host_leaves, n, out=h_out, first_action=h_first, stats=h_stats, **rollout_kwargs(step_idx))
-        if world > 1:
-            t = torch.from_numpy(h_stats).to(dev)
-            dist.all_reduce(t)
-            h_stats[:] = t.cpu().numpy()
         return int(h_out["agent_steps"].sum())
 
     e2e_step(10_000)
@@ -453,7 +515,7 @@ def run_gpu(args):
         roof = dict(bound="issue", unit="Gwarp-inst/s", peak=issue_peak / 1e9,
                     peak_note="%d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the run)"
                               % (info["sm_count"], sm_mhz),
-                    kernel="cw_rollout_kernel" if kind != "G" else "gw_rollout_kernel",
+                    kernel="cw_pool_kernel<ROLLOUT>" if kind != "G" else "gw_rollout_kernel",
                     kernel_ms_per_launch=kern_ms_max / max(args.steps, 1),
                     kernel_share_of_step=kern_ms_max / dev_ms_max if dev_ms_max else None,
                     hbm=dict(bound="hbm", achieved=hbm_achieved, peak=hbm_peak, unit="GB/s",
@@ -462,10 +524,16 @@ def run_gpu(args):
                              traffic=(ic or {}).get("dram_bytes_per_launch")))
         if ic and ic.get("warp_inst_per_agent_step"):
             achieved = per_rank_steps * ic["warp_inst_per_agent_step"] / kern_s
+            # the issue roofline on THREAD instructions (peak x 32 lanes); the gap to
+            # `frac` is the share of lanes that are masked off when an instruction issues
+            thread_rate = per_rank_steps * ic["thread_inst_per_agent_step"] / kern_s
             roof.update(achieved=achieved / 1e9, frac=achieved / issue_peak,
+                        frac_thread=thread_rate / (issue_peak * 32.0),
+                        avg_active_lanes=ic.get("avg_active_lanes"),
                         warp_inst_per_agent_step=ic["warp_inst_per_agent_step"],
                         thread_inst_per_agent_step=ic.get("thread_inst_per_agent_step"),
-                        inst_source=ic.get("source"), traffic=ic.get("dram_bytes_per_launch"))
+                        inst_source=ic.get("source"), stale=bool(ic.get("stale")),
+                        traffic=ic.get("dram_bytes_per_launch"))
         else:
             roof.update(achieved=None, frac=None, traffic=None,
                         inst_source="no ncu instruction count committed yet for this workload")
@@ -487,8 +555,9 @@ def run_gpu(args):
                                   "brm_*_rollout_root_stats call per decision) on pinned host buffers; H2D, "
                                   "kernels, D2H and the host wall clock all inside"),
                     gpu_launches=int(launches_all), roofline=roof, wall_s=t_wall)
+        line["comm"] = dict(ranks=eng.engine.comm_size(), where="brm_comm_init / NCCL inside brm_*_rollout_root_stats")
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(kind, w)
+            line["cpu_baseline"] = cpu_baseline(kind, rank)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

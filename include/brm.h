@@ -440,13 +440,31 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
                           const uint8_t* leaf_first_action, const double* returns_sum,
                           int32_t rollouts_per_leaf, double* stats);
 
+/* Root-parallel merge across GPUs (one engine = one GPU = one rank).  The
+ * communicator is NCCL (bound at run time; NVLink / NVSwitch inside a box).  Rank 0 makes an
+ * id with brm_comm_unique_id and hands it to the other ranks by any side channel (MPI, a file,
+ * torch.distributed ...); every rank then calls brm_comm_init with the same id -- a collective
+ * call, like ncclCommInitRank.  Several engines of one process (one per GPU) must call it from
+ * different threads.  With a communicator, brm_allreduce_root_stats sums `count` doubles over
+ * the ranks in place on the engine's stream, and the brm_*_rollout_root_stats calls below do
+ * that merge themselves before anything is copied back: every rank receives the statistics
+ * of the whole box.  brm_comm_size: ranks of the engine's communicator (1 without one). */
+#define BRM_COMM_ID_BYTES 128
+int brm_comm_unique_id(uint8_t id[BRM_COMM_ID_BYTES]);
+int brm_comm_init(brm_engine* e, const uint8_t id[BRM_COMM_ID_BYTES], int32_t rank, int32_t n_ranks);
+int brm_comm_destroy(brm_engine* e);
+int brm_comm_size(const brm_engine* e);
+int brm_allreduce_root_stats(brm_engine* e, int32_t mem, double* stats, int64_t count);
+
 /* One decision of a root-parallel search in ONE call: brm_*_rollout followed by
  * brm_root_stats_reduce on the device, before anything is copied back (host batches: one upload,
  * three launches, one download, one synchronisation).  out->returns_sum may be NULL for host
  * batches when only the statistics are wanted.  stats is ACCUMULATED into, like
  * brm_root_stats_reduce; leaf_first_action [n][A] uint8 (A = MCTS agents), every entry
  * < n_actions; n_actions must be at least the number of actions (motion primitives) an agent
- * has in the configured world (BRM_ERR_INVALID otherwise). */
+ * has in the configured world (BRM_ERR_INVALID otherwise).  With a communicator (brm_comm_init)
+ * the statistics the call returns are the SUM over all ranks of (the `stats` passed in + this
+ * decision's rollouts): pass zeros for a fresh decision. */
 int brm_gw_rollout_root_stats(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,
                               const brm_gw_rollout_out* out, const uint8_t* leaf_first_action,
                               int32_t n_actions, double* stats);

@@ -142,7 +142,8 @@ SYMBOLS = [
     "brm_launch_count", "brm_set_kernel_timing", "brm_kernel_time", "brm_device_info",
     "brm_gw_configure", "brm_gw_rules_per_agent", "brm_gw_execute", "brm_gw_get_num_actions",
     "brm_gw_is_terminal", "brm_gw_terminal_reward", "brm_gw_rollout", "brm_gw_replay",
-    "brm_root_stats_reduce",
+    "brm_root_stats_reduce", "brm_comm_unique_id", "brm_comm_init", "brm_comm_destroy", "brm_comm_size",
+    "brm_allreduce_root_stats",
 ]
 
 _lib = None
@@ -190,8 +191,20 @@ def load():
     lib.brm_cw_rollout_root_stats.argtypes = [vp, P(CwStates), P(RolloutParams), P(CwRolloutOut), vp, i32, vp]
     lib.brm_gw_rollout_root_stats.argtypes = [vp, P(GwStates), P(RolloutParams), P(GwRolloutOut), vp, i32, vp]
     lib.brm_cw_replay.argtypes = [vp, P(CwStates), vp, i32, P(CwTrace)]
+    lib.brm_comm_unique_id.argtypes = [vp]
+    lib.brm_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.brm_comm_destroy.argtypes = [vp]
+    lib.brm_comm_size.argtypes = [vp]
+    lib.brm_allreduce_root_stats.argtypes = [vp, i32, vp, C.c_int64]
     _lib = lib
     return lib
+
+
+def comm_unique_id():
+    """128 bytes identifying a new communicator (brm_comm_unique_id; call on one rank)."""
+    buf = (C.c_uint8 * 128)()
+    check(load().brm_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def check(rc):
@@ -222,6 +235,27 @@ class Engine:
 
     def synchronize(self):
         check(self.lib.brm_synchronize(self.handle))
+
+    # -- root-parallel communicator (NCCL behind the ABI) ------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """brm_comm_init: collective over the ranks that share `unique_id` (made on rank 0 with
+        `comm_unique_id()` and handed round by the caller)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self.lib.brm_comm_init(self.handle, buf, int(rank), int(n_ranks)))
+
+    def comm_size(self):
+        return int(self.lib.brm_comm_size(self.handle))
+
+    def comm_destroy(self):
+        check(self.lib.brm_comm_destroy(self.handle))
+
+    def allreduce_root_stats(self, stats):
+        """In-place sum over the ranks of a [..] float64 buffer (numpy or torch CUDA tensor)."""
+        dev = type(stats).__module__.startswith("torch")
+        ptr = stats.data_ptr() if dev else stats.ctypes.data
+        n = stats.numel() if dev else stats.size
+        check(self.lib.brm_allreduce_root_stats(self.handle, MEM_DEVICE if dev else MEM_HOST, ptr, int(n)))
+        return stats
 
     @property
     def launch_count(self):

@@ -64,7 +64,10 @@ struct brm_engine;
 namespace brm {
 int launch_root_stats(brm_engine* e, int32_t n_leaves, int32_t n_agents, int32_t n_actions, int32_t V,
                       const uint8_t* d_first_action, const double* d_returns_sum, int32_t rollouts_per_leaf,
-                      double* d_stats);
+                      double* d_stats, const double* d_stats_in = nullptr);  // stats = stats_in (default: stats) + ...
+// comm.cu: in-place sum over the ranks of the engine's communicator (no-op without one)
+int comm_allreduce_device(brm_engine* e, double* d_buf, size_t count);
+void comm_release(brm_engine* e);
 }
 
 struct brm_engine {
@@ -85,9 +88,16 @@ struct brm_engine {
   brm::GwBlob* d_gw_blob = nullptr;
   // continuous world (cw_engine.cu)
   void* cw = nullptr;
+  // root-parallel communicator (comm.cu)
+  void* comm = nullptr;
+  uint64_t collectives = 0;
   // scratch
   void* d_ws = nullptr;
   size_t ws_bytes = 0;
+  // one-copy staging of host-buffer calls (staging.cuh, Arena): pinned host + device, same layout
+  uint8_t* h_arena = nullptr;
+  uint8_t* d_arena = nullptr;
+  size_t arena_bytes = 0;
 
   int ensure_ws(size_t bytes);
   // timing helpers around the dominant kernels

@@ -347,46 +347,63 @@ static int cw_rollout_impl(brm_engine* e, const brm_cw_states* leaves, const brm
   if (leaves->mem == BRM_MEM_DEVICE) {
     BRM_REQUIRE(out->returns_sum, "brm_cw_rollout: device batches need a returns_sum buffer");
     BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, *leaves, *rp, *out));
-    if (first_action)
+    if (first_action) {
       BRM_TRY(brm::launch_root_stats(e, leaves->n, M, n_actions, V, first_action, out->returns_sum,
                                      rp->rollouts_per_leaf, stats));
+      BRM_TRY(brm::comm_allreduce_device(e, stats, static_cast<size_t>(M) * n_actions * (1 + V)));
+    }
     return BRM_OK;
   }
+  // host buffers: one upload, one memset, the launches, one download (staging.cuh, Arena)
   const size_t L = leaves->n, N = L * static_cast<size_t>(rp->rollouts_per_leaf);
-  Stager st(e);
-  brm_cw_states d;
-  BRM_TRY(upload_states(st, *leaves, A, M, R, &d));
+  const size_t st_count = static_cast<size_t>(M) * (first_action ? n_actions : 0) * (1 + V);
+  Arena ar(e);
+  const int i_scn = ar.in(leaves->scenario, L);
+  const int i_agents = ar.in(leaves->agents, static_cast<size_t>(A) * L * 4);
+  const int i_flags = ar.in(leaves->flags, static_cast<size_t>(A) * L);
+  const int i_hor = ar.in(leaves->horizon, L), i_term = ar.in(leaves->terminal, L);
+  const int i_q = ar.in(leaves->q, static_cast<size_t>(M) * R * L);
+  const int i_fa = first_action ? ar.in(first_action, L * M) : -1;
+  const int i_st = first_action ? ar.in(stats, st_count) : -1;
+  const int t_ws = ar.tmp_zero((L * M * V + 1) * sizeof(long long));
+  const int o_ret = ar.out(out->returns_sum, L * M * V, false);  // NULL host pointer: computed, not copied back
+  const int o_viol = out->viol_sum ? ar.out(out->viol_sum, L * M * R, true) : -1;
+  const int o_steps = out->agent_steps ? ar.out(out->agent_steps, L, true) : -1;
+  const int o_ror = out->ro_returns ? ar.out(out->ro_returns, N * M * V, false) : -1;
+  const int o_rov = out->ro_viol ? ar.out(out->ro_viol, N * M * R, false) : -1;
+  const int o_roq = out->ro_q ? ar.out(out->ro_q, N * M * R, false) : -1;
+  const int o_roa = out->ro_agents ? ar.out(out->ro_agents, N * A * 4, false) : -1;
+  const int o_rof = out->ro_flags ? ar.out(out->ro_flags, N * A, false) : -1;
+  const int o_ros = out->ro_steps ? ar.out(out->ro_steps, N, false) : -1;
+  const int o_st = first_action ? ar.out(stats, st_count, false) : -1;
+  BRM_TRY(ar.commit());
+  brm_cw_states d = *leaves;
+  d.mem = BRM_MEM_DEVICE;
+  d.scenario = ar.dev<int32_t>(i_scn);
+  d.agents = ar.dev<double>(i_agents);
+  d.flags = ar.dev<uint8_t>(i_flags);
+  d.horizon = ar.dev<int32_t>(i_hor);
+  d.terminal = ar.dev<uint8_t>(i_term);
+  d.q = ar.dev<uint8_t>(i_q);
+  d.viol = nullptr;
   brm_cw_rollout_out o = {};
-  BRM_TRY(st.alloc(L * M * V, &o.returns_sum));
-  if (out->viol_sum) BRM_TRY(st.alloc(L * M * R, &o.viol_sum));
-  if (out->agent_steps) BRM_TRY(st.alloc(L, &o.agent_steps));
-  if (out->ro_returns) BRM_TRY(st.alloc(N * M * V, &o.ro_returns));
-  if (out->ro_viol) BRM_TRY(st.alloc(N * M * R, &o.ro_viol));
-  if (out->ro_q) BRM_TRY(st.alloc(N * M * R, &o.ro_q));
-  if (out->ro_agents) BRM_TRY(st.alloc(N * A * 4, &o.ro_agents));
-  if (out->ro_flags) BRM_TRY(st.alloc(N * A, &o.ro_flags));
-  if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
-  BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, d, *rp, o));
+  o.returns_sum = ar.dev<double>(o_ret);
+  if (o_viol >= 0) o.viol_sum = ar.dev<uint64_t>(o_viol);
+  if (o_steps >= 0) o.agent_steps = ar.dev<uint64_t>(o_steps);
+  if (o_ror >= 0) o.ro_returns = ar.dev<double>(o_ror);
+  if (o_rov >= 0) o.ro_viol = ar.dev<uint8_t>(o_rov);
+  if (o_roq >= 0) o.ro_q = ar.dev<uint8_t>(o_roq);
+  if (o_roa >= 0) o.ro_agents = ar.dev<double>(o_roa);
+  if (o_rof >= 0) o.ro_flags = ar.dev<uint8_t>(o_rof);
+  if (o_ros >= 0) o.ro_steps = ar.dev<int32_t>(o_ros);
+  BRM_TRY(cw_launch_rollout(e, c->ctx, c->n_scenarios, d, *rp, o, ar.dev<long long>(t_ws)));
   if (first_action) {
-    uint8_t* d_fa;
-    double* d_st;
-    const size_t st_count = static_cast<size_t>(M) * n_actions * (1 + V);
-    BRM_TRY(st.in(first_action, L * M, &d_fa));
-    BRM_TRY(st.in(stats, st_count, &d_st));
-    BRM_TRY(brm::launch_root_stats(e, leaves->n, M, n_actions, V, d_fa, o.returns_sum, rp->rollouts_per_leaf, d_st));
-    BRM_TRY(st.out(stats, d_st, st_count));
+    double* d_st = ar.dev<double>(o_st);
+    BRM_TRY(brm::launch_root_stats(e, leaves->n, M, n_actions, V, ar.dev<uint8_t>(i_fa), o.returns_sum,
+                                   rp->rollouts_per_leaf, d_st, ar.dev<double>(i_st)));
+    BRM_TRY(brm::comm_allreduce_device(e, d_st, st_count));
   }
-  if (out->returns_sum) BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * M * V));
-  if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * M * R));
-  if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));
-  if (out->ro_returns) BRM_TRY(st.out(out->ro_returns, o.ro_returns, N * M * V));
-  if (out->ro_viol) BRM_TRY(st.out(out->ro_viol, o.ro_viol, N * M * R));
-  if (out->ro_q) BRM_TRY(st.out(out->ro_q, o.ro_q, N * M * R));
-  if (out->ro_agents) BRM_TRY(st.out(out->ro_agents, o.ro_agents, N * A * 4));
-  if (out->ro_flags) BRM_TRY(st.out(out->ro_flags, o.ro_flags, N * A));
-  if (out->ro_steps) BRM_TRY(st.out(out->ro_steps, o.ro_steps, N));
-  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-  return BRM_OK;
+  return ar.finish();
 }
 
 int brm_cw_rollout(brm_engine* e, const brm_cw_states* leaves, const brm_rollout_params* rp,

@@ -609,7 +609,7 @@ void fill_common(const CwLaunchCtx& ctx, CwArgs& a) {
 }  // namespace
 
 int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
-                      const brm_rollout_params& rp, const brm_cw_rollout_out& out) {
+                      const brm_rollout_params& rp, const brm_cw_rollout_out& out, long long* zeroed_ws) {
   const int M = ctx.M, V = ctx.V, R = ctx.R;
   CwArgs a;
   memset(&a, 0, sizeof(a));
@@ -628,16 +628,23 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   BRM_REQUIRE(a.total + 4 * 32 < (1ll << 31), "brm_cw_rollout: %lld rollouts in one call (limit 2^31)",
               static_cast<long long>(a.total));
   const size_t fx_count = static_cast<size_t>(leaves.n) * M * V;
-  int rc = e->ensure_ws((fx_count + 1) * sizeof(long long));
-  if (rc != BRM_OK) return rc;
-  a.returns_fx = static_cast<long long*>(e->d_ws);
+  int rc = BRM_OK;
+  if (zeroed_ws) {
+    // the caller cleared the workspace and the sum outputs together with one memset
+    a.returns_fx = zeroed_ws;
+  } else {
+    rc = e->ensure_ws((fx_count + 1) * sizeof(long long));
+    if (rc != BRM_OK) return rc;
+    a.returns_fx = static_cast<long long*>(e->d_ws);
+    BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, (fx_count + 1) * sizeof(long long), e->stream));
+    if (out.viol_sum)
+      BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
+                                     e->stream));
+    if (out.agent_steps)
+      BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
+                                     e->stream));
+  }
   a.work_counter = reinterpret_cast<unsigned long long*>(a.returns_fx + fx_count);
-  BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, (fx_count + 1) * sizeof(long long), e->stream));
-  if (out.viol_sum)
-    BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
-                                   e->stream));
-  if (out.agent_steps)
-    BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t), e->stream));
   e->time_begin();
   rc = launch_mode<MODE_ROLLOUT>(e, ctx, a, a.single_scenario ? a.total : leaves.n);
   if (rc != BRM_OK) return rc;

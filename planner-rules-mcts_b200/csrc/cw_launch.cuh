@@ -66,8 +66,10 @@ struct CwArgs {
   brm_cw_trace tr;
 };
 
+// zeroed_ws: NULL, or (leaves * M * V + 1) already cleared 64-bit words (the caller then also
+// cleared out.viol_sum / out.agent_steps)
 int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
-                      const brm_rollout_params& rp, const brm_cw_rollout_out& out);
+                      const brm_rollout_params& rp, const brm_cw_rollout_out& out, long long* zeroed_ws = nullptr);
 int cw_launch_batch(brm_engine* e, const CwLaunchCtx& ctx, int mode, const brm_cw_states& in,
                     const brm_cw_states* out, const uint8_t* actions, double* rewards, uint8_t* num_actions,
                     double* term_reward, int do_check_terminal, int32_t T, const brm_cw_trace* tr);

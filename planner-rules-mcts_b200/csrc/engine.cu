@@ -23,7 +23,7 @@ void set_error(const char* fmt, ...) {
 __global__ void root_stats_kernel(int32_t n_leaves, int32_t A, int32_t n_actions, int32_t V,
                                   const uint8_t* __restrict__ first_action,
                                   const double* __restrict__ returns_sum, int32_t rollouts_per_leaf,
-                                  double* __restrict__ stats) {
+                                  const double* stats_in, double* stats) {
   // one warp per output element; lanes stride over the leaves and the partial sums are
   // combined in a fixed butterfly order, so the result is deterministic
   const int elem = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -41,7 +41,7 @@ __global__ void root_stats_kernel(int32_t n_leaves, int32_t A, int32_t n_actions
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  if (lane == 0) stats[elem] += x;
+  if (lane == 0) stats[elem] = stats_in[elem] + x;  // accumulated into (stats_in may be stats itself)
 }
 
 }  // namespace brm
@@ -154,8 +154,11 @@ void brm_destroy(brm_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   brm_cw_release(e);
+  brm::comm_release(e);
   if (e->d_gw_blob) cudaFree(e->d_gw_blob);
   if (e->d_ws) cudaFree(e->d_ws);
+  if (e->d_arena) cudaFree(e->d_arena);
+  if (e->h_arena) cudaFreeHost(e->h_arena);
   for (auto& p : e->ev_pool) {
     cudaEventDestroy(p.a);
     cudaEventDestroy(p.b);
@@ -212,10 +215,11 @@ namespace brm {
 // K5 on device pointers (also used by brm_*_rollout_root_stats)
 int launch_root_stats(brm_engine* e, int32_t n_leaves, int32_t n_agents, int32_t n_actions, int32_t V,
                       const uint8_t* d_first_action, const double* d_returns_sum, int32_t rollouts_per_leaf,
-                      double* d_stats) {
+                      double* d_stats, const double* d_stats_in) {
   const int total = n_agents * n_actions * (1 + V);
   root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(n_leaves, n_agents, n_actions, V, d_first_action,
-                                                             d_returns_sum, rollouts_per_leaf, d_stats);
+                                                             d_returns_sum, rollouts_per_leaf,
+                                                             d_stats_in ? d_stats_in : d_stats, d_stats);
   e->launches++;
   BRM_CUDA_CHECK(cudaGetLastError());
   return BRM_OK;
@@ -239,7 +243,7 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
   if (mem == BRM_MEM_DEVICE) {
     brm::root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(
         n_leaves, n_agents, n_actions, reward_vec_size, leaf_first_action, returns_sum,
-        rollouts_per_leaf, stats);
+        rollouts_per_leaf, stats, stats);
     e->launches++;
     BRM_CUDA_CHECK(cudaGetLastError());
     return BRM_OK;
@@ -251,7 +255,7 @@ int brm_root_stats_reduce(brm_engine* e, int32_t mem, int32_t n_leaves, int32_t 
   BRM_TRY(st.in(returns_sum, rs_bytes / sizeof(double), &d_rs));
   BRM_TRY(st.in(stats, st_bytes / sizeof(double), &d_st));
   brm::root_stats_kernel<<<(total + 3) / 4, 128, 0, e->stream>>>(
-      n_leaves, n_agents, n_actions, reward_vec_size, d_fa, d_rs, rollouts_per_leaf, d_st);
+      n_leaves, n_agents, n_actions, reward_vec_size, d_fa, d_rs, rollouts_per_leaf, d_st, d_st);
   e->launches++;
   BRM_CUDA_CHECK(cudaGetLastError());
   BRM_TRY(st.out(stats, d_st, st_bytes / sizeof(double)));

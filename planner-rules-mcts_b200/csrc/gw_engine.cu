@@ -5,7 +5,7 @@
 
 namespace brm {
 int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_rollout_params& rp,
-                      const brm_gw_rollout_out& out);
+                      const brm_gw_rollout_out& out, bool sums_zeroed = false);
 int gw_launch_execute(brm_engine* e, const brm_gw_states& in, const uint8_t* actions,
                       const brm_gw_states& out, double* rewards);
 int gw_launch_query(brm_engine* e, const brm_gw_states& s, uint8_t* num_actions,
@@ -271,45 +271,58 @@ static int gw_rollout_impl(brm_engine* e, const brm_gw_states* leaves, const brm
   if (leaves->mem == BRM_MEM_DEVICE) {
     BRM_REQUIRE(out->returns_sum, "brm_gw_rollout: device batches need a returns_sum buffer");
     BRM_TRY(gw_launch_rollout(e, *leaves, *rp, *out));
-    if (first_action)
+    if (first_action) {
       BRM_TRY(brm::launch_root_stats(e, leaves->n, A, n_actions, V, first_action, out->returns_sum,
                                      rp->rollouts_per_leaf, stats));
+      BRM_TRY(brm::comm_allreduce_device(e, stats, static_cast<size_t>(A) * n_actions * (1 + V)));
+    }
     return BRM_OK;
   }
+  // host buffers: one upload, one memset, the launches, one download (staging.cuh, Arena)
   const size_t L = leaves->n;
   const size_t N = L * static_cast<size_t>(rp->rollouts_per_leaf);
-  Stager st(e);
-  brm_gw_states d;
-  BRM_TRY(upload_states(st, *leaves, A, R, &d));
+  const size_t st_count = static_cast<size_t>(A) * (first_action ? n_actions : 0) * (1 + V);
+  Arena ar(e);
+  const int i_agents = ar.in(leaves->agents, static_cast<size_t>(A) * L * 4);
+  const int i_term = ar.in(leaves->term, L), i_depth = ar.in(leaves->depth, L);
+  const int i_q = ar.in(leaves->q, static_cast<size_t>(A) * R * L);
+  const int i_fa = first_action ? ar.in(first_action, L * A) : -1;
+  const int o_ret = ar.out(out->returns_sum, L * A * V, false);   // NULL host pointer: computed, not copied back
+  const int o_viol = out->viol_sum ? ar.out(out->viol_sum, L * A * R, true) : -1;
+  const int o_steps = out->agent_steps ? ar.out(out->agent_steps, L, true) : -1;
+  const int o_ror = out->ro_returns ? ar.out(out->ro_returns, N * A * V, false) : -1;
+  const int o_rov = out->ro_viol ? ar.out(out->ro_viol, N * A * R, false) : -1;
+  const int o_roq = out->ro_q ? ar.out(out->ro_q, N * A * R, false) : -1;
+  const int o_roa = out->ro_agents ? ar.out(out->ro_agents, N * A * 4, false) : -1;
+  const int o_ros = out->ro_steps ? ar.out(out->ro_steps, N, false) : -1;
+  // the statistics are accumulated into: they travel up with the inputs and come back with the outputs
+  const int i_st = first_action ? ar.in(stats, st_count) : -1;
+  const int o_st = first_action ? ar.out(stats, st_count, false) : -1;
+  BRM_TRY(ar.commit());
+  brm_gw_states d = *leaves;
+  d.mem = BRM_MEM_DEVICE;
+  d.agents = ar.dev<int32_t>(i_agents);
+  d.term = ar.dev<uint8_t>(i_term);
+  d.depth = ar.dev<int32_t>(i_depth);
+  d.q = ar.dev<uint8_t>(i_q);
+  d.viol = nullptr;
   brm_gw_rollout_out o = {};
-  BRM_TRY(st.alloc(L * A * V, &o.returns_sum));
-  if (out->viol_sum) BRM_TRY(st.alloc(L * A * R, &o.viol_sum));
-  if (out->agent_steps) BRM_TRY(st.alloc(L, &o.agent_steps));
-  if (out->ro_returns) BRM_TRY(st.alloc(N * A * V, &o.ro_returns));
-  if (out->ro_viol) BRM_TRY(st.alloc(N * A * R, &o.ro_viol));
-  if (out->ro_q) BRM_TRY(st.alloc(N * A * R, &o.ro_q));
-  if (out->ro_agents) BRM_TRY(st.alloc(N * A * 4, &o.ro_agents));
-  if (out->ro_steps) BRM_TRY(st.alloc(N, &o.ro_steps));
-  BRM_TRY(gw_launch_rollout(e, d, *rp, o));
+  o.returns_sum = ar.dev<double>(o_ret);
+  if (o_viol >= 0) o.viol_sum = ar.dev<uint64_t>(o_viol);
+  if (o_steps >= 0) o.agent_steps = ar.dev<uint64_t>(o_steps);
+  if (o_ror >= 0) o.ro_returns = ar.dev<double>(o_ror);
+  if (o_rov >= 0) o.ro_viol = ar.dev<uint8_t>(o_rov);
+  if (o_roq >= 0) o.ro_q = ar.dev<uint8_t>(o_roq);
+  if (o_roa >= 0) o.ro_agents = ar.dev<int32_t>(o_roa);
+  if (o_ros >= 0) o.ro_steps = ar.dev<int32_t>(o_ros);
+  BRM_TRY(gw_launch_rollout(e, d, *rp, o, true));
   if (first_action) {
-    uint8_t* d_fa;
-    double* d_st;
-    const size_t st_count = static_cast<size_t>(A) * n_actions * (1 + V);
-    BRM_TRY(st.in(first_action, L * A, &d_fa));
-    BRM_TRY(st.in(stats, st_count, &d_st));
-    BRM_TRY(brm::launch_root_stats(e, leaves->n, A, n_actions, V, d_fa, o.returns_sum, rp->rollouts_per_leaf, d_st));
-    BRM_TRY(st.out(stats, d_st, st_count));
+    double* d_st = ar.dev<double>(o_st);
+    BRM_TRY(brm::launch_root_stats(e, leaves->n, A, n_actions, V, ar.dev<uint8_t>(i_fa), o.returns_sum,
+                                   rp->rollouts_per_leaf, d_st, ar.dev<double>(i_st)));
+    BRM_TRY(brm::comm_allreduce_device(e, d_st, st_count));
   }
-  if (out->returns_sum) BRM_TRY(st.out(out->returns_sum, o.returns_sum, L * A * V));
-  if (out->viol_sum) BRM_TRY(st.out(out->viol_sum, o.viol_sum, L * A * R));
-  if (out->agent_steps) BRM_TRY(st.out(out->agent_steps, o.agent_steps, L));
-  if (out->ro_returns) BRM_TRY(st.out(out->ro_returns, o.ro_returns, N * A * V));
-  if (out->ro_viol) BRM_TRY(st.out(out->ro_viol, o.ro_viol, N * A * R));
-  if (out->ro_q) BRM_TRY(st.out(out->ro_q, o.ro_q, N * A * R));
-  if (out->ro_agents) BRM_TRY(st.out(out->ro_agents, o.ro_agents, N * A * 4));
-  if (out->ro_steps) BRM_TRY(st.out(out->ro_steps, o.ro_steps, N));
-  BRM_CUDA_CHECK(cudaStreamSynchronize(e->stream));
-  return BRM_OK;
+  return ar.finish();
 }
 
 int brm_gw_rollout(brm_engine* e, const brm_gw_states* leaves, const brm_rollout_params* rp,

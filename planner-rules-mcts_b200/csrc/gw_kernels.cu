@@ -460,7 +460,7 @@ static void launch_leaf_reduce(brm_engine* e, const double* part, int32_t per_le
 // ---- launch wrappers used by gw_engine.cu (all pointers are device pointers here) ----
 
 int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_rollout_params& rp,
-                      const brm_gw_rollout_out& out) {
+                      const brm_gw_rollout_out& out, bool sums_zeroed) {
   const int A = e->gw_blob.A, V = e->gw_blob.V;
   GwRolloutArgs a;
   a.leaves = leaves;
@@ -478,11 +478,11 @@ int gw_launch_rollout(brm_engine* e, const brm_gw_states& leaves, const brm_roll
   int rc = e->ensure_ws(part_bytes);
   if (rc != BRM_OK) return rc;
   a.part_returns = static_cast<double*>(e->d_ws);
-  if (out.viol_sum)
+  if (out.viol_sum && !sums_zeroed)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0,
                                    static_cast<size_t>(leaves.n) * A * e->gw_blob.R * sizeof(uint64_t),
                                    e->stream));
-  if (out.agent_steps)
+  if (out.agent_steps && !sums_zeroed)
     BRM_CUDA_CHECK(cudaMemsetAsync(out.agent_steps, 0, static_cast<size_t>(leaves.n) * sizeof(uint64_t),
                                    e->stream));
   // persistent grid: a multiple of the SM count, 4 CTAs of 8 warps per SM

@@ -35,6 +35,23 @@ def rollout_base(rank, decision, rollouts_per_decision, world_size=None):
     return (int(rank) * stride + int(decision)) * int(rollouts_per_decision)
 
 
+def init_comm(engine, group=None):
+    """Give `engine` (an _abi.Engine or anything with `.engine` being one) the box-wide
+    communicator of the C ABI: rank 0 makes the id (brm_comm_unique_id), torch.distributed hands it
+    round (plumbing), every rank calls brm_comm_init.  From then on brm_*_rollout_root_stats
+    returns statistics summed over all ranks (NCCL on the engine's stream).  No-op for one rank."""
+    from . import _abi
+    rank, world = rank_and_world(group)
+    eng = getattr(engine, "engine", engine)
+    if world == 1:
+        return eng
+    import torch.distributed as dist
+    ids = [_abi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    eng.comm_init(ids[0], rank, world)
+    return eng
+
+
 def shard_leaves(n_leaves, rank, world_size):
     """Contiguous share of `n_leaves` independent units (scenarios / leaves) of `rank`."""
     lo = n_leaves * rank // world_size

@@ -47,8 +47,13 @@ for w in "MGSW":
     summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep],
                           capture_output=True, text=True).stdout
     open(os.path.join(ROOT, "profiles", "%s_ncu_full_rollout_%s.json" % (TAG, w)), "w").write(summ)
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+out["csrc_sha16"] = bench.kernel_source_hash()   # bench.py flags the counts as stale when the kernels change
 json.dump(out, open(os.path.join(ROOT, "profiles", "inst_counts.json"), "w"), indent=1)
 for w, d in out.items():
+    if not isinstance(d, dict):
+        continue
     print(w, "warp-inst/agent-step %.1f  thread-inst/agent-step %.0f  lanes %.1f  issue %.1f%%  dur %.3f ms  dram %.0f B" % (
         d["warp_inst_per_agent_step"], d["thread_inst_per_agent_step"], d["avg_active_lanes"], d["issue_active_pct"],
         d["ncu_duration_ms"], d["dram_bytes_per_launch"]))
