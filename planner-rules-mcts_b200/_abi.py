@@ -200,8 +200,31 @@ def load():
     return lib
 
 
+def _prefer_torch_nccl():
+    """libbrm.so binds NCCL at run time (dlopen "libnccl.so.2").  In a Python process that also
+    uses PyTorch there must be ONE NCCL, and it has to be the one PyTorch was built against (its
+    wheel bundles it): point BRM_NCCL_LIB at that copy unless the caller chose one."""
+    if os.environ.get("BRM_NCCL_LIB"):
+        return
+    import importlib.util
+    for pkg in ("nvidia.nccl", "torch"):
+        try:
+            spec = importlib.util.find_spec(pkg)
+        except (ImportError, ValueError):
+            spec = None
+        if not spec or not spec.submodule_search_locations:
+            continue
+        base = list(spec.submodule_search_locations)[0]
+        for cand in (os.path.join(base, "lib", "libnccl.so.2"),
+                     os.path.join(base, "..", "nvidia", "nccl", "lib", "libnccl.so.2")):
+            if os.path.exists(cand):
+                os.environ["BRM_NCCL_LIB"] = os.path.abspath(cand)
+                return
+
+
 def comm_unique_id():
     """128 bytes identifying a new communicator (brm_comm_unique_id; call on one rank)."""
+    _prefer_torch_nccl()
     buf = (C.c_uint8 * 128)()
     check(load().brm_comm_unique_id(buf))
     return bytes(buf)
@@ -240,6 +263,7 @@ class Engine:
     def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
         """brm_comm_init: collective over the ranks that share `unique_id` (made on rank 0 with
         `comm_unique_id()` and handed round by the caller)."""
+        _prefer_torch_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(self.lib.brm_comm_init(self.handle, buf, int(rank), int(n_ranks)))
 

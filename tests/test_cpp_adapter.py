@@ -92,3 +92,21 @@ def test_adapter_continuous_reference_pins(exe, tmp_path):
     assert lines[4] == "execute on terminal: error -4"     # BARK_EXPECT_TRUE(!IsTerminal()), :59
     # the collided agent is INVALID, so its rules are not evaluated any more (:177); no violation at the start
     assert lines[5] == "evaluate_rules on collided state 0, on the initial state 0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["collision", "pass", "livelock"])
+def test_cpp_host_tree_reproduces_the_threshold_suite(built, tmp_path, case):
+    """include/brm_mcts.hpp: the leaf-parallel host search in C++ (no Python in the loop) reproduces
+    test/grid_world_threshold_test.cpp:40-71 on the device engine, 3000 iterations x <= 16 decisions."""
+    exe = os.path.join(ROOT, "build", "mcts_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "mcts_test.cpp"), "-o", exe, "-L", PKG, "-lbrm",
+                    "-Wl,-rpath," + PKG], check=True)
+    rules = brm.make_default_rules()
+    arr = (_abi.Rule * len(rules))(*[r.to_abi(GW_LABELS) for r in rules])
+    path = tmp_path / "rules.bin"
+    path.write_bytes(bytes(arr))
+    rc, out = run(exe, str(path), case, "8", "16")
+    assert rc == 0 and "expectations hold" in out, out

@@ -402,3 +402,109 @@ def test_agent_rule_masks_match_oracle(built, orc):
     ref = orc.rollout_detail(oracle_config(scn), scn.initial_state, FL(4), scn.params.HORIZON, 4, 0, 48, 12,
                              scn.params.DISCOUNT_FACTOR, q0=q0)
     compare_rollouts(out, ref, "agent rules")
+
+
+def test_gpu_bits_equal_the_host_compiled_work_items(built):
+    """tests/cpp/cw_emul.cpp runs the kernels' work-item functions (csrc/cw_core.cuh) on the CPU; the
+    library is compiled with --fmad=false and spells its fused multiply-adds out, so the GPU must
+    produce the same BITS -- states, returns, everything (a scheduling bug in the pool kernel, a
+    stale slot, a lost update would show here even where the oracle comparison has tolerance)."""
+    from tests.cw_emul import CwEmul
+    em = CwEmul()
+    for make, n in ((scenarios.merge_scenario, 1500), (scenarios.highway_scenario, 800),
+                    (scenarios.intersection_scenario, 200)):
+        scn = make(seed=33)
+        eng = brm.RulesMctsEngine([scn], device=0)
+        A = len(scn.agents)
+        out = eng.rollout(eng.initial_batch(), n, seed=9, rollout_base=50, max_steps=30, detail=True)
+        ref = em.rollout_detail(scn, scn.initial_state, FL(A), scn.params.HORIZON, 9, 50, n, 30,
+                                scn.params.DISCOUNT_FACTOR)
+        for k in ("ro_returns", "ro_viol", "ro_q", "ro_agents", "ro_flags", "ro_steps"):
+            assert np.array_equal(out[k], ref[k]), (make.__name__, k)
+        assert int(out["agent_steps"][0]) == ref["agent_steps"]
+
+
+def test_agents_leaving_the_map_on_the_gpu(built, orc):
+    """remove_agents_out_of_map (src/rules_mcts_state.cpp:121-125): vanished agents, their
+    out-of-map reward, one action afterwards, no ego -> terminal; replay and rollouts vs the oracle."""
+    prim = [(0.0, 0.0), (0.0, 0.6), (2.0, -0.4)]
+    scn = scenarios.straight_road_test_world(n_others=3, multi_agent=True, primitives=prim, rules=[
+        RuleMonitor.MakeRule("G !collision_corridor", -7.0, 0), RuleMonitor.MakeRule("G !collision_ego", -3.0, 1)])
+    scn.params.REMOVE_AGENTS_OUT_OF_MAP = True
+    scn.params.REWARD_VECTOR_SIZE = 2
+    scn.initial_state[1] = (30.0, -5.25, 0.0, 5.0)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    rng = np.random.default_rng(8)
+    acts = rng.integers(0, 3, size=(96, 18, 4)).astype(np.uint8)
+    tr, outs, _ = replay_both(eng, orc, scn, acts)
+    gone = 0
+    for b, o in enumerate(outs):
+        compare_trace(tr, b, o, scn)
+        gone += int((o["flags"][:o["steps"]] == 0).any())
+    assert gone > 10
+    out = eng.rollout(eng.initial_batch(), 2000, seed=3, max_steps=30, detail=True)
+    ref = orc.rollout_detail(oracle_config(scn), scn.initial_state, FL(4), scn.params.HORIZON, 3, 0, 2000, 30,
+                             scn.params.DISCOUNT_FACTOR)
+    compare_rollouts(out, ref, "vanish")
+    assert (ref["flags"] == 0).any()
+    # StateInterface view: a vanished agent has one action, its slot earns OUT_OF_MAP_WEIGHT once
+    two = scenarios.straight_road_test_world(n_others=1, multi_agent=True, primitives=[(0.0, 0.0), (0.0, 0.6)],
+                                             rules=[RuleMonitor.MakeRule("G !collision_corridor", -7.0, 0)])
+    two.params.REMOVE_AGENTS_OUT_OF_MAP = True
+    two.initial_state[1] = (30.0, -5.25, 0.0, 5.0)
+    s = brm.MvmctsState(brm.RulesMctsEngine([two], device=0))
+    rewards = []
+    for _ in range(12):
+        s = s.Execute([0, 1], rewards)
+        if s.GetAgentFlags()[1] == 0:
+            break
+    assert s.GetAgentFlags()[1] == 0 and rewards[1][0] == -800.0 and s.GetNumActions(1) == 1
+    assert not s.IsTerminal() and s.GetMultiAgentRuleState()[1, 0] == 0     # it never saw itself off the road
+    s2 = s.Execute([0, 0], rewards)
+    assert rewards[1][0] == 0.0 and np.all(s2.GetTerminalReward()[1] == 0.0)
+
+
+def test_evaluate_rules_matches_oracle(built, orc):
+    """brm_cw_evaluate_rules (MvmctsState::EvaluateRules(), :186-197) against the oracle's restatement."""
+    scn = scenarios.merge_scenario(seed=4)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    cfg = oracle_config(scn)
+    rng = np.random.default_rng(1)
+    n = 200
+    states = np.broadcast_to(scn.initial_state, (n, 4, 4)).copy()
+    states[:, :, 0] += rng.uniform(-12, 30, size=(n, 4))
+    flags = np.broadcast_to(FL(4), (n, 4)).copy()
+    flags[rng.random((n, 4)) < 0.2] = ocw.PRESENT
+    q = rng.integers(0, 3, size=(n, 4, 4)).astype(np.uint8)
+    q[:, :, 0] = 0
+    batch = eng.make_batch(states, flags=flags, q=q)
+    nb, rew = eng.evaluate_rules(batch)
+    hits = 0
+    for i in range(n):
+        want = orc.evaluate_rules(cfg, states[i], flags[i], scn.params.HORIZON, q[i])
+        assert np.array_equal(nb.q[:, :, i], want["q"]), i
+        assert np.array_equal(nb.viol[:, :, i], want["viol"]), i
+        assert_close(rew[:, :, i], want["rewards"], i)
+        hits += int(want["viol"].sum() > 0)
+    assert hits > 0 and np.array_equal(nb.agents, batch.agents) and np.array_equal(nb.horizon, batch.horizon)
+
+
+def test_one_rollout_per_leaf(built, orc):
+    """mvmcts::RandomHeuristic runs ONE rollout per expanded node (SURVEY 3.2): thousands of different
+    leaves with one rollout each in one call, every rollout equal to the oracle's from that leaf."""
+    scn = scenarios.merge_scenario(seed=12)
+    eng = brm.RulesMctsEngine([scn], device=0)
+    cfg = oracle_config(scn)
+    rng = np.random.default_rng(6)
+    L = 3000
+    states = np.broadcast_to(scn.initial_state, (L, 4, 4)).copy()
+    states[:, :, 0] += rng.uniform(-6, 6, size=(L, 4))
+    states[:, :, 3] += rng.uniform(-2, 2, size=(L, 4))
+    leaves = eng.make_batch(states, horizon=15)
+    out = eng.rollout(leaves, 1, seed=21, rollout_base=7, max_steps=30, detail=True)
+    for l in range(0, L, 7):
+        ref = orc.rollout_detail(cfg, states[l], FL(4), 15, 21, 7 + l, 1, 30, scn.params.DISCOUNT_FACTOR)
+        if leaves.terminal[l]:
+            assert out["ro_steps"][l] == 0
+        compare_rollouts({k: v[l:l + 1] for k, v in out.items() if k.startswith("ro_")}, ref, l)
+        assert_close(out["returns_sum"][l], ref["returns"][0], l, atol=2.0 ** -23)
