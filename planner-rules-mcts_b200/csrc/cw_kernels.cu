@@ -31,6 +31,22 @@ namespace brm {
 
 namespace {
 
+// The warps of a CTA own their pools, but they walk through the phases of an iteration in step
+// (a CTA barrier per phase): twelve warps in four different phases need the whole loop (~70 KB
+// of code) in the instruction cache at once, twelve warps in the same phase a quarter of it.
+// The warps have the same number of work items per phase (the refill rule), so little is lost
+// at the barriers; a warp whose pool has run dry keeps attending them until every warp is done.
+#ifndef BRM_CW_PHASE_SYNC
+#define BRM_CW_PHASE_SYNC 1
+#endif
+#define CW_PHASE_BARRIER()  \
+  do {                      \
+    if (kPhaseSync)         \
+      __syncthreads();      \
+    else                    \
+      __syncwarp();         \
+  } while (0)
+
 constexpr double kFixScale = 16777216.0;  // 2^24: fixed-point scale of the per-leaf return sums
 
 // (re)stage the blob of scenario `scn`; all threads of the CTA call this together
@@ -145,6 +161,8 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   __shared__ int s_next, s_end;
   __shared__ unsigned long long s_unit;
 
+  // one CTA per SM (the large shape): its warps are the only ones sharing the instruction cache
+  constexpr bool kPhaseSync = BRM_CW_PHASE_SYNC != 0 && NT >= 256;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int P = args.P, A = args.A, M = args.M, R = args.R, V = args.V;
   const unsigned full = 0xffffffffu;
@@ -421,7 +439,12 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           hs[HS_RFLAG] = static_cast<uint8_t>((fin ? 1 : 0) | (init ? 2 : 0));
         }
         for (int j = 0; j < A; ++j) cw_push(listR, nR, want && (fin || init), static_cast<uint16_t>(e0 | j));
-        if (!__ballot_sync(full, in_range && (busy || init))) break;  // pool empty, no work left
+        if (kPhaseSync) {
+          // (CTA-wide: the barrier of this phase doubles as the vote on whether anybody has work)
+          if (!__syncthreads_or(in_range && (busy || init))) break;
+        } else {
+          if (!__ballot_sync(full, in_range && (busy || init))) break;  // pool empty, no work left
+        }
         // the leaf the new rollouts start from: project it once (lanes = agents), copy it per slot
         const unsigned imask = __ballot_sync(full, init);
         if (imask) {
@@ -433,7 +456,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           }
         }
       }
-      __syncwarp();
+      __syncwarp();  // (with BRM_CW_PHASE_SYNC the vote above was the barrier)
       // ---------------------------------------------------------- S2: recycle items
       for (int i0 = 0; i0 < nR; i0 += 32) {
         const int i = i0 + lane;
@@ -462,7 +485,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
         if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, n1, p1, e);
         cw_push(list2, n2, p2, e);
       }
-      __syncwarp();
+      CW_PHASE_BARRIER();
       // ---------------------------------------------------------- phase 1
       if (MODE == MODE_RULES) {
         for (int i = lane; i < n2; i += 32) {
@@ -488,7 +511,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           cw_exact_shape_item(B, p, e >> 4, e & 15);
         }
       }
-      __syncwarp();
+      CW_PHASE_BARRIER();
       // ---------------------------------------------------------- phase 2
       for (int i = lane; i < n2; i += 32) {
         const uint16_t e = list2[i];

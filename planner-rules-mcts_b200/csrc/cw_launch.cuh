@@ -8,7 +8,10 @@ namespace brm {
 
 // The two launch shapes of the continuous-world kernels (threads per CTA x resident CTAs per
 // SM; register budget 65536 / (CTAs * threads) = 170)
-constexpr int kCwThreadsLarge = 384;  // x 1
+#ifndef BRM_CW_THREADS_LARGE
+#define BRM_CW_THREADS_LARGE 384
+#endif
+constexpr int kCwThreadsLarge = BRM_CW_THREADS_LARGE;  // x 1
 constexpr int kCwThreadsSmall = 128;  // x 3
 constexpr int kCwCtasSmall = 3;
 
