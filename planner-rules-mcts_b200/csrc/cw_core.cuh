@@ -794,8 +794,10 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
   int jf = -1;
   double gf = 0.0, vf = 0.0;
   uint32_t merged_mask = 0, near_mask = 0;
-  for (int j = 0; j < A; ++j) {
-    if (j == a) continue;
+  // (the other agents in ascending order, skipping myself without a divergent iteration: the lanes
+  // of a warp are different agents, and `if (j == a) continue` would idle a quarter of them in turn)
+  for (int o = 0; o < A - 1; ++o) {
+    const int j = o + (o >= a ? 1 : 0);
     const CwMeta mj = *cw_meta(p, base + j);
     if (!(mj.flags & BRM_CW_PRESENT)) continue;
     const double* rj = cw_ag(p, base + j);
