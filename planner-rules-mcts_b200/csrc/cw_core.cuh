@@ -156,7 +156,7 @@ struct CwPool {
   double* ag;    // [P * A][kAgWords]
   double* mc;    // [P * M][mw]
   double* disc;  // [P] discount of the current step
-  int32_t* hdr;  // [P][H_WORDS]
+  int32_t* hdr;  // [H_WORDS][P]
 };
 
 BRM_HD int cw_mc_words(int R) {
@@ -184,6 +184,12 @@ BRM_HD void cw_pool_carve(CwPool& p, void* mem, int P, int A, int M, int R, int 
   p.hdr = reinterpret_cast<int32_t*>(d);
 }
 
+// Slot of agent j of rollout r.  Agent-major: the work lists group items by agent, so the lanes of
+// a warp hold the same agent of consecutive rollouts -- stored next to each other (one odd record
+// stride apart), they read a field from different banks; rollout-major storage would put them
+// A records apart and, for A = 4, eight lanes on every bank.
+BRM_HD int cw_slot(const CwPool& p, int r, int j) { return j * p.P + r; }
+BRM_HD int cw_mslot(const CwPool& p, int r, int a) { return a * p.P + r; }
 BRM_HD double* cw_ag(const CwPool& p, int s) { return p.ag + s * kAgWords; }
 BRM_HD CwMeta* cw_meta(const CwPool& p, int s) { return reinterpret_cast<CwMeta*>(p.ag + s * kAgWords + AG_META); }
 BRM_HD double* cw_mc(const CwPool& p, int sm) { return p.mc + sm * p.mw; }
@@ -191,8 +197,15 @@ BRM_HD uint32_t* cw_mc_rng(const CwPool& p, int sm) { return reinterpret_cast<ui
 BRM_HD uint32_t* cw_mc_live(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + MC_TAIL); }
 BRM_HD uint32_t* cw_mc_qw(const CwPool& p, int sm) { return cw_mc_live(p, sm) + 1; }
 BRM_HD uint8_t* cw_mc_viol(const CwPool& p, int sm) { return reinterpret_cast<uint8_t*>(cw_mc_qw(p, sm) + p.QW); }
-BRM_HD int32_t* cw_hdr(const CwPool& p, int r) { return p.hdr + r * H_WORDS; }
-BRM_HD uint8_t* cw_hstate(const CwPool& p, int r) { return reinterpret_cast<uint8_t*>(cw_hdr(p, r) + H_STATE); }
+// rollout headers are stored field by field ([H_WORDS][P]): S1 maps a lane to a rollout slot, and
+// a record per rollout (8 words) would put every fourth lane on the same bank
+struct CwHdrRef {
+  int32_t* base;  // field 0 of this rollout
+  int32_t P;
+  BRM_HD int32_t& operator[](int field) const { return base[field * P]; }
+};
+BRM_HD CwHdrRef cw_hdr(const CwPool& p, int r) { return CwHdrRef{p.hdr + r, p.P}; }
+BRM_HD uint8_t* cw_hstate(const CwPool& p, int r) { return reinterpret_cast<uint8_t*>(p.hdr + H_STATE * p.P + r); }
 
 // ------------------------------------------------------------------ small math
 BRM_HD double cw_fma(double a, double b, double c) { return fma(a, b, c); }
@@ -526,15 +539,15 @@ BRM_HD void cw_load_kin(const double* rec, CwKin& t) {
   t.x = rec[AG_X]; t.y = rec[AG_Y]; t.th = rec[AG_TH]; t.v = rec[AG_V]; t.cs = rec[AG_CS]; t.sn = rec[AG_SN];
 }
 
-BRM_HD bool cw_collides(const CwBlob& B, const CwPool& p, int base, int a) {
+BRM_HD bool cw_collides(const CwBlob& B, const CwPool& p, int r, int a) {
   const int A = p.A;
-  const double* ra = cw_ag(p, base + a);
+  const double* ra = cw_ag(p, cw_slot(p, r, a));
   const double xa = ra[AG_X], ya = ra[AG_Y], ca = ra[AG_CS], sa = ra[AG_SN];
   const double cxa = cw_fma(B.off[a], ca, xa), cya = cw_fma(B.off[a], sa, ya);
   bool coll = false;
   for (int j = 0; j < A; ++j) {
-    if (j == a || !(cw_meta(p, base + j)->flags & BRM_CW_PRESENT)) continue;
-    const double* rj = cw_ag(p, base + j);
+    if (j == a || !(cw_meta(p, cw_slot(p, r, j))->flags & BRM_CW_PRESENT)) continue;
+    const double* rj = cw_ag(p, cw_slot(p, r, j));
     const double xj = rj[AG_X], yj = rj[AG_Y], cj = rj[AG_CS], sj = rj[AG_SN];
     const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
     const double rr = B.rad[a] + B.rad[j];
@@ -564,7 +577,7 @@ struct CwStatesView {
 // agent j of state `leaf` into slot (r, j): pose, lane projection, automaton states
 BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int r, int j, int64_t leaf) {
   const int A = p.A, M = p.M, R = p.R;
-  const int s = r * A + j;
+  const int s = cw_slot(p, r, j);
   const double* src = S.agents + (static_cast<int64_t>(j) * S.n + leaf) * 4;
   CwKin t;
   t.x = src[0]; t.y = src[1]; t.th = src[2]; t.v = src[3];
@@ -589,7 +602,7 @@ BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int 
   m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits; m._spare = 0;
   *cw_meta(p, s) = m;
   if (j < M) {
-    const int sm = r * M + j;
+    const int sm = cw_mslot(p, r, j);
     double* mc = cw_mc(p, sm);
     mc[MC_COST] = 0.0;
     for (int v = 0; v < 4; ++v) mc[MC_ACC + v] = 0.0;
@@ -612,8 +625,8 @@ BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int 
 // GetTerminalReward (:148-164) of MCTS agent a in slot r
 BRM_HD void cw_terminal_reward(const CwBlob& B, const CwPool& p, int r, int a, double (&tr)[4]) {
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-  if (cw_meta(p, r * p.A + a)->flags & BRM_CW_PRESENT) {
-    const uint32_t* qw = cw_mc_qw(p, r * p.M + a);
+  if (cw_meta(p, cw_slot(p, r, a))->flags & BRM_CW_PRESENT) {
+    const uint32_t* qw = cw_mc_qw(p, cw_mslot(p, r, a));
     for (int sl = 0; sl < p.R; ++sl) {
       const brm_rule& rule = B.rules[B.slot_rule[sl]];
       if (!rule.accepting[cw_q_get(qw, sl)]) {
@@ -639,14 +652,14 @@ struct CwStepCtx {
 
 BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int a) {
   const uint32_t n_prims = B.n_prims[a];
-  const int32_t* h = cw_hdr(p, r);
+  const CwHdrRef h = cw_hdr(p, r);
   const int k = h[H_K];
   if (c.actions) {
     const int64_t i = h[H_LEAF];
     const uint32_t act = c.T > 0 ? c.actions[(i * c.T + k) * p.M + a] : c.actions[static_cast<int64_t>(a) * c.n + i];
     return act < n_prims ? act : 0u;
   }
-  uint32_t* blk = cw_mc_rng(p, r * p.M + a);
+  uint32_t* blk = cw_mc_rng(p, cw_mslot(p, r, a));
   if ((k & 3) == 0)
     cw_philox_block(c.seed, c.rollout_base + static_cast<uint64_t>(h[H_FLAT]), static_cast<uint32_t>(k),
                     static_cast<uint32_t>(a), blk);
@@ -660,7 +673,7 @@ BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, i
 // then runs cw_exact_shape_item for this agent before phase 2.
 BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int j) {
   const int A = p.A, M = p.M;
-  const int s = r * A + j;
+  const int s = cw_slot(p, r, j);
   double* rec = cw_ag(p, s);
   CwMeta* meta = cw_meta(p, s);
   CwKin t;
@@ -699,7 +712,7 @@ BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
     if (f.lane >= 0) cost = cw_fma(B.w_lane * fabs(f.lat), dt, cost);
     const double pot_new = -B.w_pot * dt * fabs(t.v - B.v_des);
     const double pot_cur = -B.w_pot * dt * fabs(v0 - B.v_des);
-    cw_mc(p, r * M + j)[MC_COST] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
+    cw_mc(p, cw_mslot(p, r, j))[MC_COST] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
   }
   rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
   rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
@@ -714,7 +727,7 @@ BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
 
 // the exact drivable-area test for an agent phase 1 left pending (near the polygon's boundary)
 BRM_HD void cw_exact_shape_item(const CwBlob& B, CwPool& p, int r, int j) {
-  const int s = r * p.A + j;
+  const int s = cw_slot(p, r, j);
   double* rec = cw_ag(p, s);
   CwMeta* meta = cw_meta(p, s);
   CwKin t;
@@ -740,7 +753,7 @@ BRM_HD void cw_exact_shape_item(const CwBlob& B, CwPool& p, int r, int j) {
 // drivable-area / goal bits of MCTS agent a in slot r as it stands (EvaluateRules() on a state
 // that is not the result of a step in this pool)
 BRM_HD void cw_shape_bits_item(const CwBlob& B, CwPool& p, int r, int a) {
-  const int s = r * p.A + a;
+  const int s = cw_slot(p, r, a);
   CwKin t;
   cw_load_kin(cw_ag(p, s), t);
   double cx[4], cy[4];
@@ -763,7 +776,7 @@ struct CwEval {
 // state as it is.  Returns through `o`; accumulates disc * reward into the slot.
 BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_only, CwEval& o) {
   const int A = p.A, M = p.M, V = p.V;
-  const int base = r * A, s = base + a, sm = r * M + a;
+  const int s = cw_slot(p, r, a), sm = cw_mslot(p, r, a);
   o.r[0] = o.r[1] = o.r[2] = o.r[3] = 0.0;
   o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
   CwMeta* meta = cw_meta(p, s);
@@ -798,14 +811,15 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
   // of a warp are different agents, and `if (j == a) continue` would idle a quarter of them in turn)
   for (int o = 0; o < A - 1; ++o) {
     const int j = o + (o >= a ? 1 : 0);
-    const CwMeta mj = *cw_meta(p, base + j);
+    const int sj = cw_slot(p, r, j);
+    const CwMeta mj = *cw_meta(p, sj);
     if (!(mj.flags & BRM_CW_PRESENT)) continue;
-    const double* rj = cw_ag(p, base + j);
+    const double* rj = cw_ag(p, sj);
     const double xj = rj[AG_X], yj = rj[AG_Y];
-    const double cj = rj[AG_CS], sj = rj[AG_SN];
-    const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], sj, yj) - cya;
+    const double cj = rj[AG_CS], snj = rj[AG_SN];
+    const double ddx = cw_fma(B.off[j], cj, xj) - cxa, ddy = cw_fma(B.off[j], snj, yj) - cya;
     const double rr = B.rad[a] + B.rad[j];
-    if (cw_fma(ddx, ddx, ddy * ddy) <= rr * rr) coll = cw_rect_overlap(B, a, xa, ya, ca, sa, j, xj, yj, cj, sj) || coll;
+    if (cw_fma(ddx, ddx, ddy * ddy) <= rr * rr) coll = cw_rect_overlap(B, a, xa, ya, ca, sa, j, xj, yj, cj, snj) || coll;
     if (!evaluated) continue;
     const int lane_j = mj.lane;
     if (lane_j >= 0) {
@@ -926,13 +940,13 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
 
 // MvmctsState::CheckTerminal (:266-285) of the state in slot r as it is
 BRM_HD bool cw_check_terminal(const CwBlob& B, const CwPool& p, int r) {
-  const int s = r * p.A;
+  const int s = cw_slot(p, r, 0);
   if (!(cw_meta(p, s)->flags & BRM_CW_PRESENT)) return true;
   CwKin t;
   cw_load_kin(cw_ag(p, s), t);
   double cx[4], cy[4];
   cw_corners(B, t, 0, cx, cy);
-  return cw_hdr(p, r)[H_HORIZON] == 0 || cw_out_of_map(B, t, 0, cx, cy) || cw_collides(B, p, s, 0) ||
+  return cw_hdr(p, r)[H_HORIZON] == 0 || cw_out_of_map(B, t, 0, cx, cy) || cw_collides(B, p, r, 0) ||
          cw_at_goal(B, t, 0, cx, cy);
 }
 

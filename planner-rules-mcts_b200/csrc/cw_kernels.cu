@@ -138,11 +138,11 @@ __device__ __forceinline__ void cw_cache_fill(const CwBlob& B, const CwStatesVie
 __device__ __forceinline__ void cw_init_from_cache(CwPool& p, const double* cache_ag, const uint32_t* cache_mc, int r,
                                                    int j) {
   const double* src = cache_ag + j * kAgWords;
-  double* rec = cw_ag(p, r * p.A + j);
+  double* rec = cw_ag(p, cw_slot(p, r, j));
 #pragma unroll
   for (int k = 0; k < kAgWords; ++k) rec[k] = src[k];
   if (j < p.M) {
-    const int sm = r * p.M + j;
+    const int sm = cw_mslot(p, r, j);
     double* mc = cw_mc(p, sm);
 #pragma unroll
     for (int k = 0; k < MC_TAIL; ++k) mc[k] = 0.0;  // cost, acc, rng
@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
 
   // ---- what is written when a rollout (state) leaves the pool
   auto finalize = [&](int r, int j) {
-    const int s = r * A + j, sm = r * M + j;
-    const int32_t* fr = fin_rec + r * 8;
+    const int s = cw_slot(p, r, j), sm = cw_mslot(p, r, j);
+    const CwHdrRef fr{fin_rec + r, P};  // field by field, like the headers
     const int64_t flat = fr[0];
     const int64_t leaf = fr[1];
     const double* rec = cw_ag(p, s);
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
       {
         const int r = lane;
         const bool in_range = r < P;
-        int32_t* h = cw_hdr(p, in_range ? r : 0);
+        const CwHdrRef h = cw_hdr(p, in_range ? r : 0);
         uint8_t* hs = cw_hstate(p, in_range ? r : 0);
         bool fin = false, busy = false;
         if (in_range) {
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
             }
             if (hs[HS_DONE] || h[H_K] >= max_steps) {
               fin = true;
-              int32_t* fr = fin_rec + r * 8;
+              const CwHdrRef fr{fin_rec + r, P};
               fr[0] = h[H_FLAT]; fr[1] = h[H_LEAF]; fr[2] = h[H_K]; fr[3] = h[H_HORIZON]; fr[4] = h[H_NSTEPS];
               fr[5] = hs[HS_DONE];
               fin_disc[r] = p.disc[r];
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
         const uint16_t e0 = static_cast<uint16_t>(r << 4);
         int moved = 0;
         for (int j = 0; j < A; ++j) {
-          const uint8_t f = cont ? cw_meta(p, r * A + j)->flags : 0;
+          const uint8_t f = cont ? cw_meta(p, cw_slot(p, r, j))->flags : 0;
           const bool p1 = cont && cw_in_list1<MODE>(f);
           if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, n1, p1, static_cast<uint16_t>(e0 | j));
           moved += p1 ? 1 : 0;
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
             else
               cw_init_item(B, p, view, r, j, leaf);
             if (hs[HS_LIVE]) {
-              const uint8_t f = cw_meta(p, r * A + j)->flags;
+              const uint8_t f = cw_meta(p, cw_slot(p, r, j))->flags;
               p1 = cw_in_list1<MODE>(f);
               p2 = j < M && cw_in_list2<MODE>(f, j);
               if (p1) atomicAdd(&cw_hdr(p, r)[H_NSTEPS], 1);
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           CwEval ev;
           cw_phase2_item(B, p, r, a, MODE == MODE_RULES, ev);
           if (MODE == MODE_REPLAY) {
-            const int32_t* h = cw_hdr(p, r);
+            const CwHdrRef h = cw_hdr(p, r);
             const int64_t bt = static_cast<int64_t>(h[H_LEAF]) * args.T + h[H_K];
             for (int v = 0; v < V; ++v) args.tr.rewards_out[(bt * M + a) * V + v] = ev.r[v];
             for (int w = 0; w < 4; ++w) args.tr.labels_out[(bt * M + a) * 4 + w] = ev.w[w];
@@ -533,10 +533,10 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
       if (MODE == MODE_REPLAY) {
         // the trace of this step: every agent of every rollout that executed it
         for (int s = lane; s < P * A; s += 32) {
-          const int r = s / A, j = s - r * A;
+          const int j = s / P, r = s - j * P;  // agent-major slots (cw_slot)
           const uint8_t* hs = cw_hstate(p, r);
           if (!hs[HS_BUSY] || !hs[HS_LIVE]) continue;
-          const int32_t* h = cw_hdr(p, r);
+          const CwHdrRef h = cw_hdr(p, r);
           const int k = h[H_K];
           const int64_t bt = static_cast<int64_t>(h[H_LEAF]) * args.T + k;
           const double* rec = cw_ag(p, s);
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           fo[0] = static_cast<double>(mt.lane); fo[1] = rec[AG_S]; fo[2] = rec[AG_LAT];
           if (j == 0) args.tr.terminal_out[bt] = hs[HS_DONE];
           if (j < M) {
-            const int sm = r * M + j;
+            const int sm = cw_mslot(p, r, j);
             uint8_t* viol = cw_mc_viol(p, sm);
             const uint32_t* qw = cw_mc_qw(p, sm);
             for (int sl = 0; sl < R; ++sl) {

@@ -71,7 +71,7 @@ OneState make_state(const CwBlob& B, int R, const double* states0, const uint8_t
 void fill_slot(Emul& e, OneState& st, int r, int horizon, int flat, double disc0) {
   CwPool& p = e.pool;
   const CwStatesView v = st.view(p.A);
-  int32_t* h = cw_hdr(p, r);
+  const CwHdrRef h = cw_hdr(p, r);
   h[H_FLAT] = flat;
   h[H_LEAF] = 0;
   h[H_K] = 0;
@@ -90,7 +90,7 @@ void step_slot(Emul& e, const CwStepCtx& c, int r, CwEval* ev /*[M]*/, double ga
   const int A = p.A, M = p.M;
   std::vector<int> l1, l2;
   for (int j = 0; j < A; ++j) {
-    const uint8_t f = cw_meta(p, r * A + j)->flags;
+    const uint8_t f = cw_meta(p, cw_slot(p, r, j))->flags;
     if ((f & BRM_CW_PRESENT) && (f & BRM_CW_VALID)) l1.push_back(j);
     if (j < M && (f & BRM_CW_PRESENT) && ((f & BRM_CW_VALID) || j == 0)) l2.push_back(j);
   }
@@ -184,7 +184,7 @@ int cwe_replay(const brm_cw_scenario* scn, const double* states0, const uint8_t*
     step_slot(e, c, r, ev.data(), 1.0);
     terminal = cw_hstate(p, r)[HS_DONE] != 0;
     for (int i = 0; i < A; ++i) {
-      const int s = r * A + i;
+      const int s = cw_slot(p, r, i);
       const double* rec = cw_ag(p, s);
       double* o = states_out + (static_cast<size_t>(t) * A + i) * 4;
       o[0] = rec[AG_X]; o[1] = rec[AG_Y]; o[2] = rec[AG_TH]; o[3] = rec[AG_V];
@@ -194,7 +194,7 @@ int cwe_replay(const brm_cw_scenario* scn, const double* states0, const uint8_t*
     }
     terminal_out[t] = terminal;
     for (int a = 0; a < M; ++a) {
-      const int sm = r * M + a;
+      const int sm = cw_mslot(p, r, a);
       for (int k = 0; k < R; ++k) {
         viol32[a * R + k] += cw_mc_viol(p, sm)[k];
         cw_mc_viol(p, sm)[k] = 0;
@@ -239,7 +239,7 @@ int cwe_rollout_detail(const brm_cw_scenario* scn, const double* states0, const 
     cw_hstate(p, r)[HS_DONE] = leaf_terminal ? 1 : 0;
     while (!cw_hstate(p, r)[HS_DONE] && cw_hdr(p, r)[H_K] < max_steps) step_slot(e, c, r, ev.data(), gamma);
     for (int a = 0; a < M; ++a) {
-      const int sm = r * M + a;
+      const int sm = cw_mslot(p, r, a);
       double tr[4];
       cw_terminal_reward(B, p, r, a, tr);
       for (int v = 0; v < V; ++v) returns[(i * M + a) * V + v] = fma(p.disc[r], tr[v], cw_mc(p, sm)[MC_ACC + v]);
@@ -249,7 +249,7 @@ int cwe_rollout_detail(const brm_cw_scenario* scn, const double* states0, const 
       }
     }
     for (int j = 0; j < A; ++j) {
-      const int s = r * A + j;
+      const int s = cw_slot(p, r, j);
       const double* rec = cw_ag(p, s);
       double* o = states_final + (i * A + j) * 4;
       o[0] = rec[AG_X]; o[1] = rec[AG_Y]; o[2] = rec[AG_TH]; o[3] = rec[AG_V];
