@@ -365,7 +365,7 @@ static int cw_rollout_impl(brm_engine* e, const brm_cw_states* leaves, const brm
   const int i_q = ar.in(leaves->q, static_cast<size_t>(M) * R * L);
   const int i_fa = first_action ? ar.in(first_action, L * M) : -1;
   const int i_st = first_action ? ar.in(stats, st_count) : -1;
-  const int t_ws = ar.tmp_zero((L * M * V + 1) * sizeof(long long));
+  const int t_ws = ar.tmp_zero(cw_rollout_ws_words(L, M, V) * sizeof(long long));
   const int o_ret = ar.out(out->returns_sum, L * M * V, false);  // NULL host pointer: computed, not copied back
   const int o_viol = out->viol_sum ? ar.out(out->viol_sum, L * M * R, true) : -1;
   const int o_steps = out->agent_steps ? ar.out(out->agent_steps, L, true) : -1;

@@ -158,7 +158,7 @@ template <int MODE, int NT, int CTAS>
 __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ int s_next, s_end;
+  __shared__ int s_leaf;
   __shared__ unsigned long long s_unit;
 
   // one CTA per SM (the large shape): its warps are the only ones sharing the instruction cache
@@ -209,10 +209,6 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
     hs[HS_DONE] = 0;
     hs[HS_LIVE] = 0;
     hs[HS_RFLAG] = 0;
-  }
-  if (tid == 0) {
-    s_next = 0;
-    s_end = 0;
   }
   int cur_scn = -1;
   uint32_t tma_phase = 0;
@@ -318,16 +314,33 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   for (;;) {
     if (!single) {
       // several scenarios: the blob is CTA-wide, so the CTA's warps work on the rollouts of one
-      // leaf at a time (claimed from the global counter); the pools drain in between
+      // leaf at a time; the pools drain in between.  Every leaf is first taken by one CTA (the
+      // global counter); CTAs that find no fresh leaf join the leaves that still have unclaimed
+      // rollouts (per-leaf counters in global memory), so the last leaves are shared
       __syncthreads();  // every warp has drained its pool
       if (tid == 0) {
         s_unit = atomicAdd(args.work_counter, 1ull);
-        s_next = 0;
-        s_end = n_per_leaf;
+        s_leaf = 0x7fffffff;
       }
       __syncthreads();
-      if (s_unit >= static_cast<unsigned long long>(args.in.n)) break;
-      unit_leaf = static_cast<int>(s_unit);
+      const int n_leaves = static_cast<int>(args.in.n);
+      if (s_unit < static_cast<unsigned long long>(n_leaves)) {
+        unit_leaf = static_cast<int>(s_unit);
+      } else {
+        const int start = static_cast<int>((s_unit * 2654435761ull) % static_cast<unsigned long long>(n_leaves));
+        for (int k = tid; k < n_leaves; k += NT) {
+          int l = start + k;
+          if (l >= n_leaves) l -= n_leaves;
+          if (*reinterpret_cast<volatile int32_t*>(args.leaf_next + l) < n_per_leaf) {
+            atomicMin(&s_leaf, k);
+            break;
+          }
+        }
+        __syncthreads();
+        if (s_leaf == 0x7fffffff) break;  // every rollout of every leaf has been claimed
+        unit_leaf = start + s_leaf;
+        if (unit_leaf >= n_leaves) unit_leaf -= n_leaves;
+      }
       cw_stage(smem, &bar, args, args.in.scenario[unit_leaf], cur_scn, tma_phase);
     }
     for (;;) {
@@ -404,9 +417,9 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
               size = base + size > args.total ? (args.total > base ? args.total - base : 0) : size;
             } else {
               size = P;
-              const int b = atomicAdd(&s_next, static_cast<int>(size));
+              const int b = atomicAdd(args.leaf_next + unit_leaf, static_cast<int>(size));
               base = static_cast<long long>(unit_leaf) * n_per_leaf + b;
-              size = b + size > s_end ? (s_end > b ? s_end - b : 0) : size;
+              size = b + size > n_per_leaf ? (n_per_leaf > b ? n_per_leaf - b : 0) : size;
             }
           }
           c_lo = __shfl_sync(full, base, 0);
@@ -656,10 +669,11 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
     // the caller cleared the workspace and the sum outputs together with one memset
     a.returns_fx = zeroed_ws;
   } else {
-    rc = e->ensure_ws((fx_count + 1) * sizeof(long long));
+    const size_t ws = cw_rollout_ws_words(static_cast<size_t>(leaves.n), M, V) * sizeof(long long);
+    rc = e->ensure_ws(ws);
     if (rc != BRM_OK) return rc;
     a.returns_fx = static_cast<long long*>(e->d_ws);
-    BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, (fx_count + 1) * sizeof(long long), e->stream));
+    BRM_CUDA_CHECK(cudaMemsetAsync(a.returns_fx, 0, ws, e->stream));
     if (out.viol_sum)
       BRM_CUDA_CHECK(cudaMemsetAsync(out.viol_sum, 0, static_cast<size_t>(leaves.n) * M * R * sizeof(uint64_t),
                                      e->stream));
@@ -668,6 +682,7 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
                                      e->stream));
   }
   a.work_counter = reinterpret_cast<unsigned long long*>(a.returns_fx + fx_count);
+  a.leaf_next = reinterpret_cast<int32_t*>(a.work_counter + 1);
   e->time_begin();
   rc = launch_mode<MODE_ROLLOUT>(e, ctx, a, a.single_scenario ? a.total : leaves.n);
   if (rc != BRM_OK) return rc;

@@ -50,6 +50,7 @@ struct CwArgs {
   int32_t warp_bytes, target_items, n_warps_total;
   brm_cw_states in;  // leaves (rollouts) / states (batch modes)
   unsigned long long* work_counter;  // next unclaimed rollout / state (one scenario) or leaf (several); zeroed
+  int32_t* leaf_next;                // several scenarios: per leaf, its next unclaimed rollout; zeroed
   int64_t total;                     // work units behind the counter
   int32_t rollouts_per_leaf, max_steps, first_exp;
   int32_t single_scenario;  // 1: every unit lives in one scenario -> slots draw from the flat range
@@ -69,7 +70,10 @@ struct CwArgs {
   brm_cw_trace tr;
 };
 
-// zeroed_ws: NULL, or (leaves * M * V + 1) already cleared 64-bit words (the caller then also
+// 64-bit words of workspace a rollout launch needs (fixed-point sums, the work counter, per-leaf counters)
+inline size_t cw_rollout_ws_words(size_t leaves, int M, int V) { return leaves * M * V + 1 + (leaves + 1) / 2; }
+
+// zeroed_ws: NULL, or cw_rollout_ws_words() already cleared 64-bit words (the caller then also
 // cleared out.viol_sum / out.agent_steps)
 int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, const brm_cw_states& leaves,
                       const brm_rollout_params& rp, const brm_cw_rollout_out& out, long long* zeroed_ws = nullptr);

@@ -214,6 +214,31 @@ def test_multi_scenario_sweep_and_determinism(built, orc):
     assert len({float(x) for x in a["returns_sum"][:, 0, 3]}) == 6  # scenarios really differ
 
 
+def test_few_leaves_shared_by_many_ctas(built, orc):
+    """Several scenarios, few leaves, many rollouts per leaf: the CTAs that find no fresh leaf join
+    the leaves that still have unclaimed rollouts.  Every rollout runs exactly once, whoever ran it."""
+    scns = [scenarios.intersection_scenario(seed=1000, scenario_id=k) for k in range(3)]
+    eng = brm.RulesMctsEngine(scns, device=0)
+    leaves = eng.initial_batch()
+    n = 3000
+    a = eng.rollout(leaves, n, seed=5, detail=True)
+    b = eng.rollout(leaves, n, seed=5, detail=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["ro_steps"] > 0).all()
+    for k, scn in enumerate(scns):
+        sl = slice(k * n, (k + 1) * n)
+        assert np.array_equal(a["viol_sum"][k], a["ro_viol"][sl].astype(np.uint64).sum(0))
+        fx = np.rint(a["ro_returns"][sl] * 2.0 ** 24).astype(np.int64).sum(0)
+        assert np.array_equal(a["returns_sum"][k], fx.astype(np.float64) / 2.0 ** 24)
+        cfg = oracle_config(scn)
+        for lo in (0, n - 40):   # the first and the last rollouts of the leaf against the oracle
+            ref = orc.rollout_detail(cfg, scn.initial_state, FL(10), 20, 5, k * n + lo, 40, 30, 0.9)
+            part = slice(k * n + lo, k * n + lo + 40)
+            compare_rollouts({k2: v[part] for k2, v in a.items() if k2.startswith("ro_")}, ref,
+                             "scenario %d rollouts %d.." % (k, lo))
+
+
 def test_full_size_properties(built):
     """BASELINE config M size (262144 rollouts/decision): split invariance, device path ==
     host path, counts add up."""
