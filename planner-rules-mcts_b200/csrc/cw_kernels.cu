@@ -5,7 +5,8 @@
 //   QUERY        CheckTerminal / GetNumActions / GetTerminalReward
 //
 // Every WARP keeps a pool of up to 32 rollouts (states) in its own piece of shared memory and
-// advances all of them one step per iteration; warps never wait for one another.  The step is
+// advances all of them one step per iteration (the warps of the large CTA shape meet at one
+// barrier per iteration, see below; data never crosses warps).  The step is
 // cut into per-agent work items (cw_core.cuh) that are compacted into lists, so that the
 // lanes always work on agents that have work:
 //   S1  lane = rollout slot: bookkeeping of the last step; finished rollouts are recorded for
@@ -31,21 +32,17 @@ namespace brm {
 
 namespace {
 
-// The warps of a CTA own their pools, but they walk through the phases of an iteration in step
-// (a CTA barrier per phase): twelve warps in four different phases need the whole loop (~70 KB
-// of code) in the instruction cache at once, twelve warps in the same phase a quarter of it.
-// The warps have the same number of work items per phase (the refill rule), so little is lost
-// at the barriers; a warp whose pool has run dry keeps attending them until every warp is done.
+// The warps of a CTA own their pools, but they start the phases of an iteration together (ONE CTA
+// barrier per iteration, in front of phase 1): twelve warps spread over all phases need the
+// whole loop (~70 KB of code) in the instruction cache at once (a quarter of all stall samples
+// were instruction fetches without it).  The warps have about the same number of work items per
+// phase (the refill rule), so they stay close until the next barrier; more barriers (one per
+// phase: -4 %) or fewer (every second iteration) measured worse.  The barrier doubles as the
+// CTA's vote on whether anybody has work left: a warp whose pool has run dry keeps attending
+// until every warp is done.
 #ifndef BRM_CW_PHASE_SYNC
 #define BRM_CW_PHASE_SYNC 1
 #endif
-#define CW_PHASE_BARRIER()  \
-  do {                      \
-    if (kPhaseSync)         \
-      __syncthreads();      \
-    else                    \
-      __syncwarp();         \
-  } while (0)
 
 constexpr double kFixScale = 16777216.0;  // 2^24: fixed-point scale of the per-leaf return sums
 
@@ -345,6 +342,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
     }
     for (;;) {
       int n1 = 0, n2 = 0, nR = 0;
+      bool has_work = false;
       // ---------------------------------------------------------- S1: lane = rollout slot
       {
         const int r = lane;
@@ -452,12 +450,8 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           hs[HS_RFLAG] = static_cast<uint8_t>((fin ? 1 : 0) | (init ? 2 : 0));
         }
         for (int j = 0; j < A; ++j) cw_push(listR, nR, want && (fin || init), static_cast<uint16_t>(e0 | j));
-        if (kPhaseSync) {
-          // (CTA-wide: the barrier of this phase doubles as the vote on whether anybody has work)
-          if (!__syncthreads_or(in_range && (busy || init))) break;
-        } else {
-          if (!__ballot_sync(full, in_range && (busy || init))) break;  // pool empty, no work left
-        }
+        has_work = in_range && (busy || init);
+        if (!kPhaseSync && !__ballot_sync(full, has_work)) break;  // pool empty, no work left
         // the leaf the new rollouts start from: project it once (lanes = agents), copy it per slot
         const unsigned imask = __ballot_sync(full, init);
         if (imask) {
@@ -498,7 +492,11 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
         if (MODE != MODE_RULES && MODE != MODE_QUERY) cw_push(list1, n1, p1, e);
         cw_push(list2, n2, p2, e);
       }
-      CW_PHASE_BARRIER();
+      if (kPhaseSync) {
+        if (!__syncthreads_or(has_work)) break;
+      } else {
+        __syncwarp();
+      }
       // ---------------------------------------------------------- phase 1
       if (MODE == MODE_RULES) {
         for (int i = lane; i < n2; i += 32) {
@@ -524,7 +522,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           cw_exact_shape_item(B, p, e >> 4, e & 15);
         }
       }
-      CW_PHASE_BARRIER();
+      __syncwarp();
       // ---------------------------------------------------------- phase 2
       for (int i = lane; i < n2; i += 32) {
         const uint16_t e = list2[i];
