@@ -37,10 +37,8 @@
 #else
 #define BRM_LOOP_SMALL
 #endif
-#if defined(__CUDA_ARCH__) && defined(BRM_CW_SMALL_EULER)
-#define BRM_LOOP_EULER _Pragma("unroll 1")
-#elif defined(__CUDA_ARCH__) && defined(BRM_CW_EULER5)
-#define BRM_LOOP_EULER _Pragma("unroll 5")
+#if defined(__CUDA_ARCH__)
+#define BRM_LOOP_EULER _Pragma("unroll 2")
 #else
 #define BRM_LOOP_EULER
 #endif
@@ -306,17 +304,21 @@ BRM_HD void cw_integrate(const CwBlob& B, CwKin& t, double acc, double kap) {
   const int n_sub = B.n_sub;
   double x = t.x, y = t.y, v = t.v;
   if (kap == 0.0) {
-    const double cs = t.cs, sn = t.sn;
+    // n_sub - 1 sub-steps of h_sub and a last one of h_last (the loop is peeled: a select of h
+    // per sub-step cost as much as the arithmetic); h_sub * acc is the same product every time
+    const double cs = t.cs, sn = t.sn, hs = B.h_sub, hl = B.h_last, dv = hs * acc;
     BRM_LOOP_EULER
-    for (int n = 0; n < n_sub; ++n) {
-      const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
-      x = x + h * (v * cs);
-      y = y + h * (v * sn);
-      v = v + h * acc;
+    for (int n = 1; n < n_sub; ++n) {
+      x = x + hs * (v * cs);
+      y = y + hs * (v * sn);
+      v = v + dv;
     }
+    x = x + hl * (v * cs);
+    y = y + hl * (v * sn);
+    v = v + hl * acc;
   } else {
     double dx = 0.0, dy = 0.0, th = t.th, c = t.cs, s = t.sn;
-    _Pragma("unroll 1")
+    BRM_LOOP_SMALL
     for (int n = 0; n < n_sub; ++n) {
       const double h = (n == n_sub - 1) ? B.h_last : B.h_sub;
       const double hv = h * v;
