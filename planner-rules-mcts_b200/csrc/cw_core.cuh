@@ -130,6 +130,7 @@ enum : uint8_t {
   CW_BIT_VANISHED = 4,  // left the map during this step (remove_agents_out_of_map)
   CW_BIT_PENDING = 8,   // phase 1 could not tell the drivable-area test from the grid: cw_exact_shape_item
   CW_BIT_BEYOND = 16,   // on a lane, at or beyond its merge point (s >= s_point): merged_e / merged_x#j
+  CW_BIT_PENDING_V = 32,  // with PENDING: the corners are certainly inside, only the road vertices are left to test
 };
 
 // Records are padded to an odd number of 8-byte words, so that the lanes of a warp, which
@@ -471,6 +472,21 @@ BRM_HD bool cw_out_of_map_corners(const CwBlob& B, const CwKin& t, int a, const 
   return inside != 0xFu || vertex_in;
 }
 
+// the second half of the exact test alone (a road vertex strictly inside the rectangle), for
+// shapes whose corners the grid has already placed inside the polygon; same arithmetic
+BRM_HD bool cw_vertex_in_shape(const CwBlob& B, const CwKin& t, int a) {
+  bool vertex_in = false;
+  const double f = B.front[a], r = B.rear[a], h = B.hw[a];
+  const int n_road = B.n_road;
+  BRM_LOOP_SMALL
+  for (int e = 0; e < n_road; ++e) {
+    const double dx = B.road_edge[e].xa - t.x, dy = B.road_edge[e].ya - t.y;
+    const double lx = cw_fma(dx, t.cs, dy * t.sn), ly = cw_fma(dy, t.cs, -(dx * t.sn));
+    vertex_in = (lx > -r && lx < f && fabs(ly) < h) || vertex_in;
+  }
+  return vertex_in;
+}
+
 // the exact test from a pose (everything by value: one out-of-line copy in the kernels)
 BRM_HD_NOINLINE bool cw_out_of_map_pose(const CwBlob& B, double x, double y, double cs, double sn, int a) {
   CwKin t;
@@ -484,8 +500,8 @@ BRM_HD bool cw_out_of_map(const CwBlob& B, const CwKin& t, int a, const double (
 }
 
 // Drivable-area test through the grid: 1 = certainly out of the map, 0 = certainly inside,
-// -1 = too close to the polygon's boundary or to one of its vertices to tell (the caller runs
-// cw_out_of_map).  A corner in an OUTSIDE cell is outside the polygon; four corners in INSIDE
+// -1 = a corner too close to the polygon's boundary to tell (the caller runs cw_out_of_map),
+// -2 = corners certainly inside but a road vertex within reach (the caller runs cw_vertex_in_shape).  A corner in an OUTSIDE cell is outside the polygon; four corners in INSIDE
 // cells with no road vertex within reach of the centre's cell leave nothing that could make
 // the exact test true.
 BRM_HD int cw_classify_shape(const CwBlob& B, const CwKin& t, const double (&cx)[4], const double (&cy)[4]) {
@@ -508,7 +524,7 @@ BRM_HD int cw_classify_shape(const CwBlob& B, const CwKin& t, const double (&cx)
   }
   if (any & CW_CELL_OUTSIDE) return 1;
   if (!(all & CW_CELL_INSIDE)) return -1;
-  return (cell(t.x, t.y) & CW_CELL_VERTEX) ? -1 : 0;
+  return (cell(t.x, t.y) & CW_CELL_VERTEX) ? -2 : 0;
 }
 
 BRM_HD bool cw_at_goal(const CwBlob& B, const CwKin& t, int a, const double (&cx)[4], const double (&cy)[4]) {
@@ -690,7 +706,7 @@ BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
     cw_corners(B, t, j, cx, cy);
     const int cls = cw_classify_shape(B, t, cx, cy);
     if (cls > 0) bits |= CW_BIT_OOM;
-    if (cls < 0) bits |= CW_BIT_PENDING;
+    if (cls < 0) bits |= cls == -2 ? (CW_BIT_PENDING | CW_BIT_PENDING_V) : CW_BIT_PENDING;
     if (j < M && cw_at_goal(B, t, j, cx, cy)) bits |= CW_BIT_GOAL;
     if (B.remove_oom && (bits & CW_BIT_OOM)) {
       // World::RemoveInvalidAgents: the agent leaves the world
@@ -737,8 +753,9 @@ BRM_HD void cw_exact_shape_item(const CwBlob& B, CwPool& p, int r, int j) {
   double cx[4], cy[4];
   cw_corners(B, t, j, cx, cy);
   CwMeta m = *meta;
-  m.bits &= static_cast<uint8_t>(~CW_BIT_PENDING);
-  if (cw_out_of_map(B, t, j, cx, cy)) {
+  const bool vertex_only = (m.bits & CW_BIT_PENDING_V) != 0;
+  m.bits &= static_cast<uint8_t>(~(CW_BIT_PENDING | CW_BIT_PENDING_V));
+  if (vertex_only ? cw_vertex_in_shape(B, t, j) : cw_out_of_map(B, t, j, cx, cy)) {
     m.bits |= CW_BIT_OOM;
     if (B.remove_oom) {
       m.bits |= CW_BIT_VANISHED;

@@ -144,6 +144,8 @@ int cwe_classify(const brm_cw_scenario* scn, double x, double y, double th, int 
   cw_corners(*e.B, t, agent, cx, cy);
   const int cls = cw_classify_shape(*e.B, t, cx, cy);
   const int exact = cw_out_of_map(*e.B, t, agent, cx, cy) ? 1 : 0;
+  // "corners certainly inside": the vertex test alone must then say what the exact test says
+  if (cls == -2 && (cw_vertex_in_shape(*e.B, t, agent) ? 1 : 0) != exact) return -5;
   return cls < 0 ? 2 + exact : (cls == exact ? cls : -3 - cls);  // 0/1 decided and right, 2/3 pending, < -2 WRONG
 }
 
