@@ -146,8 +146,8 @@ enum { AG_X = 0, AG_Y, AG_TH, AG_V, AG_CS, AG_SN, AG_S, AG_LAT, AG_META };
 // MCTS agent record, in 8-byte words: cost, acc[4], rng[4 x u32], then u32 live, u32 qw[QW],
 // u8 viol[R]
 enum { MC_COST = 0, MC_ACC = 1, MC_RNG = 5, MC_TAIL = 7 };
-// rollout header, 8 x int32: flat, leaf, k, horizon, nsteps, state bytes (busy, done, live, rflag)
-enum { H_FLAT = 0, H_LEAF, H_K, H_HORIZON, H_NSTEPS, H_STATE, H_WORDS = 8 };
+// rollout header, 6 x int32: flat, leaf, k, horizon, nsteps, state bytes (busy, done, live, rflag)
+enum { H_FLAT = 0, H_LEAF, H_K, H_HORIZON, H_NSTEPS, H_STATE, H_WORDS = 6 };
 enum { HS_BUSY = 0, HS_DONE = 1, HS_LIVE = 2, HS_RFLAG = 3 };
 
 struct CwPool {

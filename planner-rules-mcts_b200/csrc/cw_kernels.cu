@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   cw_pool_carve(p, wmem, P, A, M, R, V);
   uint8_t* sp = wmem + cw_pool_bytes(P, A, M, R);
   double* fin_disc = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(P) * 8;
-  int32_t* fin_rec = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 8 * 4;  // flat, leaf, k, horizon, nsteps, done
+  int32_t* fin_rec = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 6 * 4;  // flat, leaf, k, horizon, nsteps, done
   // the leaf most rollouts of the warp's current chunk start from, ready to be copied into a slot
   double* cache_ag = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(A) * kAgWords * 8;
   uint32_t* cache_mc = reinterpret_cast<uint32_t*>(sp); sp += static_cast<size_t>(M) * (1 + p.QW) * 4;

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Step-mode kernels (K2 gw_execute_kernel, K4 cw_batch_kernel<EXECUTE>) against the HBM
+"""Step-mode kernels (K2 gw_execute_kernel, K4 cw_pool_kernel<EXECUTE>) against the HBM
 roofline: one Execute for n device-resident states, SoA in -> SoA out.  These kernels are the
 StateInterface surface for host-side tree expansion (not the benchmark's critical path); they
 stream every state once, so their bound is HBM.  Algorithmic bytes per state are counted from
@@ -65,7 +65,7 @@ def main():
     A, M, R, V = ce.A, ce.M, ce.R, ce.V
     n2 = n // 2
     st = np.broadcast_to(scn.initial_state, (n2, A, 4)).copy()
-    st[:, :, 0] += rng.uniform(-20, 20, size=(n2, A)).astype(np.float32)
+    st[:, :, 0] += rng.uniform(-20, 20, size=(n2, A))
     cb = brm.CwBatch.zeros(A, M, R, n2, track_violations=False)
     cb.agents[:] = st.transpose(1, 0, 2)
     cb.flags[:] = 3
@@ -74,10 +74,11 @@ def main():
     dcb = cb.cuda(0)
     acts = torch.from_numpy(rng.integers(0, 3, size=(M, n2)).astype(np.uint8)).cuda()
     ms = timeit(lambda: ce.execute(dcb, acts), stream)
-    rd = A * 16 + A + 4 + 1 + 4 + M * R + M
-    wr = A * 16 + A + 4 + 1 + 4 + M * R + M * V * 4
+    # FP64 states: 32 bytes per agent in and out, rewards are doubles
+    rd = A * 32 + A + 4 + 1 + 4 + M * R + M
+    wr = A * 32 + A + 4 + 1 + 4 + M * R + M * V * 8
     gbs = n2 * (rd + wr) / (ms * 1e-3) / 1e9
-    out.append(dict(kernel="cw_batch_kernel<EXECUTE> (config M scenario)", states=n2, ms=ms, bytes_per_state=rd + wr,
+    out.append(dict(kernel="cw_pool_kernel<EXECUTE> (config M scenario)", states=n2, ms=ms, bytes_per_state=rd + wr,
                     achieved_gbs=gbs, peak_gbs=PEAK, frac=gbs / PEAK, agent_steps_per_s=n2 * A / (ms * 1e-3)))
     for o in out:
         print(json.dumps(o))
