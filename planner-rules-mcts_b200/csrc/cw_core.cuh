@@ -135,17 +135,16 @@ enum : uint8_t {
 
 // Records are padded to an odd number of 8-byte words, so that the lanes of a warp, which
 // work on neighbouring slots, read a field from different banks.
-constexpr int kAgWords = 9;  // agent record: x, y, th, v, cs, sn, s, lat, meta
-struct CwMeta {              // the 9th word of an agent record
-  int16_t lane;              // lane of the current position, -1: none
-  uint8_t flags;             // BRM_CW_PRESENT | BRM_CW_VALID
-  uint8_t bits;              // CW_BIT_*
-  uint32_t _spare;
+constexpr int kAgWords = 9;  // agent record: x, y, th, v, cs, sn, s, lat, cost of the action just taken
+struct CwMeta {              // 4 bytes per agent, in an array of their own (p.meta): consecutive
+  int16_t lane;              // slots sit in consecutive banks (inside the 9-word records every
+  uint8_t flags;             // 32-bit access would meet the lane 16 slots away in the same bank)
+  uint8_t bits;              // lane of the current position (-1: none); BRM_CW_PRESENT | VALID; CW_BIT_*
 };
-enum { AG_X = 0, AG_Y, AG_TH, AG_V, AG_CS, AG_SN, AG_S, AG_LAT, AG_META };
-// MCTS agent record, in 8-byte words: cost, acc[4], rng[4 x u32], then u32 live, u32 qw[QW],
-// u8 viol[R]
-enum { MC_COST = 0, MC_ACC = 1, MC_RNG = 5, MC_TAIL = 7 };
+static_assert(sizeof(CwMeta) == 4, "CwMeta is one 32-bit word");
+enum { AG_X = 0, AG_Y, AG_TH, AG_V, AG_CS, AG_SN, AG_S, AG_LAT, AG_COST };
+// MCTS agent record, in 8-byte words: acc[V], rng[4 x u32], then u32 live, u32 qw[QW], u8 viol[R]
+enum { MC_ACC = 0 };
 // rollout header, 6 x int32: flat, leaf, k, horizon, nsteps, state bytes (busy, done, live, rflag)
 enum { H_FLAT = 0, H_LEAF, H_K, H_HORIZON, H_NSTEPS, H_STATE, H_WORDS = 6 };
 enum { HS_BUSY = 0, HS_DONE = 1, HS_LIVE = 2, HS_RFLAG = 3 };
@@ -153,21 +152,23 @@ enum { HS_BUSY = 0, HS_DONE = 1, HS_LIVE = 2, HS_RFLAG = 3 };
 struct CwPool {
   int32_t P, A, M, R, V, QW, mw;  // QW = words of packed automaton states per agent; mw = words per MCTS record
   double* ag;    // [P * A][kAgWords]
+  uint32_t* meta;  // [P * A] CwMeta
   double* mc;    // [P * M][mw]
   double* disc;  // [P] discount of the current step
   int32_t* hdr;  // [H_WORDS][P]
 };
 
-BRM_HD int cw_mc_words(int R) {
+BRM_HD int cw_mc_words(int R, int V) {
   const int QW = (R + 7) / 8;
-  int w = MC_TAIL + (4 * (1 + QW) + R + 7) / 8;
+  int w = V + 2 + (4 * (1 + QW) + R + 7) / 8;
   return (w & 1) ? w : w + 1;
 }
 
-BRM_HD size_t cw_pool_bytes(int P, int A, int M, int R) {
+BRM_HD size_t cw_pool_bytes(int P, int A, int M, int R, int V) {
   size_t b = static_cast<size_t>(P) * A * kAgWords * sizeof(double);
-  b += static_cast<size_t>(P) * M * cw_mc_words(R) * sizeof(double);
+  b += static_cast<size_t>(P) * M * cw_mc_words(R, V) * sizeof(double);
   b += static_cast<size_t>(P) * sizeof(double);
+  b += (static_cast<size_t>(P) * A * sizeof(uint32_t) + 7) & ~static_cast<size_t>(7);
   b += static_cast<size_t>(P) * H_WORDS * sizeof(int32_t);
   return (b + 15) & ~static_cast<size_t>(15);
 }
@@ -175,11 +176,12 @@ BRM_HD size_t cw_pool_bytes(int P, int A, int M, int R) {
 // carve the arrays out of `mem` (16-byte aligned, cw_pool_bytes large)
 BRM_HD void cw_pool_carve(CwPool& p, void* mem, int P, int A, int M, int R, int V) {
   p.P = P; p.A = A; p.M = M; p.R = R; p.V = V; p.QW = (R + 7) / 8;
-  p.mw = cw_mc_words(R);
+  p.mw = cw_mc_words(R, V);
   double* d = static_cast<double*>(mem);
   p.ag = d; d += static_cast<size_t>(P) * A * kAgWords;
   p.mc = d; d += static_cast<size_t>(P) * M * p.mw;
   p.disc = d; d += P;
+  p.meta = reinterpret_cast<uint32_t*>(d); d += (static_cast<size_t>(P) * A + 1) / 2;
   p.hdr = reinterpret_cast<int32_t*>(d);
 }
 
@@ -190,10 +192,10 @@ BRM_HD void cw_pool_carve(CwPool& p, void* mem, int P, int A, int M, int R, int 
 BRM_HD int cw_slot(const CwPool& p, int r, int j) { return j * p.P + r; }
 BRM_HD int cw_mslot(const CwPool& p, int r, int a) { return a * p.P + r; }
 BRM_HD double* cw_ag(const CwPool& p, int s) { return p.ag + s * kAgWords; }
-BRM_HD CwMeta* cw_meta(const CwPool& p, int s) { return reinterpret_cast<CwMeta*>(p.ag + s * kAgWords + AG_META); }
+BRM_HD CwMeta* cw_meta(const CwPool& p, int s) { return reinterpret_cast<CwMeta*>(p.meta + s); }
 BRM_HD double* cw_mc(const CwPool& p, int sm) { return p.mc + sm * p.mw; }
-BRM_HD uint32_t* cw_mc_rng(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + MC_RNG); }
-BRM_HD uint32_t* cw_mc_live(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + MC_TAIL); }
+BRM_HD uint32_t* cw_mc_rng(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + p.V); }
+BRM_HD uint32_t* cw_mc_live(const CwPool& p, int sm) { return reinterpret_cast<uint32_t*>(cw_mc(p, sm) + p.V + 2); }
 BRM_HD uint32_t* cw_mc_qw(const CwPool& p, int sm) { return cw_mc_live(p, sm) + 1; }
 BRM_HD uint8_t* cw_mc_viol(const CwPool& p, int sm) { return reinterpret_cast<uint8_t*>(cw_mc_qw(p, sm) + p.QW); }
 // rollout headers are stored field by field ([H_WORDS][P]): S1 maps a lane to a rollout slot, and
@@ -617,13 +619,13 @@ BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int 
   rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
   rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
   CwMeta m;
-  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits; m._spare = 0;
+  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits;
   *cw_meta(p, s) = m;
+  rec[AG_COST] = 0.0;
   if (j < M) {
     const int sm = cw_mslot(p, r, j);
     double* mc = cw_mc(p, sm);
-    mc[MC_COST] = 0.0;
-    for (int v = 0; v < 4; ++v) mc[MC_ACC + v] = 0.0;
+    for (int v = 0; v < p.V; ++v) mc[MC_ACC + v] = 0.0;
     uint32_t* rng = cw_mc_rng(p, sm);
     for (int v = 0; v < 4; ++v) rng[v] = 0u;
     uint32_t* qw = cw_mc_qw(p, sm);
@@ -730,7 +732,7 @@ BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
     if (f.lane >= 0) cost = cw_fma(B.w_lane * fabs(f.lat), dt, cost);
     const double pot_new = -B.w_pot * dt * fabs(t.v - B.v_des);
     const double pot_cur = -B.w_pot * dt * fabs(v0 - B.v_des);
-    cw_mc(p, cw_mslot(p, r, j))[MC_COST] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
+    rec[AG_COST] = cost + cw_fma(B.gamma, pot_new, -pot_cur);
   }
   rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
   rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
@@ -738,7 +740,6 @@ BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r
   m.lane = static_cast<int16_t>(f.lane);
   m.flags = present ? meta->flags : 0;
   m.bits = bits;
-  m._spare = 0;
   *meta = m;
   return (bits & CW_BIT_PENDING) != 0;
 }
@@ -876,7 +877,7 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
     if (!rules_only) {
       r0 += (coll ? 1.0 : 0.0) * B.w_coll;  // :91-92
       r0 += (oom ? 1.0 : 0.0) * B.w_oom;    // :94-96
-      add_at(V - 1, mc[MC_COST]);           // :98-102
+      add_at(V - 1, cw_ag(p, s)[AG_COST]);  // :98-102
     }
     // labels (EvaluateRules, :165-185)
     uint32_t w0 = 0;
@@ -948,10 +949,10 @@ BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_
     if (coll && !rules_only) meta->flags = fl & static_cast<uint8_t>(~BRM_CW_VALID);       // :116-120
     o.r[0] = r0; o.r[1] = r1; o.r[2] = r2; o.r[3] = r3;
     const double disc = p.disc[r];
-    mc[MC_ACC + 0] = cw_fma(disc, r0, mc[MC_ACC + 0]);
-    mc[MC_ACC + 1] = cw_fma(disc, r1, mc[MC_ACC + 1]);
-    mc[MC_ACC + 2] = cw_fma(disc, r2, mc[MC_ACC + 2]);
-    mc[MC_ACC + 3] = cw_fma(disc, r3, mc[MC_ACC + 3]);
+    mc[MC_ACC + 0] = cw_fma(disc, r0, mc[MC_ACC + 0]);  // the record holds V accumulators
+    if (V > 1) mc[MC_ACC + 1] = cw_fma(disc, r1, mc[MC_ACC + 1]);
+    if (V > 2) mc[MC_ACC + 2] = cw_fma(disc, r2, mc[MC_ACC + 2]);
+    if (V > 3) mc[MC_ACC + 3] = cw_fma(disc, r3, mc[MC_ACC + 3]);
   }
   // CheckTerminal of the new state (:266-285)
   if (a == 0 && !rules_only && (cw_hdr(p, r)[H_HORIZON] - 1 == 0 || oom || coll || goal)) cw_hstate(p, r)[HS_DONE] = 1;

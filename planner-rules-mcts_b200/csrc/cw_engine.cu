@@ -154,7 +154,7 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
     for (int ctas = shapes[sh][1]; ctas >= 1 && P == 0; --ctas) {
       const size_t budget = std::min<size_t>(smem_optin, static_cast<size_t>(smem_sm) / ctas - reserved - 256);
       for (int cand = 32; cand >= 1; --cand) {
-        const size_t wb = cw_pool_bytes(cand, A, M, R) + cw_sched_bytes(cand, A, M, R);
+        const size_t wb = cw_pool_bytes(cand, A, M, R, V) + cw_sched_bytes(cand, A, M, R);
         const size_t need = static_cast<size_t>(cap) + wb * n_warps;
         if (need <= budget) {
           // a pool whose agents fill whole rounds of 32 work items runs better than a slightly
@@ -162,7 +162,7 @@ int brm_cw_configure(brm_engine* e, const brm_cw_scenario* scenarios, int32_t n_
           // rounds beat 26 slots by 2 %)
           const int full = (cand * A / 32) * 32 / A;
           P = (full >= 1 && full * 10 >= cand * 9) ? full : cand;
-          warp_bytes = cw_pool_bytes(P, A, M, R) + cw_sched_bytes(P, A, M, R);
+          warp_bytes = cw_pool_bytes(P, A, M, R, V) + cw_sched_bytes(P, A, M, R);
           smem = static_cast<size_t>(cap) + warp_bytes * n_warps;
           threads = shapes[sh][0];
           break;

@@ -95,11 +95,8 @@ __device__ __forceinline__ bool cw_in_list2(uint8_t f, int j) {
 
 // agent j of `leaf`, projected and packed the way a pool slot holds it, into the warp's cache
 __device__ __forceinline__ void cw_cache_fill(const CwBlob& B, const CwStatesView& S, const CwPool& p,
-                                              double* cache_ag, uint32_t* cache_mc, int j, int64_t leaf) {
-  // build the records in a one-slot pool view that points at the cache
-  CwPool c = p;
-  c.ag = cache_ag;
-  c.P = 1;
+                                              double* cache_ag, uint32_t* cache_meta, uint32_t* cache_mc, int j,
+                                              int64_t leaf) {
   const double* src = S.agents + (static_cast<int64_t>(j) * S.n + leaf) * 4;
   CwKin t;
   t.x = src[0]; t.y = src[1]; t.th = src[2]; t.v = src[3];
@@ -118,10 +115,10 @@ __device__ __forceinline__ void cw_cache_fill(const CwBlob& B, const CwStatesVie
   bits |= cw_beyond_bit(B, f);
   double* rec = cache_ag + j * kAgWords;
   rec[AG_X] = t.x; rec[AG_Y] = t.y; rec[AG_TH] = t.th; rec[AG_V] = t.v; rec[AG_CS] = t.cs; rec[AG_SN] = t.sn;
-  rec[AG_S] = f.s; rec[AG_LAT] = f.lat;
+  rec[AG_S] = f.s; rec[AG_LAT] = f.lat; rec[AG_COST] = 0.0;
   CwMeta m;
-  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits; m._spare = 0;
-  *reinterpret_cast<CwMeta*>(rec + AG_META) = m;
+  m.lane = static_cast<int16_t>(f.lane); m.flags = fl; m.bits = bits;
+  *reinterpret_cast<CwMeta*>(cache_meta + j) = m;
   if (j < p.M) {
     uint32_t* w = cache_mc + j * (1 + p.QW);  // live, qw[QW]
     for (int k = 0; k < p.QW; ++k) w[1 + k] = 0u;
@@ -136,17 +133,17 @@ __device__ __forceinline__ void cw_cache_fill(const CwBlob& B, const CwStatesVie
 }
 
 // slot (r, j) from the cached leaf
-__device__ __forceinline__ void cw_init_from_cache(CwPool& p, const double* cache_ag, const uint32_t* cache_mc, int r,
-                                                   int j) {
+__device__ __forceinline__ void cw_init_from_cache(CwPool& p, const double* cache_ag, const uint32_t* cache_meta,
+                                                   const uint32_t* cache_mc, int r, int j) {
   const double* src = cache_ag + j * kAgWords;
   double* rec = cw_ag(p, cw_slot(p, r, j));
 #pragma unroll
   for (int k = 0; k < kAgWords; ++k) rec[k] = src[k];
+  p.meta[cw_slot(p, r, j)] = cache_meta[j];
   if (j < p.M) {
     const int sm = cw_mslot(p, r, j);
     double* mc = cw_mc(p, sm);
-#pragma unroll
-    for (int k = 0; k < MC_TAIL; ++k) mc[k] = 0.0;  // cost, acc, rng
+    for (int k = 0; k < p.V + 2; ++k) mc[k] = 0.0;  // acc, rng
     const uint32_t* w = cache_mc + j * (1 + p.QW);
     uint32_t* dst = cw_mc_live(p, sm);
     for (int k = 0; k < 1 + p.QW; ++k) dst[k] = w[k];
@@ -173,11 +170,12 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
   uint8_t* wmem = smem + args.blob_cap + static_cast<size_t>(wid) * args.warp_bytes;
   CwPool p;
   cw_pool_carve(p, wmem, P, A, M, R, V);
-  uint8_t* sp = wmem + cw_pool_bytes(P, A, M, R);
+  uint8_t* sp = wmem + cw_pool_bytes(P, A, M, R, V);
   double* fin_disc = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(P) * 8;
   int32_t* fin_rec = reinterpret_cast<int32_t*>(sp); sp += static_cast<size_t>(P) * 6 * 4;  // flat, leaf, k, horizon, nsteps, done
   // the leaf most rollouts of the warp's current chunk start from, ready to be copied into a slot
   double* cache_ag = reinterpret_cast<double*>(sp); sp += static_cast<size_t>(A) * kAgWords * 8;
+  uint32_t* cache_meta = reinterpret_cast<uint32_t*>(sp); sp += static_cast<size_t>(A) * 4;
   uint32_t* cache_mc = reinterpret_cast<uint32_t*>(sp); sp += static_cast<size_t>(M) * (1 + p.QW) * 4;
   uint16_t* list1 = reinterpret_cast<uint16_t*>(sp); sp += static_cast<size_t>(P) * A * 2;
   uint16_t* list2 = reinterpret_cast<uint16_t*>(sp); sp += static_cast<size_t>(P) * M * 2;
@@ -463,7 +461,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           if (new_leaf != cache_leaf && n_per_leaf >= 4) {  // more rollouts of this leaf will follow
             cache_leaf = new_leaf;
             __syncwarp();
-            for (int j = lane; j < A; j += 32) cw_cache_fill(B, view, p, cache_ag, cache_mc, j, new_leaf);
+            for (int j = lane; j < A; j += 32) cw_cache_fill(B, view, p, cache_ag, cache_meta, cache_mc, j, new_leaf);
           }
         }
       }
@@ -482,7 +480,7 @@ __global__ void __launch_bounds__(NT, CTAS) cw_pool_kernel(const CwArgs args) {
           if (rf & 2) {
             const int leaf = cw_hdr(p, r)[H_LEAF];
             if (leaf == cache_leaf)
-              cw_init_from_cache(p, cache_ag, cache_mc, r, j);
+              cw_init_from_cache(p, cache_ag, cache_meta, cache_mc, r, j);
             else
               cw_init_item(B, p, view, r, j, leaf);
             if (hs[HS_LIVE]) {

@@ -7,11 +7,11 @@
 namespace brm {
 
 // The two launch shapes of the continuous-world kernels (threads per CTA x resident CTAs per
-// SM).  Thirteen warps: what 65536 registers allow at the 151 the rollout kernel needs, and what
-// fits beside the blob with 24 slots per warp for four agents (measured: 288 / 320 / 352 / 384 /
-// 416 / 448 / 512 threads with the pool sizes they leave; throughput follows warps x slots)
+// SM).  Fourteen warps of 24 slots are what fits beside the blob for four agents at 616 bytes per
+// rollout (the kernel needs 128 registers: not the limit); measured 288 ... 512 threads with
+// the pool sizes they leave: throughput follows warps x slots
 #ifndef BRM_CW_THREADS_LARGE
-#define BRM_CW_THREADS_LARGE 416
+#define BRM_CW_THREADS_LARGE 448
 #endif
 constexpr int kCwThreadsLarge = BRM_CW_THREADS_LARGE;  // x 1
 constexpr int kCwThreadsSmall = 128;  // x 3
@@ -35,9 +35,9 @@ struct CwLaunchCtx {
 
 // bytes of the arrays that follow a warp's pool in shared memory (cw_pool_kernel): what a
 // finished rollout leaves behind for its finalisation (8 + 6 * 4 bytes) and the three item lists
-inline size_t cw_sched_bytes(int P, int A, int M, int R) {
+inline size_t cw_sched_bytes(int P, int A, int M, int R) {  // (does not depend on V)
   size_t b = static_cast<size_t>(P) * (8 + 6 * 4);
-  b += static_cast<size_t>(A) * kAgWords * 8 + static_cast<size_t>(M) * (1 + (R + 7) / 8) * 4;  // cached leaf
+  b += static_cast<size_t>(A) * (kAgWords * 8 + 4) + static_cast<size_t>(M) * (1 + (R + 7) / 8) * 4;  // cached leaf
   b = (b + 7) & ~static_cast<size_t>(7);
   b += static_cast<size_t>(P) * (2 * A + M) * 2;
   return (b + 15) & ~static_cast<size_t>(15);

@@ -31,7 +31,7 @@ struct Emul {
   bool setup(const brm_cw_scenario* scn, int P) {
     B = static_cast<CwBlob*>(aligned_alloc(16, sizeof(CwBlob)));
     if (!cw_build_blob(*scn, B, &R, &err)) return false;
-    const size_t bytes = cw_pool_bytes(P, B->A, B->M, R);
+    const size_t bytes = cw_pool_bytes(P, B->A, B->M, R, B->V);
     mem = aligned_alloc(16, bytes);
     memset(mem, 0xA5, bytes);  // stale contents must never matter
     cw_pool_carve(pool, mem, P, B->A, B->M, R, B->V);
