@@ -110,3 +110,27 @@ def test_cpp_host_tree_reproduces_the_threshold_suite(built, tmp_path, case):
     path.write_bytes(bytes(arr))
     rc, out = run(exe, str(path), case, "8", "16")
     assert rc == 0 and "expectations hold" in out, out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_others,expected", [(0, 1), (1, 4)])
+def test_cpp_host_tree_plans_in_the_continuous_world(built, tmp_path, n_others, expected):
+    """include/brm_mcts.hpp over brm::MvmctsState / brm::RulesMctsRolloutEvaluator: the decision of
+    BehaviorRulesMcts::Plan from C++ -- free road: accelerate (test/single_agent_test.cpp:248), a slower
+    agent 2 m in front: brake (:268); the same pins tests/test_planner_gpu.py holds for planner.py."""
+    from planner_rules_mcts_b200.ltl import RuleMonitor
+    exe = os.path.join(ROOT, "build", "planner_test")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "planner_test.cpp"), "-o", exe, "-L", PKG, "-lbrm",
+                    "-Wl,-rpath," + PKG], check=True)
+    prims = [(0.0, 0.0), (5.0, 0.0), (0.0, -1.0), (0.0, 1.0), (-3.0, 0.0)]   # :191-200
+    scn = scenarios.straight_road_test_world(
+        n_others=n_others, rel_distance=2.0 if n_others else 7.0, ego_velocity=5.0,
+        velocity_difference=2.0 if n_others else 0.0, primitives=prims, goal=(7.5, 12.5, -4.25, 0.75),
+        params=brm.RulesMctsStateParameters(GOAL_REWARD=100.0),
+        rules=[RuleMonitor.MakeRule("G !collision_ego", -1000.0, 0)])
+    (tmp_path / "scn.bin").write_bytes(bytes(scn.to_abi()))
+    (tmp_path / "state.bin").write_bytes(np.ascontiguousarray(scn.initial_state, np.float64).tobytes())
+    rc, out = run(exe, str(tmp_path / "scn.bin"), str(tmp_path / "state.bin"), str(expected), "1000", "8", "16")
+    assert rc == 0 and "expectations hold" in out, out
