@@ -37,6 +37,15 @@ def test_adapter_compiles_and_refuses_without_gpu(exe):
         assert "error code -2" in out and "no CPU fallback" in out
 
 
+@pytest.mark.parametrize("src", ["mcts_test.cpp", "planner_test.cpp", "comm_test.cpp"])
+def test_cpp_hosts_compile_and_link_against_the_abi(built, tmp_path, src):
+    """The C++ hosts of include/brm_mcts.hpp / brm_state.hpp build with warnings as errors and link
+    against libbrm.so -- on the CPU, so a broken header shows up before a GPU box is involved."""
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", src), "-o", str(tmp_path / "a.out"), "-L", PKG, "-lbrm",
+                    "-lpthread", "-Wl,-rpath," + PKG], check=True)
+
+
 @pytest.mark.gpu
 def test_adapter_gridworld_matches_python_mirror(exe, tmp_path):
     rules = brm.make_default_rules()
