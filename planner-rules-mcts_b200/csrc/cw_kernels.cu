@@ -625,7 +625,9 @@ int launch_config(brm_engine* e, const CwLaunchCtx& ctx, CwArgs& a, int64_t unit
               ctx.smem_bytes);
   int64_t grid = static_cast<int64_t>(e->sm_count) * per_sm;
   const int64_t per_cta = static_cast<int64_t>(ctx.P) * kWarps;
-  const int64_t need = a.single_scenario ? (units + per_cta - 1) / per_cta : units;
+  // CTAs that could all be busy at once: rollouts (states) over the slots of a CTA -- also when
+  // the CTAs walk over scenarios, where the CTAs without a leaf of their own join the others'
+  const int64_t need = (units + per_cta - 1) / per_cta;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   a.n_warps_total = static_cast<int32_t>(grid) * kWarps;
@@ -697,7 +699,7 @@ int cw_launch_rollout(brm_engine* e, const CwLaunchCtx& ctx, int n_scenarios, co
   a.work_counter = reinterpret_cast<unsigned long long*>(a.returns_fx + fx_count);
   a.leaf_next = reinterpret_cast<int32_t*>(a.work_counter + 1);
   e->time_begin();
-  rc = launch_mode<MODE_ROLLOUT>(e, ctx, a, a.single_scenario ? a.total : leaves.n);
+  rc = launch_mode<MODE_ROLLOUT>(e, ctx, a, a.total);
   if (rc != BRM_OK) return rc;
   cw_finalize_returns_kernel<<<static_cast<int>((fx_count + 255) / 256), 256, 0, e->stream>>>(
       a.returns_fx, out.returns_sum, static_cast<int64_t>(fx_count), M, V, rp.coop_factor);
