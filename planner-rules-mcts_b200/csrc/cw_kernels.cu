@@ -33,14 +33,14 @@ namespace brm {
 namespace {
 
 // The warps of a CTA own their pools, but they start the phases of an iteration together (ONE
-// barrier per iteration, in front of phase 1, per group of BRM_CW_SYNC_GROUP warps): twelve warps spread over all phases need the
-// whole loop (~70 KB of code) in the instruction cache at once (a quarter of all stall samples
-// were instruction fetches without it).  The warps have about the same number of work items per
-// phase (the refill rule), so they stay close until the next barrier; more barriers (one per
-// phase: -4 %) or fewer (every second iteration) measured worse; two groups of 7 + 6 warps with a
-// named barrier each beat one barrier for all 13 (+3.5 %: less waiting for the slowest warp) and
-// groups of 4 or 5.  The barrier doubles as the group's vote on whether anybody has work left: a
-// warp whose pool has run dry keeps attending until every warp of its group is done.
+// barrier per iteration, in front of phase 1, per group of BRM_CW_SYNC_GROUP warps): warps
+// spread over all phases need the whole loop (~70 KB of code) in the instruction cache at once
+// (a quarter of all stall samples were instruction fetches without it).  The warps have about
+// the same number of work items per phase (the refill rule), so they stay close until the next
+// barrier; more barriers (one per phase: -4 %) or fewer (every second iteration) measured worse;
+// two groups of warps with a named barrier each beat one barrier for all (+3.5 %: less waiting
+// for the slowest warp) and groups of 4 or 5.  The barrier doubles as the group's vote on whether
+// anybody has work left: a warp whose pool has run dry attends until its whole group is done.
 #ifndef BRM_CW_SYNC_GROUP
 #define BRM_CW_SYNC_GROUP 7
 #endif
