@@ -596,7 +596,7 @@ struct CwStatesView {
 
 // agent j of state `leaf` into slot (r, j): pose, lane projection, automaton states
 BRM_HD void cw_init_item(const CwBlob& B, CwPool& p, const CwStatesView& S, int r, int j, int64_t leaf) {
-  const int A = p.A, M = p.M, R = p.R;
+  const int M = p.M, R = p.R;
   const int s = cw_slot(p, r, j);
   const double* src = S.agents + (static_cast<int64_t>(j) * S.n + leaf) * 4;
   CwKin t;
@@ -692,7 +692,7 @@ BRM_HD uint32_t cw_pick_action(const CwBlob& B, CwPool& p, const CwStepCtx& c, i
 // Returns true when the drivable-area test could not be decided from the grid: the caller
 // then runs cw_exact_shape_item for this agent before phase 2.
 BRM_HD bool cw_phase1_item(const CwBlob& B, CwPool& p, const CwStepCtx& c, int r, int j) {
-  const int A = p.A, M = p.M;
+  const int M = p.M;
   const int s = cw_slot(p, r, j);
   double* rec = cw_ag(p, s);
   CwMeta* meta = cw_meta(p, s);
@@ -795,7 +795,7 @@ struct CwEval {
 // (:266-285) of the new state.  `rules_only`: MvmctsState::EvaluateRules() (:186-197) on the
 // state as it is.  Returns through `o`; accumulates disc * reward into the slot.
 BRM_HD void cw_phase2_item(const CwBlob& B, CwPool& p, int r, int a, bool rules_only, CwEval& o) {
-  const int A = p.A, M = p.M, V = p.V;
+  const int A = p.A, V = p.V;
   const int s = cw_slot(p, r, a), sm = cw_mslot(p, r, a);
   o.r[0] = o.r[1] = o.r[2] = o.r[3] = 0.0;
   o.w[0] = o.w[1] = o.w[2] = o.w[3] = 0u;
