@@ -37,6 +37,17 @@ def test_adapter_compiles_and_refuses_without_gpu(exe):
         assert "error code -2" in out and "no CPU fallback" in out
 
 
+def test_cpp_host_tree_logic_on_the_cpu(built, tmp_path):
+    """include/brm_mcts.hpp with a toy state and a toy evaluator (no engine): visit counts, virtual
+    loss, back-propagation, thresholded lexicographic order, batched evaluator calls, terminal root."""
+    exe = str(tmp_path / "mcts_logic_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "mcts_logic_test.cpp"), "-o", exe, "-L", PKG, "-lbrm",
+                    "-Wl,-rpath," + PKG], check=True)
+    rc, out = run(exe)
+    assert rc == 0 and "expectations hold" in out and "FAIL" not in out, out
+
+
 @pytest.mark.parametrize("src", ["mcts_test.cpp", "planner_test.cpp", "comm_test.cpp"])
 def test_cpp_hosts_compile_and_link_against_the_abi(built, tmp_path, src):
     """The C++ hosts of include/brm_mcts.hpp / brm_state.hpp build with warnings as errors and link
